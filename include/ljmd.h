@@ -1,0 +1,201 @@
+/*
+ * ljmd.h — C ABI of the B200-native Lennard-Jones MD step.
+ *
+ * This is the drop-in boundary for the hot path of vlvovch/lennard-jones-cuda
+ * (all citations are into /root/reference/src/library/):
+ *
+ *   - MDSystem.cpp:9-25 declares the `extern "C"` seam the reference host layer
+ *     links against (defined in MDSystem.cu:155-299).  Section B below exports
+ *     the same six symbols the host layer actually calls, so the UNMODIFIED
+ *     reference MDSystem.cpp (built with -DUSE_CUDA_TOOLKIT) links against this
+ *     library instead of MDSystem.cu.
+ *   - Section A is the device-resident handle API that the source-compatible
+ *     `MDSystem` class (lennard-jones-cuda_b200/host/MDSystem.h) is written on:
+ *     one call per MDSystem method on the hot path, state kept in HBM between
+ *     steps, error codes instead of exit(), optional sharding of the i-particles
+ *     over several GPUs (one process per GPU).
+ *
+ * Plain C: pointers, sizes, ints and doubles only.  Host arrays use the
+ * reference layout: AoS float[4*N], (x,y,z,w) per particle (MDSystem.h:72-74).
+ * No function here has a CPU fallback: without a CUDA device every call that
+ * needs one returns LJMD_ERR_CUDA.
+ */
+#ifndef LJMD_H
+#define LJMD_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ status */
+#define LJMD_OK 0
+#define LJMD_ERR_CUDA 1     /* a CUDA runtime call failed / no device          */
+#define LJMD_ERR_ARG 2      /* invalid argument                                */
+#define LJMD_ERR_NCCL 3     /* a NCCL call failed / built without NCCL         */
+#define LJMD_ERR_DOMAIN 4   /* input outside the documented domain             */
+
+/* Last error message of the calling thread ("" if none). */
+const char* ljmd_last_error(void);
+
+/* Boundary conditions: MDSystem.h:24-25. */
+#define LJMD_BC_PERIODIC 0
+#define LJMD_BC_HARDWALL 1
+#define LJMD_BC_NONE 2
+
+#define LJMD_RDF_BINS 256   /* MDSystem.cpp:97 */
+
+/* Indices into the scalar block returned by ljmd_get_scalars
+ * (public members of MDSystem, MDSystem.h:63-66,80,83,98-99). */
+enum {
+  LJMD_S_U = 0, LJMD_S_T, LJMD_S_K, LJMD_S_V, LJMD_S_P,
+  LJMD_S_PVIRIAL,      /* virial part of P before CalculateParameters (MDSystem.cpp:307) */
+  LJMD_S_TIME, LJMD_S_L,
+  LJMD_S_AV_U_TOT, LJMD_S_AV_T_TOT, LJMD_S_AV_P_TOT, LJMD_S_AV_ITERS,
+  LJMD_S_CHI,          /* last TVN rescale factor (MDSystem.cpp:499)             */
+  LJMD_S_TKIN_TRIAL,   /* last KineticTemperature(t_Vel) (MDSystem.cpp:498)      */
+  LJMD_S_COUNT = 16
+};
+
+typedef struct ljmd_system ljmd_system;
+
+/* ------------------------------------------------- A. device-resident API */
+
+/* Number of visible CUDA devices (0 when none / no driver). */
+int ljmd_device_count(void);
+
+/*
+ * Create a system of N particles at density rho in a cubic box of edge
+ * L = (N/rho)^(1/3) (MDSystem.cpp:70).  N, rho, T0, canonical, bc as in
+ * MDSystemConfiguration (MDSystem.h:10-41).  rdf_dr2: bin width in r^2
+ * (MDSystem.cpp:93-95; ljmd_rdf_dr2(N) restates that rule).
+ * Replaces: MDSystem::Reinitialize/ReallocateMemory device part (MDSystem.cpp:116-144).
+ */
+int ljmd_create(ljmd_system** out, int N, double rho, double T0, int canonical, int bc,
+                float rdf_dr2, int device);
+
+/*
+ * Same, as rank `rank` of `world` cooperating processes (one GPU each).  The
+ * i-particles are split in contiguous shards; every rank holds all positions.
+ * nccl_unique_id: the 128-byte ncclUniqueId produced by ljmd_nccl_unique_id on
+ * rank 0 and shipped to the others by the caller (torch.distributed, MPI, ...).
+ * New functionality: the reference is single-device.
+ */
+int ljmd_create_distributed(ljmd_system** out, int N, double rho, double T0, int canonical, int bc,
+                            float rdf_dr2, int device, int rank, int world,
+                            const void* nccl_unique_id);
+int ljmd_nccl_unique_id(void* out128);
+
+int ljmd_destroy(ljmd_system* s);
+
+/* MDSystem.cpp:93-95. */
+float ljmd_rdf_dr2(int N);
+
+/* Live switches the callers flip between steps (MDSystem.h:160-163,
+ * semiGCEfluctuations.cpp:58,66). */
+int ljmd_set_canonical(ljmd_system* s, int canonical);
+int ljmd_set_boundary(ljmd_system* s, int bc);
+int ljmd_set_T0(ljmd_system* s, double T0);
+
+/*
+ * Upload a snapshot (host AoS float[4N] each; all ranks pass the full arrays)
+ * and evaluate forces, V, virial, K, T, P, U on it; zero t and the av_*
+ * accumulators.  Equivalent to writing h_Pos/h_Vel and calling
+ * CalculateForces(); CalculateParameters(); resetAveraging()
+ * (MDSystem.cpp:232-235,325-359,701-705) — the tail of Reinitialize (:99-113).
+ * Coordinates may lie outside [0,L] (the minimum image handles any offset).
+ */
+int ljmd_set_state(ljmd_system* s, const float* pos4, const float* vel4);
+
+/* Upload only velocities (after a host-side rescale, MDSystem.cpp:375-404) and
+ * recompute K, T, P, U without touching the av_* accumulators or forces. */
+int ljmd_set_velocities(ljmd_system* s, const float* vel4);
+
+/* Download the current state into host AoS float[4N] arrays (any may be NULL).
+ * pos4.w keeps the uploaded w (L/150, MDSystem.cpp:168); force4.w = per-particle
+ * sum_j (r^-12 - r^-6) as on the reference GPU path (MDSystem.cu:52,135).
+ * Replaces copyArrayFromDevice (MDSystem.cu:199-210). */
+int ljmd_get_state(ljmd_system* s, float* pos4, float* vel4, float* force4);
+
+/*
+ * nsteps x MDSystem::Integrate(dt) (MDSystem.cpp:438-583): drift, force
+ * evaluation, EVN half-kick or TVN chi-rescale, boundary conditions,
+ * CalculateParameters, t += dt.  Everything stays on the device; returns after
+ * the last step completed.  rdf_every > 0: the RDF histogram is rebuilt on
+ * every rdf_every-th step of this call (and accumulated, see ljmd_get_rdf_accum);
+ * 0: no RDF work (ljmd_get_rdf evaluates it lazily when asked).
+ */
+int ljmd_step(ljmd_system* s, double dt, int nsteps, int rdf_every);
+
+/*
+ * The drop-in single step with HOST buffers: upload pos/vel, one Integrate(dt),
+ * download pos/vel (and forces when force4 != NULL).  This is what
+ * MDSystem::Integrate costs a caller that reads h_Pos/h_Vel after every step.
+ */
+int ljmd_integrate_host(ljmd_system* s, double dt, float* pos4, float* vel4, float* force4);
+
+/* Re-evaluate forces/V/virial (and parameters) at the current positions:
+ * MDSystem::CalculateForces + CalculateParameters without the av_* update. */
+int ljmd_compute_forces(ljmd_system* s, int with_rdf);
+
+/* out[LJMD_S_COUNT] doubles, see the enum above. */
+int ljmd_get_scalars(ljmd_system* s, double* out);
+
+/* MDSystem::resetAveraging (MDSystem.cpp:701-705). */
+int ljmd_reset_averaging(ljmd_system* s);
+
+/*
+ * RDF histogram of the most recent force evaluation, CPU-path semantics
+ * (MDSystem.cpp:279-285: bins in r^2, width rdf_dr2, pairs beyond bin 255
+ * dropped, every unordered pair counted twice).  Bit-exact with that path.
+ * Computed lazily from the saved evaluation positions if the last step did not
+ * build it.  out256: int32 as NdNdr2 (MDSystem.h:90).
+ */
+int ljmd_get_rdf(ljmd_system* s, int* out256);
+
+/* Sum of the histograms built by ljmd_step(..., rdf_every) since the last
+ * reset, and how many evaluations went in.  reset != 0 clears afterwards. */
+int ljmd_get_rdf_accum(ljmd_system* s, long long* out256, int* nsamples, int reset);
+
+/*
+ * Speed histogram counts (MDSystem.cpp:651-662,676-688):
+ * bin = (int)(sqrt(vx^2+vy^2+vz^2) / step), dropped when >= nbins.  Bit-exact.
+ */
+int ljmd_velocity_histogram(ljmd_system* s, double step, int nbins, int* out);
+
+/* Kernel launches issued by this handle so far (for bench.py's gpu_launches). */
+long long ljmd_launch_count(ljmd_system* s);
+
+/* Milliseconds the last ljmd_step spent in its force kernels / in total, from
+ * CUDA events on the handle's stream (0 when event timing is off). */
+int ljmd_set_event_timing(ljmd_system* s, int on);
+int ljmd_last_step_timing(ljmd_system* s, double* force_ms, double* total_ms, int* force_launches);
+
+/* Static facts for rooflines: out[0]=SM count, out[1]=i-tile size, out[2]=j-splits,
+ * out[3]=force CTAs per launch, out[4]=world size, out[5]=local particles. */
+int ljmd_get_launch_info(ljmd_system* s, int* out6);
+
+/* ------------------------------------------------- B. legacy seam ---------
+ * The six symbols MDSystem.cpp calls (MDSystem.cpp:9-25; definitions replaced:
+ * MDSystem.cu:167-173,181-184,199-216,230-291,294-297).  Same signatures, same
+ * ownership (opaque device float* owned by the caller, host_RDF holds 256 ints).
+ * Differences, all documented in INTEGRATION.md: RDF uses the CPU-path semantics
+ * above; failures print to stderr and leave outputs zeroed instead of exit().
+ */
+void allocateArray(float** dest, int number);
+void deleteArray(float* arr);
+void copyArrayToDevice(float* device, const float* host, int numBodies);
+void copyArrayFromDevice(float* host, const float* device, unsigned int pbo, int numBodies);
+void calculateNForces(float* Pos, float* Force, float* host_pressure, int numBodies, float host_L,
+                      int Lperiodic, int* host_RDF, float host_dr2, int p, int q);
+void threadExit(void);
+/* Declared by the reference host layer but never called (MDSystem.cpp:13,15,21-23). */
+void allocateNBodyArrays(float* vel[2], int numBodies);
+void deleteNBodyArrays(float* vel[2]);
+void registerGLBufferObject(unsigned int pbo);
+void unregisterGLBufferObject(unsigned int pbo);
+void threadSync(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LJMD_H */

@@ -1,0 +1,749 @@
+// Host side of the C ABI in include/ljmd.h: handle, launch logic, collectives.
+// Product code: no CPU fallback anywhere — every entry point needs a CUDA device.
+#include "../../include/ljmd.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#ifdef LJMD_WITH_NCCL
+#include <nccl.h>
+#endif
+
+#include "ljmd_force.cuh"
+#include "ljmd_step.cuh"
+
+using namespace ljmd;
+
+// ------------------------------------------------------------------------------------- errors
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+extern "C" const char* ljmd_last_error(void) { return g_err; }
+
+#define CU(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess)                                                                        \
+      return set_err(LJMD_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+#ifdef LJMD_WITH_NCCL
+#define NC(call)                                                                                  \
+  do {                                                                                            \
+    ncclResult_t r_ = (call);                                                                     \
+    if (r_ != ncclSuccess)                                                                        \
+      return set_err(LJMD_ERR_NCCL, "%s:%d %s -> %s", __FILE__, __LINE__, #call, ncclGetErrorString(r_)); \
+  } while (0)
+#endif
+
+// --------------------------------------------------------------------------------- the handle
+constexpr int kForceThreads = 128;
+constexpr int kITile = kForceThreads * kIPT;  // i-particles per CTA
+constexpr int kTileJ = 1024;                  // j-records per smem stage
+constexpr int kMinBlocks = 4;                 // resident CTAs/SM the non-RDF kernel is built for
+constexpr int kMinBlocksRdf = 3;
+
+struct ljmd_system {
+  int N = 0, bc = 0, canonical = 0;
+  double rho = 0., L = 0., T0 = 0.;
+  float dr2 = 0.1f;
+  int device = 0, rank = 0, world = 1;
+  int cnt = 0;      // shard capacity = ceil(N/world)
+  int i_begin = 0, i_end = 0, nloc = 0;
+  int npad = 0;     // world*cnt
+  int num_sms = 148;
+  int nsplit = 1, n_itiles = 1;
+  float thr1 = 0.f, thr2 = 0.f;
+  cudaStream_t stream = nullptr;
+  float4 *pos = nullptr, *posA = nullptr, *vel = nullptr, *force = nullptr, *tforce = nullptr, *fpart = nullptr;
+  float4* gath = nullptr;  // [npad] scratch for on-demand all-gathers of sharded arrays
+  uint4* upos = nullptr;
+  double *blockW = nullptr, *part = nullptr;
+  unsigned int* counter = nullptr;
+  unsigned int* velh = nullptr;
+  DevScalars* sc = nullptr;
+  DevScalars* h_sc = nullptr;  // pinned mirror
+  unsigned long long *rdf_cur = nullptr, *rdf_acc = nullptr;
+  unsigned long long* h_rdf = nullptr;  // pinned [256]
+  int rdf_valid = 0;  // rdf_cur matches the latest force evaluation
+  int rdf_nacc = 0;
+  long long launches = 0;
+  // event timing of the force kernel
+  int timing = 0;
+  std::vector<cudaEvent_t> ev;
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  double last_force_ms = 0., last_total_ms = 0.;
+  int last_force_launches = 0;
+#ifdef LJMD_WITH_NCCL
+  ncclComm_t comm = nullptr;
+#endif
+};
+
+// MDSystem.cpp:732-739 on the host, for the threshold bisection only.
+static int fast_round_host(float x) { return x > 0 ? (int)(x + 0.5f) : (int)(x - 0.5f); }
+
+// Smallest positive float d with fast_round((float)((double)d / L)) >= k.  The map is monotone
+// in d, so bisect over the (ordered) bit patterns of positive floats.
+static float image_threshold(double L, int k) {
+  uint32_t lo = 0u, hi = 0x7f7fffffu;  // fast_round(0)=0 < k ; FLT_MAX/L rounds huge
+  while (hi - lo > 1u) {
+    uint32_t mid = lo + (hi - lo) / 2u;
+    float d;
+    memcpy(&d, &mid, 4);
+    double q = (double)d / L;
+    float qf = (float)q;
+    int n = (qf < 1.0e9f) ? fast_round_host(qf) : 0x7fffffff;
+    if (n >= k) hi = mid; else lo = mid;
+  }
+  float d;
+  memcpy(&d, &hi, 4);
+  return d;
+}
+
+// j-split heuristic: balance n_itiles*S CTAs over the SMs while keeping chunks long enough to
+// amortise the per-CTA prologue/epilogue (DESIGN.md §grid sizing).
+static int choose_split(int n_itiles, int N, int num_sms, int nloc) {
+  const double ovh = 96.;  // per-CTA fixed cost in j-equivalents
+  int best = 1;
+  double best_cost = 1e300;
+  const int smax = std::max(1, std::min(N / 128, 4 * num_sms));
+  for (int s = 1; s <= smax; ++s) {
+    if ((double)s * nloc * 16. > 1.5e9) break;  // partial-force buffer cap
+    const double chunk = (double)N / s + ovh;
+    const double cost = ((double)n_itiles * s / num_sms) * chunk + chunk;  // balanced part + tail
+    if (cost < best_cost * 0.995) { best_cost = cost; best = s; }
+  }
+  return best;
+}
+
+static StepParams make_step_params(ljmd_system* s, double dt) {
+  StepParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = s->N; p.nloc = s->nloc; p.i_begin = s->i_begin; p.bc = s->bc;
+  p.nsplit = s->nsplit; p.ilocal_cap = s->cnt; p.nforce_blocks = s->n_itiles * s->nsplit; p.world = s->world;
+  p.dt = dt; p.dt2 = dt * dt; p.L = s->L; p.rho = s->rho; p.T0 = s->T0;
+  p.fix_scale = 4294967296.0 / s->L;
+  p.pos = s->pos; p.posA = s->posA; p.upos = s->upos; p.vel = s->vel; p.force = s->force; p.tforce = s->tforce;
+  p.fpart = s->fpart; p.blockW = s->blockW; p.part = s->part; p.counter = s->counter; p.sc = s->sc;
+  return p;
+}
+
+static int step_grid(const ljmd_system* s) { return (s->nloc + kStepThreads - 1) / kStepThreads; }
+
+template <bool PERIODIC, bool RDF>
+static cudaError_t launch_force_t(ljmd_system* s, const ForceParams& fp) {
+  constexpr int MINB = RDF ? kMinBlocksRdf : kMinBlocks;
+  auto kern = k_force<PERIODIC, RDF, kForceThreads, MINB>;
+  const size_t smem = force_smem_bytes(PERIODIC, RDF, kTileJ, kForceThreads);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  dim3 grid(s->n_itiles, s->nsplit);
+  kern<<<grid, kForceThreads, smem, s->stream>>>(fp);
+  return cudaGetLastError();
+}
+
+static int launch_force(ljmd_system* s, bool rdf) {
+  ForceParams fp;
+  memset(&fp, 0, sizeof(fp));
+  const bool periodic = (s->bc == LJMD_BC_PERIODIC);
+  fp.jrec = periodic ? s->upos : reinterpret_cast<const uint4*>(s->posA);
+  fp.posf = s->posA;
+  fp.fpart = s->fpart;
+  fp.blockW = s->blockW;
+  fp.rdf = s->rdf_cur;
+  fp.N = s->N; fp.i_begin = s->i_begin; fp.i_end = s->i_end; fp.ilocal_cap = s->cnt; fp.tile_j = kTileJ;
+  const double k2 = 4294967296.0 / s->L;
+  fp.c2 = periodic ? (float)(k2 * k2) : 1.f;
+  fp.fscale = periodic ? (float)(4.0 * s->L / 4294967296.0) : 4.f;
+  const double cut = (double)kRdfBins * (double)s->dr2 * 1.001;
+  fp.cut_fast = (float)(periodic ? cut * k2 * k2 : cut);
+  fp.L = s->L; fp.thr1 = s->thr1; fp.thr2 = s->thr2; fp.dr2 = s->dr2; fp.inv_dr2 = 1.0f / s->dr2;
+  if (rdf) CU(cudaMemsetAsync(s->rdf_cur, 0, kRdfBins * sizeof(unsigned long long), s->stream));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (s->timing) {
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, s->stream));
+  }
+  cudaError_t e;
+  if (periodic) e = rdf ? launch_force_t<true, true>(s, fp) : launch_force_t<true, false>(s, fp);
+  else e = rdf ? launch_force_t<false, true>(s, fp) : launch_force_t<false, false>(s, fp);
+  if (e != cudaSuccess) return set_err(LJMD_ERR_CUDA, "force kernel launch: %s", cudaGetErrorString(e));
+  if (s->timing) {
+    CU(cudaEventRecord(e1, s->stream));
+    s->ev.push_back(e0);
+    s->ev.push_back(e1);
+  }
+  s->launches += 1;
+  s->rdf_valid = rdf ? 1 : 0;
+  return LJMD_OK;
+}
+
+// ---- collectives (no-ops for world == 1) -------------------------------------------------------
+static int allgather_positions(ljmd_system* s) {
+#ifdef LJMD_WITH_NCCL
+  if (s->world > 1) {
+    const size_t bytes = (size_t)s->cnt * 16;
+    NC(ncclAllGather((const char*)s->posA + (size_t)s->rank * bytes, s->posA, bytes, ncclChar, s->comm, s->stream));
+    if (s->bc == LJMD_BC_PERIODIC)
+      NC(ncclAllGather((const char*)s->upos + (size_t)s->rank * bytes, s->upos, bytes, ncclChar, s->comm, s->stream));
+  }
+#endif
+  return LJMD_OK;
+}
+static int allreduce_sums(ljmd_system* s, int first, int count) {
+#ifdef LJMD_WITH_NCCL
+  if (s->world > 1) {
+    double* ptr = s->sc->sums + first;
+    NC(ncclAllReduce(ptr, ptr, count, ncclDouble, ncclSum, s->comm, s->stream));
+  }
+#endif
+  return LJMD_OK;
+}
+
+// force evaluation at posA/upos + gather in the given mode
+static int evaluate(ljmd_system* s, const StepParams& p, int mode, bool rdf, int accumulate) {
+  int rc = launch_force(s, rdf);
+  if (rc) return rc;
+  const int g = step_grid(s);
+  const int fin = (s->world == 1) ? 1 : 0;
+  if (mode == GATHER_EVAL) k_gather<GATHER_EVAL><<<g, kStepThreads, 0, s->stream>>>(p, fin, accumulate);
+  else if (mode == GATHER_EVN) k_gather<GATHER_EVN><<<g, kStepThreads, 0, s->stream>>>(p, fin, accumulate);
+  else k_gather<GATHER_TVN><<<g, kStepThreads, 0, s->stream>>>(p, fin, accumulate);
+  CU(cudaGetLastError());
+  s->launches += 1;
+  if (mode == GATHER_TVN) {
+    if ((rc = allreduce_sums(s, SUM_PE, 3))) return rc;  // PE, W, TV2
+    k_finish_tvn<<<g, kStepThreads, 0, s->stream>>>(p, fin);
+    CU(cudaGetLastError());
+    s->launches += 1;
+    if (s->world > 1) {
+      if ((rc = allreduce_sums(s, SUM_K, 1))) return rc;
+      k_params<<<1, 32, 0, s->stream>>>(p, accumulate);
+      CU(cudaGetLastError());
+      s->launches += 1;
+    }
+  } else if (s->world > 1) {
+    if ((rc = allreduce_sums(s, SUM_PE, SUM_COUNT))) return rc;
+    k_params<<<1, 32, 0, s->stream>>>(p, accumulate);
+    CU(cudaGetLastError());
+    s->launches += 1;
+  }
+  if (rdf && mode != GATHER_EVAL) {
+    k_rdf_accum<<<1, kRdfBins, 0, s->stream>>>(s->rdf_cur, s->rdf_acc);
+    CU(cudaGetLastError());
+    s->launches += 1;
+    s->rdf_nacc += 1;
+  }
+  return LJMD_OK;
+}
+
+static int one_step(ljmd_system* s, const StepParams& p, bool rdf) {
+  const int g = step_grid(s);
+  if (s->canonical) k_drift<true><<<g, kStepThreads, 0, s->stream>>>(p);
+  else k_drift<false><<<g, kStepThreads, 0, s->stream>>>(p);
+  CU(cudaGetLastError());
+  s->launches += 1;
+  int rc = allgather_positions(s);
+  if (rc) return rc;
+  return evaluate(s, p, s->canonical ? GATHER_TVN : GATHER_EVN, rdf, 1);
+}
+
+static int sync_scalars(ljmd_system* s) {
+  CU(cudaMemcpyAsync(s->h_sc, s->sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return LJMD_OK;
+}
+
+static void collect_timing(ljmd_system* s) {
+  s->last_force_ms = 0.;
+  s->last_force_launches = 0;
+  for (size_t k = 0; k + 1 < s->ev.size(); k += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s->ev[k], s->ev[k + 1]) == cudaSuccess) {
+      s->last_force_ms += ms;
+      s->last_force_launches += 1;
+    }
+    cudaEventDestroy(s->ev[k]);
+    cudaEventDestroy(s->ev[k + 1]);
+  }
+  s->ev.clear();
+}
+
+// ------------------------------------------------------------------------------------ C ABI: A
+extern "C" int ljmd_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+extern "C" float ljmd_rdf_dr2(int N) {
+  float dr2 = (float)std::max(0.2 * sqrt(100. / N), 0.05);   // MDSystem.cpp:93
+  if (250 * dr2 < 25.0) dr2 = (float)(25.0 / 250);            // :94-95
+  return dr2;
+}
+
+extern "C" int ljmd_nccl_unique_id(void* out128) {
+#ifdef LJMD_WITH_NCCL
+  ncclUniqueId id;
+  NC(ncclGetUniqueId(&id));
+  static_assert(sizeof(id) == 128, "ncclUniqueId size");
+  memcpy(out128, &id, 128);
+  return LJMD_OK;
+#else
+  (void)out128;
+  return set_err(LJMD_ERR_NCCL, "library built without NCCL");
+#endif
+}
+
+static int destroy_impl(ljmd_system* s) {
+  if (!s) return LJMD_OK;
+  cudaSetDevice(s->device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+#ifdef LJMD_WITH_NCCL
+  if (s->comm) ncclCommDestroy(s->comm);
+#endif
+  cudaFree(s->pos); cudaFree(s->posA); cudaFree(s->vel); cudaFree(s->force); cudaFree(s->tforce);
+  cudaFree(s->fpart); cudaFree(s->gath); cudaFree(s->upos); cudaFree(s->blockW); cudaFree(s->part);
+  cudaFree(s->counter); cudaFree(s->velh); cudaFree(s->sc); cudaFree(s->rdf_cur); cudaFree(s->rdf_acc);
+  cudaFreeHost(s->h_sc); cudaFreeHost(s->h_rdf);
+  for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
+  if (s->ev_begin) cudaEventDestroy(s->ev_begin);
+  if (s->ev_end) cudaEventDestroy(s->ev_end);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+  return LJMD_OK;
+}
+
+static int create_impl(ljmd_system** out, int N, double rho_or_negL, double T0, int canonical, int bc, float rdf_dr2,
+                       int device, int rank, int world, const void* uid) {
+  if (!out) return set_err(LJMD_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (N < 2) return set_err(LJMD_ERR_ARG, "N must be >= 2 (got %d)", N);
+  if (bc < 0 || bc > 2) return set_err(LJMD_ERR_ARG, "boundary condition must be 0, 1 or 2 (got %d)", bc);
+  if (world < 1 || rank < 0 || rank >= world) return set_err(LJMD_ERR_ARG, "bad rank/world %d/%d", rank, world);
+  if (!(rdf_dr2 > 0.f)) return set_err(LJMD_ERR_ARG, "rdf_dr2 must be positive");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return set_err(LJMD_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  }
+  if (device < 0 || device >= ndev) return set_err(LJMD_ERR_ARG, "device %d out of range (%d visible)", device, ndev);
+  CU(cudaSetDevice(device));
+  ljmd_system* s = new (std::nothrow) ljmd_system();
+  if (!s) return set_err(LJMD_ERR_ARG, "out of host memory");
+  s->N = N; s->bc = bc; s->canonical = canonical ? 1 : 0; s->T0 = T0; s->dr2 = rdf_dr2;
+  s->device = device; s->rank = rank; s->world = world;
+  if (rho_or_negL > 0.) { s->rho = rho_or_negL; s->L = pow(N / s->rho, 1. / 3.); }   // MDSystem.cpp:70
+  else { s->L = -rho_or_negL; s->rho = N / (s->L * s->L * s->L); }
+  s->cnt = (N + world - 1) / world;
+  s->npad = s->cnt * world;
+  s->i_begin = std::min(N, rank * s->cnt);
+  s->i_end = std::min(N, (rank + 1) * s->cnt);
+  s->nloc = s->i_end - s->i_begin;
+  if (s->nloc < 1) { delete s; return set_err(LJMD_ERR_ARG, "rank %d of %d has no particles for N=%d", rank, world, N); }
+  cudaDeviceProp prop;
+  cudaError_t pe = cudaGetDeviceProperties(&prop, device);
+  if (pe != cudaSuccess) { delete s; return set_err(LJMD_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(pe)); }
+  if (prop.major < 10) {
+    delete s;
+    return set_err(LJMD_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                   prop.minor);
+  }
+  s->num_sms = prop.multiProcessorCount;
+  s->n_itiles = (s->nloc + kITile - 1) / kITile;
+  s->nsplit = choose_split(s->n_itiles, N, s->num_sms, s->cnt);
+  s->thr1 = image_threshold(s->L, 1);
+  s->thr2 = image_threshold(s->L, 2);
+
+#define CUC(call)                                                                                       \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess) {                                                                            \
+      set_err(LJMD_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));     \
+      destroy_impl(s);                                                                                  \
+      return LJMD_ERR_CUDA;                                                                             \
+    }                                                                                                   \
+  } while (0)
+  CUC(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  const size_t b16 = 16;
+  CUC(cudaMalloc(&s->pos, (size_t)s->cnt * b16));
+  CUC(cudaMalloc(&s->posA, (size_t)s->npad * b16));
+  CUC(cudaMalloc(&s->upos, (size_t)s->npad * b16));
+  CUC(cudaMalloc(&s->gath, (size_t)s->npad * b16));
+  CUC(cudaMalloc(&s->vel, (size_t)s->cnt * b16));
+  CUC(cudaMalloc(&s->force, (size_t)s->cnt * b16));
+  CUC(cudaMalloc(&s->tforce, (size_t)s->cnt * b16));
+  CUC(cudaMalloc(&s->fpart, (size_t)s->nsplit * s->cnt * b16));
+  CUC(cudaMalloc(&s->blockW, (size_t)s->n_itiles * s->nsplit * sizeof(double)));
+  CUC(cudaMalloc(&s->part, (size_t)2 * (step_grid(s) + 1) * sizeof(double)));
+  CUC(cudaMalloc(&s->counter, sizeof(unsigned int)));
+  CUC(cudaMalloc(&s->velh, 65536 * sizeof(unsigned int)));
+  CUC(cudaMalloc(&s->sc, sizeof(DevScalars)));
+  CUC(cudaMalloc(&s->rdf_cur, kRdfBins * sizeof(unsigned long long)));
+  CUC(cudaMalloc(&s->rdf_acc, kRdfBins * sizeof(unsigned long long)));
+  CUC(cudaMallocHost(&s->h_sc, sizeof(DevScalars)));
+  CUC(cudaMallocHost(&s->h_rdf, kRdfBins * sizeof(unsigned long long)));
+  CUC(cudaMemsetAsync(s->posA, 0, (size_t)s->npad * b16, s->stream));
+  CUC(cudaMemsetAsync(s->upos, 0, (size_t)s->npad * b16, s->stream));
+  CUC(cudaMemsetAsync(s->pos, 0, (size_t)s->cnt * b16, s->stream));
+  CUC(cudaMemsetAsync(s->vel, 0, (size_t)s->cnt * b16, s->stream));
+  CUC(cudaMemsetAsync(s->force, 0, (size_t)s->cnt * b16, s->stream));
+  CUC(cudaMemsetAsync(s->tforce, 0, (size_t)s->cnt * b16, s->stream));
+  CUC(cudaMemsetAsync(s->counter, 0, sizeof(unsigned int), s->stream));
+  CUC(cudaMemsetAsync(s->sc, 0, sizeof(DevScalars), s->stream));
+  CUC(cudaMemsetAsync(s->rdf_cur, 0, kRdfBins * sizeof(unsigned long long), s->stream));
+  CUC(cudaMemsetAsync(s->rdf_acc, 0, kRdfBins * sizeof(unsigned long long), s->stream));
+  CUC(cudaEventCreate(&s->ev_begin));
+  CUC(cudaEventCreate(&s->ev_end));
+  CUC(cudaStreamSynchronize(s->stream));
+  memset(s->h_sc, 0, sizeof(DevScalars));
+#undef CUC
+  if (world > 1) {
+#ifdef LJMD_WITH_NCCL
+    if (!uid) { destroy_impl(s); return set_err(LJMD_ERR_ARG, "nccl_unique_id is NULL"); }
+    ncclUniqueId id;
+    memcpy(&id, uid, 128);
+    ncclResult_t r = ncclCommInitRank(&s->comm, world, id, rank);
+    if (r != ncclSuccess) {
+      set_err(LJMD_ERR_NCCL, "ncclCommInitRank: %s", ncclGetErrorString(r));
+      s->comm = nullptr;
+      destroy_impl(s);
+      return LJMD_ERR_NCCL;
+    }
+#else
+    destroy_impl(s);
+    return set_err(LJMD_ERR_NCCL, "library built without NCCL; world must be 1");
+#endif
+  }
+  *out = s;
+  return LJMD_OK;
+}
+
+extern "C" int ljmd_create(ljmd_system** out, int N, double rho, double T0, int canonical, int bc, float rdf_dr2,
+                           int device) {
+  if (!(rho > 0.)) return set_err(LJMD_ERR_ARG, "rho must be positive");
+  return create_impl(out, N, rho, T0, canonical, bc, rdf_dr2, device, 0, 1, nullptr);
+}
+extern "C" int ljmd_create_distributed(ljmd_system** out, int N, double rho, double T0, int canonical, int bc,
+                                       float rdf_dr2, int device, int rank, int world, const void* uid) {
+  if (!(rho > 0.)) return set_err(LJMD_ERR_ARG, "rho must be positive");
+  return create_impl(out, N, rho, T0, canonical, bc, rdf_dr2, device, rank, world, uid);
+}
+// Internal (legacy seam): explicit box edge instead of density.
+int ljmd_create_with_L(ljmd_system** out, int N, double L, int bc, float rdf_dr2, int device) {
+  if (!(L > 0.)) return set_err(LJMD_ERR_ARG, "L must be positive");
+  return create_impl(out, N, -L, 1.0, 0, bc, rdf_dr2, device, 0, 1, nullptr);
+}
+
+extern "C" int ljmd_destroy(ljmd_system* s) { return destroy_impl(s); }
+
+#define CHECK_S(s)                                              \
+  do {                                                          \
+    if (!(s)) return set_err(LJMD_ERR_ARG, "system is NULL");   \
+    CU(cudaSetDevice((s)->device));                             \
+  } while (0)
+
+extern "C" int ljmd_set_canonical(ljmd_system* s, int canonical) {
+  CHECK_S(s);
+  s->canonical = canonical ? 1 : 0;
+  return LJMD_OK;
+}
+extern "C" int ljmd_set_T0(ljmd_system* s, double T0) {
+  CHECK_S(s);
+  if (!(T0 > 0.)) return set_err(LJMD_ERR_ARG, "T0 must be positive");
+  s->T0 = T0;
+  return LJMD_OK;
+}
+extern "C" int ljmd_set_boundary(ljmd_system* s, int bc) {
+  CHECK_S(s);
+  if (bc < 0 || bc > 2) return set_err(LJMD_ERR_ARG, "boundary condition must be 0, 1 or 2 (got %d)", bc);
+  if (bc != s->bc) {
+    s->bc = bc;
+    s->rdf_valid = 0;
+    // Re-anchor the evaluation positions on what the caller sees (the wrapped positions) and,
+    // for a periodic box, rebuild the fixed-point records the other modes do not maintain.
+    StepParams p = make_step_params(s, 0.);
+    k_prepare<<<step_grid(s), kStepThreads, 0, s->stream>>>(p);
+    CU(cudaGetLastError());
+    s->launches += 1;
+    int rc = allgather_positions(s);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+  }
+  return LJMD_OK;
+}
+
+static int check_domain(const ljmd_system* s, const float* pos4) {
+  for (int i = 0; i < s->N; ++i)
+    for (int k = 0; k < 3; ++k) {
+      const float x = pos4[4 * (size_t)i + k];
+      if (!(fabsf(x) <= 3.0e38f))
+        return set_err(LJMD_ERR_DOMAIN, "particle %d coordinate %d is not finite", i, k);
+    }
+  return LJMD_OK;
+}
+
+static int upload_state(ljmd_system* s, const float* pos4, const float* vel4) {
+  const size_t off = (size_t)s->i_begin * 4;
+  if (pos4) CU(cudaMemcpyAsync(s->pos, pos4 + off, (size_t)s->nloc * 16, cudaMemcpyHostToDevice, s->stream));
+  if (vel4) CU(cudaMemcpyAsync(s->vel, vel4 + off, (size_t)s->nloc * 16, cudaMemcpyHostToDevice, s->stream));
+  return LJMD_OK;
+}
+
+extern "C" int ljmd_set_state(ljmd_system* s, const float* pos4, const float* vel4) {
+  CHECK_S(s);
+  if (!pos4 || !vel4) return set_err(LJMD_ERR_ARG, "pos4/vel4 must not be NULL");
+  int rc = check_domain(s, pos4);
+  if (rc) return rc;
+  if ((rc = upload_state(s, pos4, vel4))) return rc;
+  StepParams p = make_step_params(s, 0.);
+  k_prepare<<<step_grid(s), kStepThreads, 0, s->stream>>>(p);
+  CU(cudaGetLastError());
+  s->launches += 1;
+  if ((rc = allgather_positions(s))) return rc;
+  CU(cudaMemsetAsync(s->sc, 0, sizeof(DevScalars), s->stream));  // t = 0, av_* = 0
+  if ((rc = evaluate(s, p, GATHER_EVAL, false, 0))) return rc;
+  s->rdf_nacc = 0;
+  CU(cudaMemsetAsync(s->rdf_acc, 0, kRdfBins * sizeof(unsigned long long), s->stream));
+  return sync_scalars(s);
+}
+
+extern "C" int ljmd_set_velocities(ljmd_system* s, const float* vel4) {
+  CHECK_S(s);
+  if (!vel4) return set_err(LJMD_ERR_ARG, "vel4 must not be NULL");
+  int rc = upload_state(s, nullptr, vel4);
+  if (rc) return rc;
+  StepParams p = make_step_params(s, 0.);
+  k_kinetic<<<step_grid(s), kStepThreads, 0, s->stream>>>(p);
+  CU(cudaGetLastError());
+  if ((rc = allreduce_sums(s, SUM_K, 1))) return rc;
+  k_params<<<1, 32, 0, s->stream>>>(p, 0);
+  CU(cudaGetLastError());
+  s->launches += 2;
+  return sync_scalars(s);
+}
+
+// full-length copy of a sharded array into host memory
+static int download_sharded(ljmd_system* s, const float4* dev_local, float* host4) {
+  if (s->world == 1) {
+    CU(cudaMemcpyAsync(host4, dev_local, (size_t)s->N * 16, cudaMemcpyDeviceToHost, s->stream));
+    return LJMD_OK;
+  }
+#ifdef LJMD_WITH_NCCL
+  const size_t bytes = (size_t)s->cnt * 16;
+  CU(cudaMemcpyAsync((char*)s->gath + (size_t)s->rank * bytes, dev_local, (size_t)s->nloc * 16,
+                     cudaMemcpyDeviceToDevice, s->stream));
+  NC(ncclAllGather((const char*)s->gath + (size_t)s->rank * bytes, s->gath, bytes, ncclChar, s->comm, s->stream));
+  CU(cudaMemcpyAsync(host4, s->gath, (size_t)s->N * 16, cudaMemcpyDeviceToHost, s->stream));
+  return LJMD_OK;
+#else
+  return set_err(LJMD_ERR_NCCL, "built without NCCL");
+#endif
+}
+
+extern "C" int ljmd_get_state(ljmd_system* s, float* pos4, float* vel4, float* force4) {
+  CHECK_S(s);
+  int rc;
+  if (pos4 && (rc = download_sharded(s, s->pos, pos4))) return rc;
+  if (vel4 && (rc = download_sharded(s, s->vel, vel4))) return rc;
+  if (force4 && (rc = download_sharded(s, s->force, force4))) return rc;
+  CU(cudaStreamSynchronize(s->stream));
+  return LJMD_OK;
+}
+
+extern "C" int ljmd_step(ljmd_system* s, double dt, int nsteps, int rdf_every) {
+  CHECK_S(s);
+  if (nsteps < 0) return set_err(LJMD_ERR_ARG, "nsteps must be >= 0");
+  StepParams p = make_step_params(s, dt);
+  if (s->timing) CU(cudaEventRecord(s->ev_begin, s->stream));
+  for (int k = 0; k < nsteps; ++k) {
+    const bool rdf = rdf_every > 0 && ((k + 1) % rdf_every == 0);
+    int rc = one_step(s, p, rdf);
+    if (rc) return rc;
+  }
+  if (s->timing) CU(cudaEventRecord(s->ev_end, s->stream));
+  int rc = sync_scalars(s);
+  if (rc) return rc;
+  if (s->timing) {
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, s->ev_begin, s->ev_end));
+    s->last_total_ms = ms;
+    collect_timing(s);
+  }
+  return LJMD_OK;
+}
+
+extern "C" int ljmd_integrate_host(ljmd_system* s, double dt, float* pos4, float* vel4, float* force4) {
+  CHECK_S(s);
+  if (!pos4 || !vel4) return set_err(LJMD_ERR_ARG, "pos4/vel4 must not be NULL");
+  int rc = upload_state(s, pos4, vel4);
+  if (rc) return rc;
+  StepParams p = make_step_params(s, dt);
+  if ((rc = one_step(s, p, false))) return rc;
+  if ((rc = download_sharded(s, s->pos, pos4))) return rc;
+  if ((rc = download_sharded(s, s->vel, vel4))) return rc;
+  if (force4 && (rc = download_sharded(s, s->force, force4))) return rc;
+  rc = sync_scalars(s);
+  if (s->timing) collect_timing(s);
+  return rc;
+}
+
+extern "C" int ljmd_compute_forces(ljmd_system* s, int with_rdf) {
+  CHECK_S(s);
+  // positions the caller sees are the wrapped ones: evaluate there (CalculateForces reads h_Pos)
+  StepParams p = make_step_params(s, 0.);
+  k_prepare<<<step_grid(s), kStepThreads, 0, s->stream>>>(p);
+  CU(cudaGetLastError());
+  s->launches += 1;
+  int rc = allgather_positions(s);
+  if (rc) return rc;
+  if ((rc = evaluate(s, p, GATHER_EVAL, with_rdf != 0, 0))) return rc;
+  rc = sync_scalars(s);
+  if (s->timing) collect_timing(s);
+  return rc;
+}
+
+extern "C" int ljmd_get_scalars(ljmd_system* s, double* out) {
+  CHECK_S(s);
+  if (!out) return set_err(LJMD_ERR_ARG, "out is NULL");
+  const DevScalars& h = *s->h_sc;
+  for (int k = 0; k < LJMD_S_COUNT; ++k) out[k] = 0.;
+  out[LJMD_S_U] = h.U; out[LJMD_S_T] = h.T; out[LJMD_S_K] = h.K; out[LJMD_S_V] = h.V; out[LJMD_S_P] = h.P;
+  out[LJMD_S_PVIRIAL] = h.Pvirial; out[LJMD_S_TIME] = h.t; out[LJMD_S_L] = s->L;
+  out[LJMD_S_AV_U_TOT] = h.av_U_tot; out[LJMD_S_AV_T_TOT] = h.av_T_tot; out[LJMD_S_AV_P_TOT] = h.av_p_tot;
+  out[LJMD_S_AV_ITERS] = (double)h.av_iters; out[LJMD_S_CHI] = h.chi; out[LJMD_S_TKIN_TRIAL] = h.Tkin_trial;
+  return LJMD_OK;
+}
+
+extern "C" int ljmd_reset_averaging(ljmd_system* s) {
+  CHECK_S(s);
+  DevScalars z;
+  memset(&z, 0, sizeof(z));
+  const size_t off = offsetof(DevScalars, av_U_tot);
+  const size_t len = offsetof(DevScalars, chi) - off;
+  CU(cudaMemsetAsync((char*)s->sc + off, 0, len, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  s->h_sc->av_U_tot = s->h_sc->av_T_tot = s->h_sc->av_p_tot = 0.;
+  s->h_sc->av_iters = 0;
+  return LJMD_OK;
+}
+
+static int fetch_rdf(ljmd_system* s, const unsigned long long* dev, unsigned long long* host256) {
+#ifdef LJMD_WITH_NCCL
+  if (s->world > 1) {
+    unsigned long long* tmp = reinterpret_cast<unsigned long long*>(s->gath);
+    CU(cudaMemcpyAsync(tmp, dev, kRdfBins * 8, cudaMemcpyDeviceToDevice, s->stream));
+    NC(ncclAllReduce(tmp, tmp, kRdfBins, ncclUint64, ncclSum, s->comm, s->stream));
+    dev = tmp;
+  }
+#endif
+  CU(cudaMemcpyAsync(host256, dev, kRdfBins * 8, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return LJMD_OK;
+}
+
+extern "C" int ljmd_get_rdf(ljmd_system* s, int* out256) {
+  CHECK_S(s);
+  if (!out256) return set_err(LJMD_ERR_ARG, "out256 is NULL");
+  int rc;
+  if (!s->rdf_valid) {
+    // lazy: rebuild from the saved evaluation positions (posA/upos); forces are recomputed into
+    // scratch (fpart/blockW) and discarded, the gathered force array is untouched.
+    if ((rc = launch_force(s, true))) return rc;
+  }
+  if ((rc = fetch_rdf(s, s->rdf_cur, s->h_rdf))) return rc;
+  for (int k = 0; k < kRdfBins; ++k) out256[k] = (int)s->h_rdf[k];
+  return LJMD_OK;
+}
+
+extern "C" int ljmd_get_rdf_accum(ljmd_system* s, long long* out256, int* nsamples, int reset) {
+  CHECK_S(s);
+  if (!out256) return set_err(LJMD_ERR_ARG, "out256 is NULL");
+  int rc = fetch_rdf(s, s->rdf_acc, s->h_rdf);
+  if (rc) return rc;
+  for (int k = 0; k < kRdfBins; ++k) out256[k] = (long long)s->h_rdf[k];
+  if (nsamples) *nsamples = s->rdf_nacc;
+  if (reset) {
+    CU(cudaMemsetAsync(s->rdf_acc, 0, kRdfBins * 8, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    s->rdf_nacc = 0;
+  }
+  return LJMD_OK;
+}
+
+extern "C" int ljmd_velocity_histogram(ljmd_system* s, double step, int nbins, int* out) {
+  CHECK_S(s);
+  if (!out || nbins < 1 || nbins > 65536 / 2 || !(step > 0.)) return set_err(LJMD_ERR_ARG, "bad histogram arguments");
+  CU(cudaMemsetAsync(s->velh, 0, (size_t)nbins * 4, s->stream));
+  const int g = std::min(step_grid(s), 4 * s->num_sms);
+  k_velhist<<<g, kStepThreads, (size_t)nbins * 4, s->stream>>>(s->vel, s->nloc, step, nbins, s->velh);
+  CU(cudaGetLastError());
+  s->launches += 1;
+#ifdef LJMD_WITH_NCCL
+  if (s->world > 1) NC(ncclAllReduce(s->velh, s->velh, nbins, ncclUint32, ncclSum, s->comm, s->stream));
+#endif
+  std::vector<unsigned int> h((size_t)nbins);
+  CU(cudaMemcpyAsync(h.data(), s->velh, (size_t)nbins * 4, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  for (int k = 0; k < nbins; ++k) out[k] = (int)h[k];
+  return LJMD_OK;
+}
+
+extern "C" long long ljmd_launch_count(ljmd_system* s) { return s ? s->launches : 0; }
+
+extern "C" int ljmd_set_event_timing(ljmd_system* s, int on) {
+  CHECK_S(s);
+  s->timing = on ? 1 : 0;
+  return LJMD_OK;
+}
+extern "C" int ljmd_last_step_timing(ljmd_system* s, double* force_ms, double* total_ms, int* force_launches) {
+  CHECK_S(s);
+  if (force_ms) *force_ms = s->last_force_ms;
+  if (total_ms) *total_ms = s->last_total_ms;
+  if (force_launches) *force_launches = s->last_force_launches;
+  return LJMD_OK;
+}
+extern "C" int ljmd_get_launch_info(ljmd_system* s, int* out6) {
+  CHECK_S(s);
+  if (!out6) return set_err(LJMD_ERR_ARG, "out6 is NULL");
+  out6[0] = s->num_sms; out6[1] = kITile; out6[2] = s->nsplit; out6[3] = s->n_itiles * s->nsplit;
+  out6[4] = s->world; out6[5] = s->nloc;
+  return LJMD_OK;
+}
+
+// ------------------------------------------------------------------------------------ C ABI: B
+// Worker for the legacy seam (ljmd_legacy.cu): forces on caller-owned device arrays.
+int ljmd_legacy_forces(ljmd_system* s, const float* d_pos, float* d_force, float* pressure, int* rdf256) {
+  CHECK_S(s);
+  CU(cudaMemcpyAsync(s->pos, d_pos, (size_t)s->N * 16, cudaMemcpyDeviceToDevice, s->stream));
+  StepParams p = make_step_params(s, 0.);
+  k_prepare<<<step_grid(s), kStepThreads, 0, s->stream>>>(p);
+  CU(cudaGetLastError());
+  s->launches += 1;
+  int rc = evaluate(s, p, GATHER_EVAL, rdf256 != nullptr, 0);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(d_force, s->force, (size_t)s->N * 16, cudaMemcpyDeviceToDevice, s->stream));
+  if ((rc = sync_scalars(s))) return rc;
+  if (pressure) *pressure = (float)s->h_sc->Pvirial;
+  if (rdf256) {
+    if ((rc = fetch_rdf(s, s->rdf_cur, s->h_rdf))) return rc;
+    for (int k = 0; k < kRdfBins; ++k) rdf256[k] = (int)s->h_rdf[k];
+  }
+  return LJMD_OK;
+}

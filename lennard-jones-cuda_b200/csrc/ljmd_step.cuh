@@ -1,0 +1,322 @@
+// O(N) kernels of the MD step: drift, gather (+EVN finish), TVN finish, parameters,
+// velocity histogram, fixed-point conversion.  All HBM-bound; float4 AoS, one thread per
+// particle, coalesced 16-byte accesses.
+//
+// Arithmetic follows /root/reference/src/library/MDSystem.cpp literally where the reference
+// evaluates in double and stores to float (drift :447-449/:473-475, kicks :451-453,:460-462,
+// TVN :477-505, boundaries :414-435, parameters :325-359), using explicit round-to-nearest
+// intrinsics so nvcc cannot contract a*b+c into an FMA the CPU build (-ffp-contract=off)
+// does not have.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ljmd {
+
+constexpr int kStepThreads = 256;
+
+enum { SUM_PE = 0, SUM_W = 1, SUM_TV2 = 2, SUM_K = 3, SUM_COUNT = 4 };
+
+// Device-resident scalar block (mirrors the public members of MDSystem, MDSystem.h:63-66,80,98-99).
+struct DevScalars {
+  double U, T, K, V, P, Pvirial, t;
+  double av_U_tot, av_T_tot, av_p_tot;
+  long long av_iters;
+  double chi, Tkin_trial;
+  double sums[SUM_COUNT];  // raw sums of the current step (local, then all-reduced in place)
+};
+
+struct StepParams {
+  int N;            // all particles
+  int nloc;         // particles of this rank
+  int i_begin;      // first global index of this rank
+  int bc;           // 0 periodic, 1 hard wall, 2 none
+  int nsplit;       // rows of fpart
+  int ilocal_cap;   // row stride of fpart
+  int nforce_blocks;  // entries of blockW
+  int world;        // number of ranks
+  double dt, dt2;   // dt, dt*dt
+  double L;         // box edge
+  double rho;       // N / rho is the volume the reference divides by (MDSystem.cpp:350)
+  double T0;
+  double fix_scale;  // 2^32 / L
+  float4* pos;      // [nloc]   wrapped positions (what h_Pos shows after Integrate)
+  float4* posA;     // [Npad]   positions at force-evaluation time (all ranks' shards)
+  uint4* upos;      // [Npad]   fixed-point box fractions of posA (periodic)
+  float4* vel;      // [nloc]
+  float4* force;    // [nloc]   f(t) (xyz), w = per-particle sum_j(r^-12 - r^-6)
+  float4* tforce;   // [nloc]   TVN t_Force
+  const float4* fpart;   // [nsplit][ilocal_cap]
+  const double* blockW;  // [nforce_blocks]
+  double* part;     // [2][gridDim.x] per-block partial sums
+  unsigned int* counter;  // last-block ticket
+  DevScalars* sc;
+};
+
+__device__ __forceinline__ uint32_t to_fixed(float x, double fix_scale) {
+  // box fraction in 32-bit fixed point; the cast to 32 bits is the periodic wrap
+  return (uint32_t)(unsigned long long)__double2ll_rn(__dmul_rn((double)x, fix_scale));
+}
+
+// pos += dt*v + dt*dt*f/2  in double, stored to float (MDSystem.cpp:447-449, :473-475)
+__device__ __forceinline__ float drift1(float x, float v, float f, double dt, double dt2) {
+  const double a = __dmul_rn(dt, (double)v);
+  const double b = __dmul_rn(__dmul_rn(dt2, (double)f), 0.5);
+  return (float)__dadd_rn((double)x, __dadd_rn(a, b));
+}
+// v += dt*f/2 (MDSystem.cpp:451-453, :460-462)
+__device__ __forceinline__ float kick1(float v, float f, double dt) {
+  return (float)__dadd_rn((double)v, __dmul_rn(__dmul_rn(dt, (double)f), 0.5));
+}
+// float expression vx*vx+vy*vy+vz*vz, un-fused, left to right (MDSystem.cpp:334,367,660)
+__device__ __forceinline__ float sq3(float x, float y, float z) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+}
+
+// MDSystem::ApplyBoundaryConditions for one particle (MDSystem.cpp:406-436).
+__device__ __forceinline__ void apply_bc(float4& p, float4& v, double L, int bc) {
+  if (bc == 0) {
+    if ((double)p.x < 0.) p.x = (float)__dadd_rn((double)p.x, L);
+    if ((double)p.x > L) p.x = (float)__dadd_rn((double)p.x, -L);
+    if ((double)p.y < 0.) p.y = (float)__dadd_rn((double)p.y, L);
+    if ((double)p.y > L) p.y = (float)__dadd_rn((double)p.y, -L);
+    if ((double)p.z < 0.) p.z = (float)__dadd_rn((double)p.z, L);
+    if ((double)p.z > L) p.z = (float)__dadd_rn((double)p.z, -L);
+  } else if (bc == 1) {
+    if ((double)p.x < 0. && v.x < 0.f) v.x = -v.x;
+    if ((double)p.x > L && v.x > 0.f) v.x = -v.x;
+    if ((double)p.y < 0. && v.y < 0.f) v.y = -v.y;
+    if ((double)p.y > L && v.y > 0.f) v.y = -v.y;
+    if ((double)p.z < 0. && v.z < 0.f) v.z = -v.z;
+    if ((double)p.z > L && v.z > 0.f) v.z = -v.z;
+  }
+}
+
+// MDSystem::CalculateParameters (MDSystem.cpp:348-358) + t += dt (:582) from the reduced sums.
+// accumulate: 1 inside Integrate, 0 for a bare evaluation (set_state resets av_* anyway).
+__device__ __forceinline__ void finalize_params(const StepParams& p, int accumulate) {
+  DevScalars* sc = p.sc;
+  const double K = sc->sums[SUM_K];
+  const double V = sc->sums[SUM_PE] * (4. / 2.);            // :308
+  const double Pvir = sc->sums[SUM_W] * (4. / 3. / 2.);     // :307
+  const double T = 2. * K / 3. / p.N;                        // :348
+  double P = Pvir + p.N * T;                                 // :349
+  P /= (p.N / p.rho);                                        // :350
+  sc->K = K; sc->V = V; sc->T = T; sc->P = P; sc->Pvirial = Pvir;
+  sc->U = K + V;                                             // :351
+  if (accumulate) {
+    sc->av_iters += 1;                                       // :355-358
+    sc->av_U_tot += sc->U;
+    sc->av_p_tot += P;
+    sc->av_T_tot += T;
+    sc->t += p.dt;                                           // :582
+  }
+}
+
+template <bool CANON>
+__global__ void __launch_bounds__(kStepThreads) k_drift(const StepParams p) {
+  const int il = blockIdx.x * kStepThreads + threadIdx.x;
+  if (il >= p.nloc) return;
+  float4 x = p.pos[il];
+  float4 v = p.vel[il];
+  const float4 f = p.force[il];
+  x.x = drift1(x.x, v.x, f.x, p.dt, p.dt2);
+  x.y = drift1(x.y, v.y, f.y, p.dt, p.dt2);
+  x.z = drift1(x.z, v.z, f.z, p.dt, p.dt2);
+  const int ig = p.i_begin + il;
+  p.posA[ig] = x;
+  if (p.bc == 0) p.upos[ig] = make_uint4(to_fixed(x.x, p.fix_scale), to_fixed(x.y, p.fix_scale),
+                                        to_fixed(x.z, p.fix_scale), 0u);
+  if (!CANON) {
+    v.x = kick1(v.x, f.x, p.dt);
+    v.y = kick1(v.y, f.y, p.dt);
+    v.z = kick1(v.z, f.z, p.dt);
+    p.vel[il] = v;
+  }
+}
+
+// posA/upos from pos for a freshly uploaded snapshot (local shard -> global slots).
+__global__ void __launch_bounds__(kStepThreads) k_prepare(const StepParams p) {
+  const int il = blockIdx.x * kStepThreads + threadIdx.x;
+  if (il >= p.nloc) return;
+  const float4 x = p.pos[il];
+  const int ig = p.i_begin + il;
+  p.posA[ig] = x;
+  if (p.bc == 0) p.upos[ig] = make_uint4(to_fixed(x.x, p.fix_scale), to_fixed(x.y, p.fix_scale),
+                                        to_fixed(x.z, p.fix_scale), 0u);
+}
+
+// Deterministic two-value block reduction + last-block final sum over all blocks.
+// Returns true in thread 0 of the last block after sc->sums[ia], sc->sums[ib] are written.
+__device__ __forceinline__ bool reduce_two(double a, double b, const StepParams& p, int ia, int ib,
+                                           bool also_force_blocks) {
+  __shared__ double sa[kStepThreads / 32], sb[kStepThreads / 32];
+  __shared__ bool is_last;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sa[w] = a; sb[w] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ta = 0., tb = 0.;
+#pragma unroll
+    for (int k = 0; k < kStepThreads / 32; ++k) { ta += sa[k]; tb += sb[k]; }
+    p.part[blockIdx.x] = ta;
+    p.part[gridDim.x + blockIdx.x] = tb;
+    __threadfence();
+    const unsigned int ticket = atomicAdd(p.counter, 1u);
+    is_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return false;
+  __threadfence();
+  // last block: fixed-order sums (deterministic run to run)
+  double ta = 0., tb = 0., tw = 0.;
+  const volatile double* part = p.part;
+  for (int k = threadIdx.x; k < (int)gridDim.x; k += kStepThreads) { ta += part[k]; tb += part[gridDim.x + k]; }
+  if (also_force_blocks) {
+    const volatile double* bw = p.blockW;
+    for (int k = threadIdx.x; k < p.nforce_blocks; k += kStepThreads) tw += bw[k];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ta += __shfl_xor_sync(0xffffffffu, ta, o);
+    tb += __shfl_xor_sync(0xffffffffu, tb, o);
+    tw += __shfl_xor_sync(0xffffffffu, tw, o);
+  }
+  __shared__ double sw[kStepThreads / 32];
+  __syncthreads();
+  if (l == 0) { sa[w] = ta; sb[w] = tb; sw[w] = tw; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ta = tb = tw = 0.;
+#pragma unroll
+    for (int k = 0; k < kStepThreads / 32; ++k) { ta += sa[k]; tb += sb[k]; tw += sw[k]; }
+    p.sc->sums[ia] = ta;
+    p.sc->sums[ib] = tb;
+    if (also_force_blocks) p.sc->sums[SUM_W] = tw;
+    *p.counter = 0u;
+    return true;
+  }
+  return false;
+}
+
+enum { GATHER_EVAL = 0, GATHER_EVN = 1, GATHER_TVN = 2 };
+
+// Sum the j-split partial forces; then, per mode,
+//  EVAL: K from the current velocities (a bare CalculateForces + CalculateParameters)
+//  EVN : second half-kick, boundary conditions, K            (MDSystem.cpp:458-463,578-579)
+//  TVN : t_Force, t_Vel and sum t_Vel^2                       (MDSystem.cpp:484-498)
+template <int MODE>
+__global__ void __launch_bounds__(kStepThreads) k_gather(const StepParams p, int finalize, int accumulate) {
+  const int il = blockIdx.x * kStepThreads + threadIdx.x;
+  double pe = 0., q = 0.;
+  if (il < p.nloc) {
+    float4 f = p.fpart[il];
+    for (int s = 1; s < p.nsplit; ++s) {
+      const float4 g = p.fpart[(size_t)s * p.ilocal_cap + il];
+      f.x += g.x; f.y += g.y; f.z += g.z; f.w += g.w;
+    }
+    pe = (double)f.w;
+    float4 v = p.vel[il];
+    if (MODE == GATHER_EVAL) {
+      p.force[il] = f;
+      q = (double)sq3(v.x, v.y, v.z) * 0.5;                 // :334
+    } else if (MODE == GATHER_EVN) {
+      p.force[il] = f;
+      v.x = kick1(v.x, f.x, p.dt);
+      v.y = kick1(v.y, f.y, p.dt);
+      v.z = kick1(v.z, f.z, p.dt);
+      float4 x = p.posA[p.i_begin + il];
+      apply_bc(x, v, p.L, p.bc);
+      p.pos[il] = x;
+      p.vel[il] = v;
+      q = (double)sq3(v.x, v.y, v.z) * 0.5;
+    } else {
+      const float4 fo = p.force[il];
+      p.force[il] = f;
+      float4 tf;
+      tf.x = __fadd_rn(__fmul_rn(0.5f, fo.x), __fmul_rn(0.5f, f.x));   // :477-479,486-488
+      tf.y = __fadd_rn(__fmul_rn(0.5f, fo.y), __fmul_rn(0.5f, f.y));
+      tf.z = __fadd_rn(__fmul_rn(0.5f, fo.z), __fmul_rn(0.5f, f.z));
+      tf.w = 0.f;
+      p.tforce[il] = tf;
+      const float tx = kick1(v.x, tf.x, p.dt);                           // :493-495
+      const float ty = kick1(v.y, tf.y, p.dt);
+      const float tz = kick1(v.z, tf.z, p.dt);
+      q = (double)sq3(tx, ty, tz);                                       // :367
+    }
+  }
+  const bool last = reduce_two(pe, q, p, SUM_PE, (MODE == GATHER_TVN) ? SUM_TV2 : SUM_K, true);
+  if (last && finalize && MODE != GATHER_TVN) finalize_params(p, accumulate);
+}
+
+// TVN velocity update with chi = sqrt(T0 / Tkin(t_Vel)), boundaries, K  (MDSystem.cpp:498-506,578-579)
+__global__ void __launch_bounds__(kStepThreads) k_finish_tvn(const StepParams p, int finalize) {
+  const int il = blockIdx.x * kStepThreads + threadIdx.x;
+  double Tkin = p.sc->sums[SUM_TV2];
+  Tkin *= 1. / 3. / p.N;                                     // :370
+  const double chi = sqrt(p.T0 / Tkin);                      // :499
+  double q = 0.;
+  if (il < p.nloc) {
+    float4 v = p.vel[il];
+    const float4 tf = p.tforce[il];
+    const double a = 2. * chi - 1.;
+    const double b = chi * p.dt;
+    v.x = (float)__dadd_rn(__dmul_rn(a, (double)v.x), __dmul_rn(b, (double)tf.x));   // :503-505
+    v.y = (float)__dadd_rn(__dmul_rn(a, (double)v.y), __dmul_rn(b, (double)tf.y));
+    v.z = (float)__dadd_rn(__dmul_rn(a, (double)v.z), __dmul_rn(b, (double)tf.z));
+    float4 x = p.posA[p.i_begin + il];
+    apply_bc(x, v, p.L, p.bc);
+    p.pos[il] = x;
+    p.vel[il] = v;
+    q = (double)sq3(v.x, v.y, v.z) * 0.5;
+  }
+  if (il == 0) { p.sc->chi = chi; p.sc->Tkin_trial = Tkin; }
+  const bool last = reduce_two(q, 0., p, SUM_K, SUM_TV2, false);
+  if (last && finalize) finalize_params(p, 1);
+}
+
+// K only (after a velocity upload).
+__global__ void __launch_bounds__(kStepThreads) k_kinetic(const StepParams p) {
+  const int il = blockIdx.x * kStepThreads + threadIdx.x;
+  double q = 0.;
+  if (il < p.nloc) {
+    const float4 v = p.vel[il];
+    q = (double)sq3(v.x, v.y, v.z) * 0.5;
+  }
+  reduce_two(q, 0., p, SUM_K, SUM_TV2, false);
+}
+
+// Multi-rank: parameters from the all-reduced sums.
+__global__ void k_params(const StepParams p, int accumulate) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) finalize_params(p, accumulate);
+}
+
+// Speed histogram, shared-memory privatised (MDSystem.cpp:651-662,676-688).
+// bin = (int)(sqrt((double)(float)(vx^2+vy^2+vz^2)) / step); IEEE double sqrt and divide are
+// correctly rounded on the device, so bins are bit-exact with the CPU path.
+__global__ void __launch_bounds__(kStepThreads) k_velhist(const float4* __restrict__ vel, int n, double step,
+                                                           int nbins, unsigned int* __restrict__ out) {
+  extern __shared__ unsigned int h[];
+  for (int k = threadIdx.x; k < nbins; k += kStepThreads) h[k] = 0u;
+  __syncthreads();
+  for (int i = blockIdx.x * kStepThreads + threadIdx.x; i < n; i += gridDim.x * kStepThreads) {
+    const float4 v = vel[i];
+    const double s = sqrt((double)sq3(v.x, v.y, v.z));
+    const double b = __ddiv_rn(s, step);
+    if (b < (double)nbins) atomicAdd(&h[(int)b], 1u);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < nbins; k += kStepThreads)
+    if (h[k]) atomicAdd(&out[k], h[k]);
+}
+
+__global__ void k_rdf_accum(const unsigned long long* cur, unsigned long long* acc) {
+  acc[threadIdx.x] += cur[threadIdx.x];
+}
+
+}  // namespace ljmd
