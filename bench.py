@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Benchmark of the Lennard-Jones MD step (BASELINE.json: pair interactions/s and MD steps/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C5] [--impl reference]
+
+A "step" is one MDSystem::Integrate(dt): drift, all-pairs force/potential/virial, EVN half-kick or TVN
+rescale, boundary conditions, parameters.  N(N-1) ordered pair interactions per step.  With N > 1 ranks
+(torchrun, one process per GPU) the i-particles are sharded: strong scaling on the same workload.
+
+Prints ONE JSON line on rank 0.  See DESIGN.md §Measurement for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import ljpkg  # noqa: E402
+
+DT = 0.004                      # GUI/task default (reference src/gui/mainwindow.cpp:150, input/*)
+FLOP_PER_PAIR = {0: 37, 1: 25, 2: 25}   # periodic / open
+INSTR_PER_PAIR = {0: 29, 1: 20, 2: 20}  # SURVEY.md §8d minimal FP32-pipe instruction counts
+SM_COUNT, FP32_LANES = 148, 128
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+class ClockSampler:
+    """SM clock + throttle reasons sampled during the timed region (pynvml, else nvidia-smi)."""
+
+    def __init__(self, index=0, period=0.1):
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self._mode = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._mode = "nvml"
+        except Exception:
+            self._mode = "smi"
+
+    def _reason_names(self, mask):
+        nv = self._nv
+        table = [("hw_slowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                 ("hw_thermal_slowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                 ("sw_thermal_slowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                 ("sw_power_cap", "nvmlClocksThrottleReasonSwPowerCap"),
+                 ("hw_power_brake", "nvmlClocksThrottleReasonHwPowerBrakeSlowdown"),
+                 ("sync_boost", "nvmlClocksThrottleReasonSyncBoost"),
+                 ("app_clocks", "nvmlClocksThrottleReasonApplicationsClocksSetting")]
+        out = []
+        for name, attr in table:
+            bit = getattr(nv, attr, None)
+            if bit is not None and (mask & bit):
+                out.append(name)
+        return out
+
+    def _run_nvml(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                self.reasons.update(self._reason_names(mask))
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def _run_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                f = [x.strip() for x in out.stdout.strip().splitlines()[0].split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(max(self.period, 0.2))
+
+    def start(self):
+        self._thread = threading.Thread(target=self._run_nvml if self._mode == "nvml" else self._run_smi, daemon=True)
+        self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=5)
+        if not self.samples:
+            return None
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples), "source": self._mode}
+
+
+def workload(pkg, name):
+    cfg = dict(pkg.snapshots.CONFIGS[name])
+    pos, vel = pkg.snapshots.make(name)
+    return cfg, pos, vel
+
+
+def describe(name, cfg, world):
+    ens = "TVN" if cfg["canonical"] else "EVN"
+    bc = {0: "periodic", 1: "hard-wall", 2: "open"}[cfg["bc"]]
+    return {"workload": f"{name}: N={cfg['N']} T*={cfg['T']} rho*={cfg['rho']} {bc} {ens} dt*={DT}"
+                        + (f" RDF every {cfg['rdf_every']} steps" if cfg["rdf_every"] else ""),
+            "N": cfg["N"], "rho": cfg["rho"], "T": cfg["T"], "boundary": bc, "ensemble": ens,
+            "rdf_every": cfg["rdf_every"], "dt": DT,
+            "parallelism": f"i-shards x{world}" if world > 1 else "single GPU",
+            "init": "reference start lattice (MDSystem.cpp:147-168) + 5% jitter, seeded Gaussian velocities",
+            "l2": "192 MiB scratch overwritten before every step (L2 flush); inputs themselves fit in L2 by design"}
+
+
+# ------------------------------------------------------------------------------------- reference arm
+def reference_sample_n(cfg, steps, warmup, budget_s=150.0):
+    for n in (16384, 8192, 4096, 2048, 1024):
+        if n <= cfg["N"] and (steps + warmup + 2) * 4.0e-8 * n * n <= budget_s:
+            return n
+    return min(cfg["N"], 1024)
+
+
+def run_reference_sample(pkg, cfg, n_s, steps, warmup):
+    """Time the reference's own CPU implementation (oracle/_ref when built, else the C restatement) on a
+    bounded sample: the same density / temperature / boundary / ensemble at a smaller N.  The reference
+    cost is exactly N(N-1) pair evaluations per step on one thread, so pairs/s transfers."""
+    from oracle.oracle import Oracle, Reference, reference_available
+    sub = dict(cfg, N=n_s)
+    pos = pkg.snapshots.lattice(n_s, cfg["rho"], jitter=0.05)
+    vel = pkg.snapshots.velocities(n_s, cfg["T"])
+    if reference_available():
+        kind = "reference"
+        ref = Reference(n_s, cfg["T"], cfg["rho"], cfg["canonical"], cfg["bc"])
+        ref.set_state(pos, vel)
+        for _ in range(warmup):
+            ref.integrate(DT, 1)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ref.integrate(DT, 1)
+        dt_s = time.perf_counter() - t0
+        ref.close()
+    else:
+        kind = "port"
+        o = Oracle()
+        L, dr2 = o.box_length(n_s, cfg["rho"]), o.rdf_dr2(n_s)
+        frc, _, _ = o.forces(pos, L, cfg["bc"], dr2)
+        p, v, f = pos, vel, frc
+        for _ in range(warmup):
+            p, v, f, _, _ = o.integrate(n_s, cfg["rho"], cfg["T"], cfg["canonical"], cfg["bc"], DT, p, v, f)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            p, v, f, _, _ = o.integrate(n_s, cfg["rho"], cfg["T"], cfg["canonical"], cfg["bc"], DT, p, v, f)
+        dt_s = time.perf_counter() - t0
+    pairs = float(n_s) * (n_s - 1) * steps
+    return dict(value=pairs / dt_s, ms_per_step=1e3 * dt_s / steps, kind=kind, n=sub["N"], steps=steps)
+
+
+def host_description():
+    model = "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    return f"{model}, {os.cpu_count()} logical CPUs; the reference CPU path is single-threaded"
+
+
+def main_reference(args, pkg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cfg = dict(pkg.snapshots.CONFIGS[args.config])
+    n_s = reference_sample_n(cfg, args.steps, args.warmup)
+    r = run_reference_sample(pkg, cfg, n_s, args.steps, args.warmup)
+    sample = (f"{args.steps} x Integrate(dt) at N={n_s} (same rho*, T*, boundary, ensemble as the workload; "
+              f"cost is N(N-1) pair evaluations per step); {host_description()}")
+    steps_per_s_full = r["value"] / (float(cfg["N"]) * (cfg["N"] - 1))
+    line = {
+        "impl": "reference", "metric": "pair_interactions_per_s", "value": r["value"], "unit": "pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32/f64 mixed (reference CPU)",
+        "data": "synthetic", "config": describe(args.config, cfg, 1),
+        "md_steps_per_s_extrapolated": steps_per_s_full,
+        "cpu_baseline": {"value": r["value"], "unit": "pairs/s", "cores": 1, "kind": r["kind"], "sample": sample},
+        "e2e": {"value": r["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def main_ours(args, pkg):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    ljmd = pkg.ljmd
+    uid = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        box = [ljmd.LJSystem.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        uid = box[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    cfg, pos, vel = workload(pkg, args.config)
+    N = cfg["N"]
+    sysm = ljmd.LJSystem(N, T0=cfg["T"], rho=cfg["rho"], canonical=cfg["canonical"], bc=cfg["bc"], device=local_rank,
+                         rank=rank, world=world, nccl_unique_id=uid)
+    sysm.set_state(pos, vel)
+    sysm.set_l2_flush(192 << 20)
+    sysm.set_event_timing(True)
+    info = sysm.launch_info()
+    rdf_every = cfg["rdf_every"]
+
+    # ---- device-resident: W warm-up steps, then exactly K timed steps
+    sysm.step(DT, args.warmup, rdf_every)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.start()
+    l0 = sysm.launch_count()
+    t0 = time.perf_counter()
+    sysm.step(DT, args.steps, rdf_every)
+    barrier()
+    wall_s = time.perf_counter() - t0
+    launches = sysm.launch_count() - l0
+    tim = sysm.last_step_timing()
+    clocks = sampler.stop() if sampler else None
+    dev_ms = max_over_ranks(tim["total_ms"])
+    force_ms = max_over_ranks(tim["force_ms"] / max(1, tim["force_launches"]))
+    sc = sysm.scalars()
+    pairs_per_step = float(N) * (N - 1)
+    value = pairs_per_step * args.steps / (dev_ms * 1e-3)
+
+    # ---- end to end through the drop-in call with pinned HOST buffers (upload + step + download each step)
+    sysm.set_event_timing(False)
+    hp = torch.empty((N, 4), dtype=torch.float32).pin_memory()
+    hv = torch.empty((N, 4), dtype=torch.float32).pin_memory()
+    hp_np, hv_np = hp.numpy(), hv.numpy()
+    p_now, v_now, _ = sysm.get_state(force=False)
+    hp_np[...] = p_now
+    hv_np[...] = v_now
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(2):
+        sysm.integrate_host(DT, hp_np, hv_np)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        sysm.integrate_host(DT, hp_np, hv_np)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = pairs_per_step * e2e_steps / e2e_s
+    h2d = 2 * 16 * info["n_local"] * world            # every rank uploads its shard of pos and vel
+    d2h = 2 * 16 * N * world + 8 * 20 * world         # every rank reads back full pos, vel and the scalar block
+
+    # ---- roofline of the dominant kernel (force): algorithmic flops / measured launch duration
+    peaks = measured_peaks()
+    sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+    fp32_peak = SM_COUNT * FP32_LANES * 2 * sm_max * 1e6 / 1e12      # TFLOP/s at max clock
+    flops_per_launch = FLOP_PER_PAIR[cfg["bc"]] * pairs_per_step / world
+    achieved = flops_per_launch / (force_ms * 1e-3) / 1e12
+    clk = (clocks or {}).get("sm_mhz") or sm_max
+    pipe_util = (INSTR_PER_PAIR[cfg["bc"]] * pairs_per_step / world / (force_ms * 1e-3)) / (SM_COUNT * FP32_LANES * clk * 1e6)
+    roofline = {
+        "bound": "fp32",
+        "kernel": "k_force (all-pairs LJ force/potential/virial)",
+        "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+        "peak_source": f"148 SMs x 128 FP32 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz; that file holds "
+                       "no FP32 CUDA-core figure — the kernel is FP32-issue bound, not HBM or tensor bound)",
+        "flop_per_pair": FLOP_PER_PAIR[cfg["bc"]], "pairs_per_launch": pairs_per_step / world,
+        "kernel_ms": force_ms, "kernel_share_of_step": force_ms * args.steps / dev_ms,
+        "fp32_pipe_util_at_sampled_clock": pipe_util,
+        "traffic": None,
+    }
+    if rank == 0:
+        line = {
+            "metric": "pair_interactions_per_s", "value": value, "unit": "pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": describe(args.config, cfg, world),
+            "md_steps_per_s": args.steps / (dev_ms * 1e-3),
+            "wall_ms_per_step": 1e3 * wall_s / args.steps,
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps,
+                    "call": "ljmd_integrate_host (upload pos+vel, Integrate, download pos+vel+scalars)"},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "launch": info,
+            "state": {"U_per_N": sc["U"] / N, "T": sc["T"], "P": sc["P"]},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            n_s = 16384 if N >= 16384 else N
+            r = run_reference_sample(pkg, cfg, n_s, 1 if n_s >= 8192 else 20, 0)
+            line["cpu_baseline"] = {
+                "value": r["value"], "unit": "pairs/s", "cores": 1, "kind": r["kind"],
+                "sample": f"{r['steps']} x Integrate(dt) at N={n_s} (same rho*, T*, boundary, ensemble; the reference "
+                          f"cost is N(N-1) pair evaluations per step); {host_description()}"}
+        print(json.dumps(line))
+    sysm.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="C5", choices=["C1", "C2", "C3", "C4", "C5"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    pkg = ljpkg.load()
+    if args.impl == "reference":
+        return main_reference(args, pkg)
+    return main_ours(args, pkg)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

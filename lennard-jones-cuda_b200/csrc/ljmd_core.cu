@@ -49,7 +49,9 @@ extern "C" const char* ljmd_last_error(void) { return g_err; }
 
 // --------------------------------------------------------------------------------- the handle
 constexpr int kForceThreads = 128;
-constexpr int kITile = kForceThreads * kIPT;  // i-particles per CTA
+constexpr int kNPair = 2;                     // packed i-pairs per thread
+constexpr int kUnroll = 4;                    // j-loop unroll
+constexpr int kITile = kForceThreads * 2 * kNPair;  // i-particles per CTA
 constexpr int kTileJ = 1024;                  // j-records per smem stage
 constexpr int kMinBlocks = 4;                 // resident CTAs/SM the non-RDF kernel is built for
 constexpr int kMinBlocksRdf = 3;
@@ -76,6 +78,8 @@ struct ljmd_system {
   DevScalars* h_sc = nullptr;  // pinned mirror
   unsigned long long *rdf_cur = nullptr, *rdf_acc = nullptr;
   unsigned long long* h_rdf = nullptr;  // pinned [256]
+  void* flush_buf = nullptr;  // optional L2-flush scratch (benchmark hygiene)
+  size_t flush_bytes = 0;
   int rdf_valid = 0;  // rdf_cur matches the latest force evaluation
   int rdf_nacc = 0;
   long long launches = 0;
@@ -111,18 +115,21 @@ static float image_threshold(double L, int k) {
   return d;
 }
 
-// j-split heuristic: balance n_itiles*S CTAs over the SMs while keeping chunks long enough to
-// amortise the per-CTA prologue/epilogue (DESIGN.md §grid sizing).
+// j-split heuristic (DESIGN.md §grid sizing).  The grid is n_itiles x S CTAs of equal work and the SM
+// holds kMinBlocks of them, so the launch runs in ceil(n_itiles*S / (SMs*kMinBlocks)) waves of
+// (N/S + overhead) j-iterations each; pick the S that minimises that product, smallest S on ties
+// (fewer partial-force rows to write and re-read).
 static int choose_split(int n_itiles, int N, int num_sms, int nloc) {
-  const double ovh = 96.;  // per-CTA fixed cost in j-equivalents
+  const double ovh = 128.;  // per-CTA fixed cost (prologue, first tile latency, epilogue) in j-iterations
+  const long long slots = (long long)num_sms * kMinBlocks;
   int best = 1;
   double best_cost = 1e300;
-  const int smax = std::max(1, std::min(N / 128, 4 * num_sms));
+  const int smax = std::max(1, std::min(N / 64, 8 * num_sms));
   for (int s = 1; s <= smax; ++s) {
     if ((double)s * nloc * 16. > 1.5e9) break;  // partial-force buffer cap
-    const double chunk = (double)N / s + ovh;
-    const double cost = ((double)n_itiles * s / num_sms) * chunk + chunk;  // balanced part + tail
-    if (cost < best_cost * 0.995) { best_cost = cost; best = s; }
+    const long long waves = ((long long)n_itiles * s + slots - 1) / slots;
+    const double cost = (double)waves * ((double)N / s + ovh);
+    if (cost < best_cost * 0.999) { best_cost = cost; best = s; }
   }
   return best;
 }
@@ -144,7 +151,7 @@ static int step_grid(const ljmd_system* s) { return (s->nloc + kStepThreads - 1)
 template <bool PERIODIC, bool RDF>
 static cudaError_t launch_force_t(ljmd_system* s, const ForceParams& fp) {
   constexpr int MINB = RDF ? kMinBlocksRdf : kMinBlocks;
-  auto kern = k_force<PERIODIC, RDF, kForceThreads, MINB>;
+  auto kern = k_force<P2, PERIODIC, RDF, kForceThreads, MINB, kNPair, kUnroll>;
   const size_t smem = force_smem_bytes(PERIODIC, RDF, kTileJ, kForceThreads);
   static bool attr_done = false;
   if (!attr_done) {
@@ -311,6 +318,19 @@ extern "C" int ljmd_nccl_unique_id(void* out128) {
 #endif
 }
 
+extern "C" float ljmd_image_threshold(double L, int k) { return image_threshold(L, k); }
+
+extern "C" int ljmd_plan(int N, int rank, int world, int num_sms, int* out6) {
+  if (!out6 || N < 2 || world < 1 || rank < 0 || rank >= world || num_sms < 1)
+    return set_err(LJMD_ERR_ARG, "bad arguments to ljmd_plan");
+  const int cnt = (N + world - 1) / world;
+  const int b = std::min(N, rank * cnt), e = std::min(N, (rank + 1) * cnt);
+  const int nit = (e - b + kITile - 1) / kITile;
+  const int ns = (e > b) ? choose_split(nit, N, num_sms, cnt) : 0;
+  out6[0] = b; out6[1] = e; out6[2] = nit; out6[3] = ns; out6[4] = nit * ns; out6[5] = kITile;
+  return LJMD_OK;
+}
+
 static int destroy_impl(ljmd_system* s) {
   if (!s) return LJMD_OK;
   cudaSetDevice(s->device);
@@ -321,6 +341,7 @@ static int destroy_impl(ljmd_system* s) {
   cudaFree(s->pos); cudaFree(s->posA); cudaFree(s->vel); cudaFree(s->force); cudaFree(s->tforce);
   cudaFree(s->fpart); cudaFree(s->gath); cudaFree(s->upos); cudaFree(s->blockW); cudaFree(s->part);
   cudaFree(s->counter); cudaFree(s->velh); cudaFree(s->sc); cudaFree(s->rdf_cur); cudaFree(s->rdf_acc);
+  cudaFree(s->flush_buf);
   cudaFreeHost(s->h_sc); cudaFreeHost(s->h_rdf);
   for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
   if (s->ev_begin) cudaEventDestroy(s->ev_begin);
@@ -574,6 +595,7 @@ extern "C" int ljmd_step(ljmd_system* s, double dt, int nsteps, int rdf_every) {
   if (s->timing) CU(cudaEventRecord(s->ev_begin, s->stream));
   for (int k = 0; k < nsteps; ++k) {
     const bool rdf = rdf_every > 0 && ((k + 1) % rdf_every == 0);
+    if (s->flush_bytes) CU(cudaMemsetAsync(s->flush_buf, k & 0xff, s->flush_bytes, s->stream));
     int rc = one_step(s, p, rdf);
     if (rc) return rc;
   }
@@ -702,6 +724,22 @@ extern "C" int ljmd_velocity_histogram(ljmd_system* s, double step, int nbins, i
   CU(cudaMemcpyAsync(h.data(), s->velh, (size_t)nbins * 4, cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
   for (int k = 0; k < nbins; ++k) out[k] = (int)h[k];
+  return LJMD_OK;
+}
+
+extern "C" int ljmd_set_l2_flush(ljmd_system* s, long long bytes) {
+  CHECK_S(s);
+  if (bytes < 0) return set_err(LJMD_ERR_ARG, "bytes must be >= 0");
+  if ((size_t)bytes != s->flush_bytes) {
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaFree(s->flush_buf));
+    s->flush_buf = nullptr;
+    s->flush_bytes = 0;
+    if (bytes > 0) {
+      CU(cudaMalloc(&s->flush_buf, (size_t)bytes));
+      s->flush_bytes = (size_t)bytes;
+    }
+  }
   return LJMD_OK;
 }
 

@@ -4,7 +4,7 @@
 // (/root/reference/src/library/MDSystem.cu:21-153) and its CPU double loop
 // (/root/reference/src/library/MDSystem.cpp:252-310).  Not a port: see DESIGN.md.
 //
-//  * i-particles live in registers, 4 per thread, as two packed f32x2 pairs so the
+//  * i-particles live in registers, 2*NPAIR per thread, as packed f32x2 pairs so the
 //    FP32-pipe work issues as FFMA2/FMUL2/FADD2 (one issue slot, two lanes).
 //  * j-records stream through shared memory in double-buffered tiles filled by
 //    1-D TMA bulk copies (cp.async.bulk -> UBLKCP) completing on an mbarrier.
@@ -26,25 +26,51 @@ namespace ljmd {
 
 typedef unsigned long long u64;
 
-// ---- packed f32x2 helpers (PTX ISA 8.6, sm_100+) ------------------------------------------
-__device__ __forceinline__ u64 pk(float lo, float hi) {
-  u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+// ---- two-lane FP32 values -------------------------------------------------------------------------
+// P2: one 64-bit register pair driven by the packed f32x2 instructions of sm_100 (PTX ISA 8.6:
+//     fma/mul/add/sub.rn.f32x2 -> SASS FFMA2/FMUL2/FADD2): one issue slot for two lanes.
+// S2: the same two lanes as two scalar instructions (kept for A/B measurements in tools/tune_force.cu).
+struct P2 { u64 v; };
+struct S2 { float lo, hi; };
+
+__device__ __forceinline__ void pk(P2& r, float lo, float hi) {
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
 }
-__device__ __forceinline__ float2 upk(u64 v) {
-  float2 o; asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(v)); return o;
+__device__ __forceinline__ float2 upk(const P2& a) {
+  float2 o; asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(a.v)); return o;
 }
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
-  u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
+__device__ __forceinline__ P2 fma2(const P2& a, const P2& b, const P2& c) {
+  P2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r;
 }
-__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
-  u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+__device__ __forceinline__ P2 mul2(const P2& a, const P2& b) {
+  P2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r;
 }
-__device__ __forceinline__ u64 add2(u64 a, u64 b) {
-  u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+__device__ __forceinline__ P2 add2(const P2& a, const P2& b) {
+  P2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r;
 }
-__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
-  u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+__device__ __forceinline__ P2 sub2(const P2& a, const P2& b) {
+  P2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r;
 }
+
+__device__ __forceinline__ void pk(S2& r, float lo, float hi) { r.lo = lo; r.hi = hi; }
+__device__ __forceinline__ float2 upk(const S2& a) { return make_float2(a.lo, a.hi); }
+__device__ __forceinline__ S2 fma2(const S2& a, const S2& b, const S2& c) {
+  S2 r; r.lo = __fmaf_rn(a.lo, b.lo, c.lo); r.hi = __fmaf_rn(a.hi, b.hi, c.hi); return r;
+}
+__device__ __forceinline__ S2 mul2(const S2& a, const S2& b) {
+  S2 r; r.lo = __fmul_rn(a.lo, b.lo); r.hi = __fmul_rn(a.hi, b.hi); return r;
+}
+__device__ __forceinline__ S2 add2(const S2& a, const S2& b) {
+  S2 r; r.lo = __fadd_rn(a.lo, b.lo); r.hi = __fadd_rn(a.hi, b.hi); return r;
+}
+__device__ __forceinline__ S2 sub2(const S2& a, const S2& b) {
+  S2 r; r.lo = __fsub_rn(a.lo, b.lo); r.hi = __fsub_rn(a.hi, b.hi); return r;
+}
+template <typename V>
+__device__ __forceinline__ V mk2(float lo, float hi) { V r; pk(r, lo, hi); return r; }
+template <typename V>
+__device__ __forceinline__ V bc2(float a) { V r; pk(r, a, a); return r; }
+
 __device__ __forceinline__ float rcp_approx(float x) {
   float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
 }
@@ -64,17 +90,22 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
                : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  int spins = 0;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    // a bulk copy that never lands must fail the launch, not hang the device
+    if (!done && ++spins > (1 << 22)) __trap();
+  } while (!done);
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile(
@@ -86,7 +117,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 
 // ---- kernel parameters -------------------------------------------------------------------------
 constexpr int kRdfBins = 256;  // MDSystem.cpp:97
-constexpr int kIPT = 4;        // i-particles per thread (two packed pairs)
 
 struct ForceParams {
   const uint4* jrec;     // [N] j-records: periodic -> fixed-point {ux,uy,uz,0}; open -> float4 bits {x,y,z,w}
@@ -148,55 +178,62 @@ __device__ __forceinline__ void rdf_slow(float xi, float yi, float zi, const flo
   if ((unsigned)b < (unsigned)kRdfBins) atomicAdd(&hist[b], 1u);
 }
 
-// One packed pair of i-particles against one j-record.
+// One pair of i-particles (two lanes of V).
+template <typename V>
 struct PairAcc {
-  u64 fx, fy, fz;  // force accumulators (k-units when periodic)
-  u64 s6, w;       // sum r^-6, sum u
+  V fx, fy, fz;  // force accumulators (k-units when periodic)
+  V s6, w;       // tile-level sum r^-6, sum u
+};
+template <typename V>
+struct PairI {
+  int ax, ay, az, bx, by, bz;  // fixed-point coordinates of the two particles (periodic)
+  V x2, y2, z2;                // float coordinates (open boxes; RDF slow path)
+  bool v_lo, v_hi;             // lane holds a real particle (not a clamped duplicate)
 };
 
-template <bool PERIODIC, bool DIAG, bool RDF>
-__device__ __forceinline__ void pair_body(const uint4& uj, const int4& ia, const int4& ib,  // fixed-point i (periodic)
-                                          u64 xi2, u64 yi2, u64 zi2,                        // packed float i (open)
-                                          PairAcc& acc, bool self_lo, bool self_hi, bool v_lo, bool v_hi,
-                                          const ForceParams& p, const float4* pjf, unsigned int* hist) {
-  u64 dx, dy, dz;
+template <typename V, bool PERIODIC, bool DIAG, bool RDF>
+__device__ __forceinline__ void pair_body(const uint4& uj, const PairI<V>& pi, PairAcc<V>& acc, bool self_lo,
+                                          bool self_hi, const ForceParams& p, const float4* pjf, unsigned int* hist) {
+  V dx, dy, dz;
   if (PERIODIC) {
-    // wrap of the 32-bit subtract IS the minimum image
-    int ax = ia.x - (int)uj.x, ay = ia.y - (int)uj.y, az = ia.z - (int)uj.z;
-    int bx = ib.x - (int)uj.x, by = ib.y - (int)uj.y, bz = ib.z - (int)uj.z;
-    dx = pk(__int2float_rn(ax), __int2float_rn(bx));
-    dy = pk(__int2float_rn(ay), __int2float_rn(by));
-    dz = pk(__int2float_rn(az), __int2float_rn(bz));
+    // the wrap of the 32-bit subtract IS the minimum image
+    dx = mk2<V>(__int2float_rn(pi.ax - (int)uj.x), __int2float_rn(pi.bx - (int)uj.x));
+    dy = mk2<V>(__int2float_rn(pi.ay - (int)uj.y), __int2float_rn(pi.by - (int)uj.y));
+    dz = mk2<V>(__int2float_rn(pi.az - (int)uj.z), __int2float_rn(pi.bz - (int)uj.z));
   } else {
-    float xj = __uint_as_float(uj.x), yj = __uint_as_float(uj.y), zj = __uint_as_float(uj.z);
-    dx = sub2(xi2, pk(xj, xj));
-    dy = sub2(yi2, pk(yj, yj));
-    dz = sub2(zi2, pk(zj, zj));
+    dx = sub2(pi.x2, bc2<V>(__uint_as_float(uj.x)));
+    dy = sub2(pi.y2, bc2<V>(__uint_as_float(uj.y)));
+    dz = sub2(pi.z2, bc2<V>(__uint_as_float(uj.z)));
   }
-  u64 r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
-  float2 r2s = upk(r2);
+  const V r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+  const float2 r2s = upk(r2);
   float inv0 = rcp_approx(r2s.x), inv1 = rcp_approx(r2s.y);
   if (DIAG) {
     if (self_lo) inv0 = 0.f;
     if (self_hi) inv1 = 0.f;
   }
-  u64 x = pk(inv0, inv1);
-  if (PERIODIC) x = mul2(x, pk(p.c2, p.c2));
-  u64 x2 = mul2(x, x);
-  u64 r6 = mul2(x2, x);
-  u64 t = fma2(r6, pk(12.f, 12.f), pk(-6.f, -6.f));
-  u64 u = mul2(r6, t);
-  u64 s = mul2(u, x);
+  V x = mk2<V>(inv0, inv1);
+  if (PERIODIC) x = mul2(x, bc2<V>(p.c2));
+  const V x2 = mul2(x, x);
+  const V r6 = mul2(x2, x);
+  const V t = fma2(r6, bc2<V>(12.f), bc2<V>(-6.f));
+  const V u = mul2(r6, t);
+  const V s = mul2(u, x);
   acc.fx = fma2(dx, s, acc.fx);
   acc.fy = fma2(dy, s, acc.fy);
   acc.fz = fma2(dz, s, acc.fz);
   acc.s6 = add2(acc.s6, r6);
   acc.w = add2(acc.w, u);
   if (RDF) {
-    float2 xs = upk(xi2), ys = upk(yi2), zs = upk(zi2);
     // clamped duplicate lanes (v_* false) and the self pair never count
-    if (r2s.x < p.cut_fast && v_lo && !(DIAG && self_lo)) rdf_slow<PERIODIC>(xs.x, ys.x, zs.x, *pjf, p, hist);
-    if (r2s.y < p.cut_fast && v_hi && !(DIAG && self_hi)) rdf_slow<PERIODIC>(xs.y, ys.y, zs.y, *pjf, p, hist);
+    if (r2s.x < p.cut_fast && pi.v_lo && !(DIAG && self_lo)) {
+      const float2 xs = upk(pi.x2), ys = upk(pi.y2), zs = upk(pi.z2);
+      rdf_slow<PERIODIC>(xs.x, ys.x, zs.x, *pjf, p, hist);
+    }
+    if (r2s.y < p.cut_fast && pi.v_hi && !(DIAG && self_hi)) {
+      const float2 xs = upk(pi.x2), ys = upk(pi.y2), zs = upk(pi.z2);
+      rdf_slow<PERIODIC>(xs.y, ys.y, zs.y, *pjf, p, hist);
+    }
   }
 }
 
@@ -216,9 +253,11 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return t;  // valid in thread 0
 }
 
-// grid: (i-tiles, j-splits).  block: THREADS.  dyn smem: see force_smem_bytes().
-template <bool PERIODIC, bool RDF, int THREADS, int MINB>
+// grid: (i-tiles, j-splits).  block: THREADS.  dyn smem: force_smem_bytes().
+// A thread owns 2*NPAIR i-particles: particle m is ibase + m*THREADS + tid; packed pair q = (2q, 2q+1).
+template <typename V, bool PERIODIC, bool RDF, int THREADS, int MINB, int NPAIR, int UNROLL>
 __global__ void __launch_bounds__(THREADS, MINB) k_force(const ForceParams p) {
+  constexpr int IPT = 2 * NPAIR;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int TJ = p.tile_j;
@@ -229,7 +268,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force(const ForceParams p) {
   double* red = reinterpret_cast<double*>(tail + 16);          // [THREADS/32]
   unsigned int* hist = reinterpret_cast<unsigned int*>(tail + 16 + 8 * (THREADS / 32));  // [THREADS/32][256] (RDF)
 
-  const int ibase = p.i_begin + blockIdx.x * (THREADS * kIPT);
+  const int ibase = p.i_begin + blockIdx.x * (THREADS * IPT);
   // j-split: near-equal contiguous chunks
   const int ns = gridDim.y;
   const int jb = (int)(((long long)p.N * blockIdx.y) / ns);
@@ -257,25 +296,29 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force(const ForceParams p) {
   };
   if (tid == 0 && ntiles > 0) issue(0);
 
-  // my four i's: m-th is ibase + m*THREADS + tid; pairs are (m=0,1) and (m=2,3)
-  int4 ui[kIPT];
-  float4 xf[kIPT];
-  bool valid[kIPT];
+  PairI<V> pi[NPAIR];
+  PairAcc<V> acc[NPAIR];
+  V s6run[NPAIR], wrun[NPAIR];  // run-level sums (two-level float summation)
+  const V zero2 = bc2<V>(0.f);
 #pragma unroll
-  for (int m = 0; m < kIPT; ++m) {
-    int i = ibase + m * THREADS + tid;
-    valid[m] = i < p.i_end;
-    if (!valid[m]) i = p.i_end - 1;
-    uint4 r = p.jrec[i];
-    ui[m] = make_int4((int)r.x, (int)r.y, (int)r.z, 0);
-    xf[m] = (PERIODIC && !RDF) ? make_float4(0.f, 0.f, 0.f, 0.f) : p.posf[i];
+  for (int q = 0; q < NPAIR; ++q) {
+    int i0 = ibase + (2 * q) * THREADS + tid, i1 = i0 + THREADS;
+    pi[q].v_lo = i0 < p.i_end;
+    pi[q].v_hi = i1 < p.i_end;
+    if (!pi[q].v_lo) i0 = p.i_end - 1;
+    if (!pi[q].v_hi) i1 = p.i_end - 1;
+    const uint4 r0 = p.jrec[i0], r1 = p.jrec[i1];
+    pi[q].ax = (int)r0.x; pi[q].ay = (int)r0.y; pi[q].az = (int)r0.z;
+    pi[q].bx = (int)r1.x; pi[q].by = (int)r1.y; pi[q].bz = (int)r1.z;
+    if (!PERIODIC || RDF) {
+      const float4 f0 = p.posf[i0], f1 = p.posf[i1];
+      pi[q].x2 = mk2<V>(f0.x, f1.x); pi[q].y2 = mk2<V>(f0.y, f1.y); pi[q].z2 = mk2<V>(f0.z, f1.z);
+    } else {
+      pi[q].x2 = pi[q].y2 = pi[q].z2 = zero2;
+    }
+    acc[q].fx = acc[q].fy = acc[q].fz = acc[q].s6 = acc[q].w = zero2;
+    s6run[q] = wrun[q] = zero2;
   }
-  u64 xA = pk(xf[0].x, xf[1].x), yA = pk(xf[0].y, xf[1].y), zA = pk(xf[0].z, xf[1].z);
-  u64 xB = pk(xf[2].x, xf[3].x), yB = pk(xf[2].y, xf[3].y), zB = pk(xf[2].z, xf[3].z);
-
-  const u64 zero2 = pk(0.f, 0.f);
-  PairAcc A = {zero2, zero2, zero2, zero2, zero2}, B = {zero2, zero2, zero2, zero2, zero2};
-  u64 s6A = zero2, wA = zero2, s6B = zero2, wB = zero2;  // run-level (two-level float summation)
   unsigned int* myhist = hist + (tid >> 5) * kRdfBins;
 
   for (int t = 0; t < ntiles; ++t) {
@@ -287,53 +330,54 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force(const ForceParams p) {
     const uint4* tu = tile_u + (size_t)st * TJ;
     const float4* tf = (RDF && PERIODIC) ? (tile_f + (size_t)st * TJ) : reinterpret_cast<const float4*>(tu);
     // does this tile contain any of this CTA's own particles?
-    const bool diag = (j0 < ibase + THREADS * kIPT) && (j0 + nj > ibase);
+    const bool diag = (j0 < ibase + THREADS * IPT) && (j0 + nj > ibase);
     if (!diag) {
-#pragma unroll 4
+#pragma unroll UNROLL
       for (int j = 0; j < nj; ++j) {
         const uint4 uj = tu[j];
-        pair_body<PERIODIC, false, RDF>(uj, ui[0], ui[1], xA, yA, zA, A, false, false, valid[0], valid[1], p, tf + j,
-                                        myhist);
-        pair_body<PERIODIC, false, RDF>(uj, ui[2], ui[3], xB, yB, zB, B, false, false, valid[2], valid[3], p, tf + j,
-                                        myhist);
+#pragma unroll
+        for (int q = 0; q < NPAIR; ++q)
+          pair_body<V, PERIODIC, false, RDF>(uj, pi[q], acc[q], false, false, p, tf + j, myhist);
       }
     } else {
-      const int jrel0 = j0 - ibase - tid;  // j-index relative to my m=0 particle
+      const int jrel0 = j0 - ibase - tid;  // j-index relative to my particle m = 0
 #pragma unroll 2
       for (int j = 0; j < nj; ++j) {
         const uint4 uj = tu[j];
         const int jr = jrel0 + j;
-        pair_body<PERIODIC, true, RDF>(uj, ui[0], ui[1], xA, yA, zA, A, jr == 0, jr == THREADS, valid[0], valid[1], p,
-                                       tf + j, myhist);
-        pair_body<PERIODIC, true, RDF>(uj, ui[2], ui[3], xB, yB, zB, B, jr == 2 * THREADS, jr == 3 * THREADS, valid[2],
-                                       valid[3], p, tf + j, myhist);
+#pragma unroll
+        for (int q = 0; q < NPAIR; ++q)
+          pair_body<V, PERIODIC, true, RDF>(uj, pi[q], acc[q], jr == (2 * q) * THREADS, jr == (2 * q + 1) * THREADS,
+                                            p, tf + j, myhist);
       }
     }
-    // two-level summation of the scalar sums: tile-level floats folded into run-level floats
-    s6A = add2(s6A, A.s6); wA = add2(wA, A.w); A.s6 = zero2; A.w = zero2;
-    s6B = add2(s6B, B.s6); wB = add2(wB, B.w); B.s6 = zero2; B.w = zero2;
+#pragma unroll
+    for (int q = 0; q < NPAIR; ++q) {
+      s6run[q] = add2(s6run[q], acc[q].s6);
+      wrun[q] = add2(wrun[q], acc[q].w);
+      acc[q].s6 = zero2;
+      acc[q].w = zero2;
+    }
     __syncthreads();  // everyone is done with stage st before it is refilled
   }
 
-  // ---- epilogue ----
+  // ---- epilogue: scale, store partial forces + per-particle potential, reduce the virial sum ----
   const float fs = p.fscale;
-  float2 fxA = upk(A.fx), fyA = upk(A.fy), fzA = upk(A.fz), fxB = upk(B.fx), fyB = upk(B.fy), fzB = upk(B.fz);
-  float2 a6 = upk(s6A), aw = upk(wA), b6 = upk(s6B), bw = upk(wB);
-  const float fxs[kIPT] = {fxA.x, fxA.y, fxB.x, fxB.y};
-  const float fys[kIPT] = {fyA.x, fyA.y, fyB.x, fyB.y};
-  const float fzs[kIPT] = {fzA.x, fzA.y, fzB.x, fzB.y};
-  const float s6s[kIPT] = {a6.x, a6.y, b6.x, b6.y};
-  const float ws[kIPT] = {aw.x, aw.y, bw.x, bw.y};
   double wsum = 0.;
   float4* out = p.fpart + (size_t)blockIdx.y * p.ilocal_cap;
 #pragma unroll
-  for (int m = 0; m < kIPT; ++m) {
-    if (valid[m]) {
-      const int il = (ibase - p.i_begin) + m * THREADS + tid;
-      // r^-12 - r^-6 = u/12 - r^-6/2
-      const float pe = ws[m] * (1.f / 12.f) - 0.5f * s6s[m];
-      out[il] = make_float4(fxs[m] * fs, fys[m] * fs, fzs[m] * fs, pe);
-      wsum += (double)ws[m];
+  for (int q = 0; q < NPAIR; ++q) {
+    const float2 fx = upk(acc[q].fx), fy = upk(acc[q].fy), fz = upk(acc[q].fz);
+    const float2 s6 = upk(s6run[q]), w = upk(wrun[q]);
+    const int il = (ibase - p.i_begin) + (2 * q) * THREADS + tid;
+    // r^-12 - r^-6 = u/12 - r^-6/2
+    if (pi[q].v_lo) {
+      out[il] = make_float4(fx.x * fs, fy.x * fs, fz.x * fs, w.x * (1.f / 12.f) - 0.5f * s6.x);
+      wsum += (double)w.x;
+    }
+    if (pi[q].v_hi) {
+      out[il + THREADS] = make_float4(fx.y * fs, fy.y * fs, fz.y * fs, w.y * (1.f / 12.f) - 0.5f * s6.y);
+      wsum += (double)w.y;
     }
   }
   const double wtot = block_sum<THREADS>(wsum, red);

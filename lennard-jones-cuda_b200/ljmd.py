@@ -25,6 +25,7 @@ API_SYMBOLS = [
     "ljmd_set_velocities", "ljmd_get_state", "ljmd_step", "ljmd_integrate_host", "ljmd_compute_forces",
     "ljmd_get_scalars", "ljmd_reset_averaging", "ljmd_get_rdf", "ljmd_get_rdf_accum", "ljmd_velocity_histogram",
     "ljmd_launch_count", "ljmd_set_event_timing", "ljmd_last_step_timing", "ljmd_get_launch_info",
+    "ljmd_image_threshold", "ljmd_plan", "ljmd_set_l2_flush",
     # legacy seam (MDSystem.cpp:9-25)
     "allocateArray", "deleteArray", "copyArrayToDevice", "copyArrayFromDevice", "calculateNForces", "threadExit",
     "allocateNBodyArrays", "deleteNBodyArrays", "registerGLBufferObject", "unregisterGLBufferObject", "threadSync",
@@ -74,6 +75,10 @@ def load_library(path=None):
     lib.ljmd_set_event_timing.argtypes = [vp, C.c_int]
     lib.ljmd_last_step_timing.argtypes = [vp, dp, dp, ip]
     lib.ljmd_get_launch_info.argtypes = [vp, ip]
+    lib.ljmd_set_l2_flush.argtypes = [vp, C.c_longlong]
+    lib.ljmd_image_threshold.restype = C.c_float
+    lib.ljmd_image_threshold.argtypes = [C.c_double, C.c_int]
+    lib.ljmd_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, ip]
     lib.calculateNForces.argtypes = [vp, vp, fp, C.c_int, C.c_float, C.c_int, ip, C.c_float, C.c_int, C.c_int]
     lib.calculateNForces.restype = None
     lib.allocateArray.argtypes = [C.POINTER(vp), C.c_int]
@@ -236,6 +241,9 @@ class LJSystem:
     def set_event_timing(self, on=True):
         self._check(self._lib.ljmd_set_event_timing(self._h, int(on)))
 
+    def set_l2_flush(self, nbytes):
+        self._check(self._lib.ljmd_set_l2_flush(self._h, int(nbytes)))
+
     def last_step_timing(self):
         f, t, n = C.c_double(0), C.c_double(0), C.c_int(0)
         self._check(self._lib.ljmd_last_step_timing(self._h, C.byref(f), C.byref(t), C.byref(n)))
@@ -245,6 +253,20 @@ class LJSystem:
         buf = (C.c_int * 6)()
         self._check(self._lib.ljmd_get_launch_info(self._h, buf))
         return dict(num_sms=buf[0], i_tile=buf[1], j_splits=buf[2], force_ctas=buf[3], world=buf[4], n_local=buf[5])
+
+
+def image_threshold(L, k=1):
+    return float(load_library().ljmd_image_threshold(float(L), int(k)))
+
+
+def plan(N, rank=0, world=1, num_sms=148):
+    """Launch plan of the force kernel (host logic only; no device needed)."""
+    lib = load_library()
+    buf = (C.c_int * 6)()
+    rc = lib.ljmd_plan(int(N), int(rank), int(world), int(num_sms), buf)
+    if rc != 0:
+        raise LJMDError(lib.ljmd_last_error().decode())
+    return dict(i_begin=buf[0], i_end=buf[1], i_tiles=buf[2], j_splits=buf[3], force_ctas=buf[4], i_tile=buf[5])
 
 
 def rdf_curve(N, L, dr2, counts):

@@ -30,7 +30,7 @@ def lattice(N, rho, jitter=0.0, seed=12345):
     ns = int(math.ceil(math.pow(N, 1.0 / 3.0)))
     dL = L / ns
     idx = np.arange(N, dtype=np.int64)
-    pos = np.empty((N, 4), dtype=np.float64)
+    pos = np.zeros((N, 4), dtype=np.float64)
     pos[:, 0] = ((idx % ns) + 0.5) * dL
     pos[:, 1] = (((idx // ns) % ns) + 0.5) * dL
     pos[:, 2] = ((idx // (ns * ns)) + 0.5) * dL

@@ -106,12 +106,14 @@ void ljo_forces(int N, const float* pos, double L, int bc, float rdf_dr2,
  * of reference arithmetic — used to judge which of two FP32 answers is closer
  * and to build the per-particle normalisation sum_j |f_ij| for the tolerance.
  * out: frc[3N] doubles (x,y,z, x4 applied), fabs_sum[N] = 4*sum_j |f_ij|,
- * scal[0]=V, scal[1]=P(virial part) with the reference's prefactors.
+ * scal[0]=V, scal[1]=P(virial part) with the reference's prefactors;
+ * scal[2]=sum of |pair potential| terms, scal[3]=sum of |pair virial| terms (same prefactors): the
+ * scales against which "relative" errors of V and P are judged when V or P nearly cancels.
  */
 void ljo_forces_f64(int N, const float* pos, double L, int bc,
                     double* frc, double* fabs_sum, double* scal)
 {
-  double V = 0., P = 0.;
+  double V = 0., P = 0., Vabs = 0., Pabs = 0.;
   int i, j;
   for (i = 0; i < N; ++i) {
     double fx = 0., fy = 0., fz = 0., fa = 0.;
@@ -130,12 +132,16 @@ void ljo_forces_f64(int N, const float* pos, double L, int bc,
       fa += fabs(s) * sqrt(r2);
       V += r6 * r6 - r6;
       P += s * r2;
+      Vabs += r6 * r6 + r6;
+      Pabs += fabs(s * r2);
     }
     frc[3 * i] = 4. * fx; frc[3 * i + 1] = 4. * fy; frc[3 * i + 2] = 4. * fz;
     fabs_sum[i] = 4. * fa;
   }
   scal[0] = V * 4. / 2.;
   scal[1] = P * 4. / 3. / 2.;
+  scal[2] = Vabs * 4. / 2.;
+  scal[3] = Pabs * 4. / 3. / 2.;
 }
 
 /* MDSystem.cpp:361-373 */

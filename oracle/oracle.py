@@ -74,14 +74,14 @@ class Oracle:
         return frc, dict(V=scal[0], Pvirial=scal[1], Pshear_conf=scal[2]), rdf
 
     def forces_f64(self, pos, L, bc):
-        """FP64 arbiter -> frc[N,3] float64, fabs_sum[N] float64, dict(V, Pvirial)"""
+        """FP64 arbiter -> frc[N,3] float64, fabs_sum[N] float64, dict(V, Pvirial, Vabs, Pabs)"""
         pos = _f4(pos)
         N = pos.size // 4
         frc = np.zeros((N, 3), dtype=np.float64)
         fa = np.zeros(N, dtype=np.float64)
-        scal = np.zeros(2, dtype=np.float64)
+        scal = np.zeros(4, dtype=np.float64)
         self.lib.ljo_forces_f64(N, _p(pos), L, bc, _p(frc), _p(fa), _p(scal))
-        return frc, fa, dict(V=scal[0], Pvirial=scal[1])
+        return frc, fa, dict(V=scal[0], Pvirial=scal[1], Vabs=scal[2], Pabs=scal[3])
 
     def parameters(self, N, rho, vel, V, Pvirial, Pshear_conf=0.0):
         vel = _f4(vel)

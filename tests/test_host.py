@@ -1,0 +1,168 @@
+"""CPU: host-side logic of the product — the C-ABI library loads and exports everything the header
+declares, fails loudly without a device, and its launch plan / exact-RDF constants are right.
+No compute is launched here (there is no GPU in the build container)."""
+import ctypes as C
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle.rdf_numpy import reference_r2
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "ljmd.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{]*\)\s*;", src)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    lib = pkg.ljmd.load_library()
+    declared = header_functions()
+    assert len(declared) >= 35
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/ljmd.h but not exported"
+    assert sorted(pkg.ljmd.API_SYMBOLS) == declared
+
+
+def test_no_cpu_fallback(pkg):
+    """Without a device the product refuses to construct; with a missing library it refuses to load."""
+    lib = pkg.ljmd.load_library()
+    if lib.ljmd_device_count() == 0:
+        with pytest.raises(pkg.ljmd.LJMDError, match="no CUDA device"):
+            pkg.ljmd.LJSystem(64)
+    with pytest.raises(pkg.ljmd.LJMDError, match="no CPU fallback"):
+        pkg.ljmd.load_library(os.path.join(ROOT, "does_not_exist.so"))
+
+
+def test_product_never_imports_oracle():
+    pkgdir = os.path.join(ROOT, "lennard-jones-cuda_b200")
+    for dirpath, _, files in os.walk(pkgdir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".c")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
+                assert "ljmd_oracle" not in text and "ljref_" not in text and "libljmd_ref" not in text, f
+
+
+def test_argument_errors(pkg):
+    lib = pkg.ljmd.load_library()
+    h = C.c_void_p()
+    assert lib.ljmd_create(C.byref(h), 1, 0.5, 1.0, 0, 0, C.c_float(0.1), 0) == 2      # N < 2
+    assert b"N must be" in lib.ljmd_last_error()
+    assert lib.ljmd_create(C.byref(h), 100, -1.0, 1.0, 0, 0, C.c_float(0.1), 0) == 2   # rho <= 0
+    assert lib.ljmd_create(C.byref(h), 100, 0.5, 1.0, 0, 7, C.c_float(0.1), 0) == 2    # bad bc
+    assert lib.ljmd_step(None, 0.004, 1, 0) == 2                                        # NULL handle
+    buf = (C.c_int * 6)()
+    assert lib.ljmd_plan(100, 3, 2, 148, buf) == 2
+
+
+def test_rdf_dr2_rule(pkg, oracle):
+    lib = pkg.ljmd.load_library()
+    for N in [2, 50, 100, 128, 399, 400, 401, 512, 4096, 65536, 1048576]:
+        assert float(lib.ljmd_rdf_dr2(N)) == oracle.rdf_dr2(N) == pkg.snapshots.rdf_dr2(N)
+    assert float(lib.ljmd_rdf_dr2(400)) == float(np.float32(0.1))
+    assert float(lib.ljmd_rdf_dr2(100)) == float(np.float32(0.2))
+
+
+@pytest.mark.parametrize("N,world", [(400, 1), (16384, 1), (65536, 1), (262144, 8), (1048576, 8), (1000003, 8),
+                                     (777, 4), (65536, 2)])
+def test_launch_plan_tiles_the_problem(pkg, N, world):
+    covered = 0
+    for r in range(world):
+        p = pkg.ljmd.plan(N, r, world, 148)
+        assert p["i_begin"] == covered
+        covered = p["i_end"]
+        n_loc = p["i_end"] - p["i_begin"]
+        assert p["i_tiles"] * p["i_tile"] >= n_loc > (p["i_tiles"] - 1) * p["i_tile"]
+        assert 1 <= p["j_splits"] <= max(1, N // 64)
+        assert p["force_ctas"] == p["i_tiles"] * p["j_splits"]
+        if N >= 16384:   # big enough to fill the machine: the last wave must be nearly full
+            slots = 148 * 4
+            waves = math.ceil(p["force_ctas"] / slots)
+            assert p["force_ctas"] / (waves * slots) > 0.93
+    assert covered == N
+
+
+def _emulate_image(d, L, thr1, thr2):
+    """numpy model of image_exact() in csrc/ljmd_force.cuh."""
+    a = np.abs(d)
+    n = np.zeros(d.shape, dtype=np.float64)
+    n[a >= thr1] = 1.0
+    far = a >= thr2
+    qf = (a[far].astype(np.float64) / L).astype(np.float32)
+    n[far] = np.trunc(qf + np.float32(0.5)).astype(np.float64)
+    n = np.where(d < 0, -n, n)
+    out = (d.astype(np.float64) - L * n).astype(np.float32)
+    return np.where(a < thr1, d, out)
+
+
+def _emulate_bin(r2, dr2):
+    """numpy model of rdf_bin_exact(): approximate quotient + exact-sign FMA residual fix-ups."""
+    dr2 = np.float32(dr2)
+    inv = np.float32(1.0) / dr2
+    b = np.floor(r2 * inv).astype(np.float64)
+    res = b * np.float64(dr2) - r2.astype(np.float64)             # exact in double (24x24-bit product)
+    too_big = res > 0
+    res2 = (b + 1.0) * np.float64(dr2) - r2.astype(np.float64)
+    too_small = (~too_big) & (res2 <= 0)
+    return b - too_big + too_small
+
+
+@pytest.mark.parametrize("N,rho", [(400, 0.05), (16384, 0.85), (65536, 1.1), (1048576, 0.3), (512, 0.316)])
+def test_exact_rdf_device_algorithm_matches_reference_semantics(pkg, N, rho):
+    L = math.pow(N / rho, 1.0 / 3.0)
+    thr1, thr2 = np.float32(pkg.ljmd.image_threshold(L, 1)), np.float32(pkg.ljmd.image_threshold(L, 2))
+    rng = np.random.Generator(np.random.PCG64(99))
+    n = 400_000
+    xi = (rng.random((n, 3)) * L * 1.2 - 0.1 * L).astype(np.float32)
+    xj = (rng.random((n, 3)) * L * 1.2 - 0.1 * L).astype(np.float32)
+    # a quarter of the samples sit within a few ulp of the image threshold, a quarter far outside
+    k = n // 4
+    xj[:k] = xi[:k] - np.float32(0.5 * L) + (rng.integers(-8, 9, (k, 3)) * np.spacing(np.float32(L))).astype(np.float32)
+    xj[k:2 * k] += (rng.integers(-3, 4, (k, 3)) * L).astype(np.float32)
+    d = xi - xj
+    img = _emulate_image(d, L, thr1, thr2)
+    ref = d.astype(np.float32)
+    nref = np.where(((d.astype(np.float64) / L).astype(np.float32)) > 0,
+                    np.trunc((d.astype(np.float64) / L).astype(np.float32) + np.float32(0.5)),
+                    np.trunc((d.astype(np.float64) / L).astype(np.float32) - np.float32(0.5)))
+    ref = (d.astype(np.float64) - L * nref.astype(np.float64)).astype(np.float32)
+    assert np.array_equal(img, ref)
+    # bins: random r^2 plus values clustered on bin edges
+    dr2 = pkg.snapshots.rdf_dr2(N)
+    r2 = reference_r2(xi, xj, L, 0)
+    edges = (np.arange(1, 300, dtype=np.float64) * np.float64(np.float32(dr2))).astype(np.float32)
+    near = np.concatenate([np.nextafter(edges, np.float32(0)), edges, np.nextafter(edges, np.float32(1e9))])
+    r2 = np.concatenate([r2, near, (rng.random(200_000) * 30).astype(np.float32)])
+    want = np.floor(r2.astype(np.float64) / np.float64(np.float32(dr2)))
+    assert np.array_equal(_emulate_bin(r2, dr2), want)
+
+
+def test_image_threshold_is_the_first_float_that_rounds_up(pkg):
+    for L in [7.3231346668217085, 19.999999999999996, 26.812275377187092, 151.76078099157598, 297.0]:
+        for k in (1, 2):
+            t = np.float32(pkg.ljmd.image_threshold(L, k))
+            below = np.nextafter(t, np.float32(0))
+            for x, want_ge in ((t, True), (below, False)):
+                qf = np.float32(np.float64(x) / L)
+                n = int(np.trunc(qf + np.float32(0.5)))
+                assert (n >= k) == want_ge
+
+
+def test_snapshots_are_deterministic_and_exact(pkg):
+    snap = pkg.snapshots
+    p1, v1 = snap.make("C2")
+    p2, v2 = snap.make("C2")
+    assert np.array_equal(p1, p2) and np.array_equal(v1, v2)
+    assert p1.shape == (16384, 4) and p1.dtype == np.float32
+    L = snap.box_length(16384, 0.85)
+    assert p1[:, :3].min() >= 0 and p1[:, :3].max() < L
+    v = v1[:, :3].astype(np.float64)
+    assert abs((v * v).sum() / (3 * 16384) - 1.0) < 1e-6 and np.abs(v.mean(axis=0)).max() < 1e-6
+    g = snap.random_gas(2000, 0.3, min_sep=0.9, seed=5)
+    from scipy.spatial import cKDTree
+    assert len(cKDTree(g[:, :3].astype(np.float64), boxsize=snap.box_length(2000, 0.3) + 1e-6).query_pairs(0.899)) == 0

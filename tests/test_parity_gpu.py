@@ -1,0 +1,398 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes -> libljmd.so), against
+the oracle on the same seeded inputs and against the golden fixtures generated from the reference.
+
+Tolerances (north star: <= 1e-5 relative in FP32, RDF bit-exact):
+  * forces: per particle, max-norm error divided by sum_j |f_ij| (the scale the cancellation in a
+    dense phase hides).  Against the FP64 arbiter (exact arithmetic on the same float
+    inputs) the bound is a flat FORCE_TOL = 1e-5.  Against the reference CPU path the bound is
+    FORCE_TOL plus the reference's own distance from the arbiter on that particle: the reference
+    subtracts coordinates in float BEFORE imaging, so a pair that interacts across the periodic
+    boundary carries an error of ulp(L)/2 in its separation (3e-5 on this metric at L = 20), while
+    the CUDA path keeps L*2^-33.  The system-wide relative L2 error against the reference is < 1e-5.
+  * V and the virial: 1e-5 of the sum of |pair terms| (V itself can cancel to ~0).
+  * K, T: 1e-6 relative (same float squares, double sums in a different order).
+  * RDF and speed-histogram bins: bit-exact.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+from oracle.oracle import Reference, reference_available
+from oracle.rdf_numpy import rdf_counts as rdf_numpy
+
+pytestmark = pytest.mark.gpu
+
+FORCE_TOL = 1e-5
+SCALAR_TOL = 1e-5
+
+
+def make_system(pkg, g_or_cfg):
+    c = g_or_cfg
+    return pkg.ljmd.LJSystem(c["N"], T0=c["T0"], rho=c["rho"], canonical=c["canonical"], bc=c["bc"])
+
+
+def check_forces(oracle, pos, L, bc, dr2, f_gpu, sc_gpu, rdf_gpu=None, ref_force=None):
+    """Forces / V / virial / RDF of one evaluation against oracle + arbiter.  Returns error summary."""
+    N = pos.shape[0]
+    f64, fabs_sum, sc64 = oracle.forces_f64(pos, L, bc)
+    if ref_force is None:
+        ref_force, sc_ref, rdf_ref = oracle.forces(pos, L, bc, dr2)
+    else:
+        _, sc_ref, rdf_ref = oracle.forces(pos, L, bc, dr2)
+    fg = f_gpu[:, :3].astype(np.float64)
+    fr = ref_force[:, :3].astype(np.float64)
+    err_arb = np.abs(fg - f64).max(axis=1) / fabs_sum
+    err_ref = np.abs(fg - fr).max(axis=1) / fabs_sum
+    ref_own = np.abs(fr - f64).max(axis=1) / fabs_sum
+    assert err_arb.max() <= FORCE_TOL, f"force vs FP64 arbiter: {err_arb.max():.3e}"
+    assert (err_ref <= FORCE_TOL + ref_own).all(), f"force vs reference: {err_ref.max():.3e}"
+    nrm = max(np.linalg.norm(fr), 1e-300)
+    rel_l2 = np.linalg.norm(fg - fr) / nrm
+    if np.linalg.norm(fr) > 1e-3 * fabs_sum.sum() / np.sqrt(N):   # skip when the net forces cancel (perfect lattice)
+        assert rel_l2 <= FORCE_TOL + np.linalg.norm(fr - f64) / nrm, f"relative L2 vs reference: {rel_l2:.3e}"
+    assert abs(sc_gpu["V"] - sc_ref["V"]) <= SCALAR_TOL * sc64["Vabs"]
+    assert abs(sc_gpu["Pvirial"] - sc_ref["Pvirial"]) <= SCALAR_TOL * sc64["Pabs"]
+    # force.w carries the per-particle potential sum (reference GPU layout, MDSystem.cu:52)
+    assert abs(2.0 * f_gpu[:, 3].astype(np.float64).sum() - sc_ref["V"]) <= SCALAR_TOL * sc64["Vabs"]
+    if rdf_gpu is not None:
+        assert np.array_equal(rdf_gpu, rdf_ref), "RDF bins differ from the reference CPU path"
+    return dict(err_arb=err_arb.max(), err_ref=err_ref.max(), ref_own=ref_own.max(), rel_l2=rel_l2)
+
+
+# ------------------------------------------------------------------ golden fixtures (reference outputs)
+@pytest.mark.parametrize("name", golden_names())
+def test_evaluation_matches_golden(pkg, oracle, gpu_lib, name):
+    g = load_golden(name)
+    with make_system(pkg, g) as s:
+        assert s.L == g["s0"]["L"] and s.rdf_dr2 == g["dr2"]
+        s.set_state(g["pos0"], g["vel0"])
+        pos, vel, frc = s.get_state()
+        assert np.array_equal(pos, g["pos0"]) and np.array_equal(vel, g["vel0"])
+        sc = s.scalars()
+        rdf = s.rdf_counts()
+        assert np.array_equal(rdf, g["rdf0"]), "RDF bins differ from the golden reference output"
+        check_forces(oracle, g["pos0"], s.L, g["bc"], g["dr2"], frc, sc, rdf, ref_force=g["force0"])
+        for k in ("K", "T"):
+            assert abs(sc[k] - g["s0"][k]) <= 1e-6 * abs(g["s0"][k]), k
+        f64, fabs_sum, sc64 = oracle.forces_f64(g["pos0"], s.L, g["bc"])
+        assert abs(sc["V"] - g["s0"]["V"]) <= SCALAR_TOL * sc64["Vabs"]
+        vol = g["N"] / g["rho"]
+        assert abs(sc["P"] - g["s0"]["P"]) <= SCALAR_TOL * (sc64["Pabs"] + g["N"] * g["s0"]["T"]) / vol
+        assert abs(sc["U"] - g["s0"]["U"]) <= SCALAR_TOL * (sc64["Vabs"] + g["s0"]["K"])
+        assert sc["av_iters"] == 0 and sc["t"] == 0.0
+        assert np.array_equal(s.velocity_histogram(0.12, 101), g["velhist0"])
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_steps_match_golden(pkg, oracle, gpu_lib, name):
+    g = load_golden(name)
+    with make_system(pkg, g) as s:
+        s.set_state(g["pos0"], g["vel0"])
+        s.step(g["dt"], g["steps"])
+        pos, vel, frc = s.get_state()
+        sc = s.scalars()
+        # a few steps: trajectories differ only through force rounding (1e-7 relative per step)
+        assert np.abs(pos[:, :3] - g["pos1"][:, :3]).max() <= 2e-6 * max(1.0, s.L)
+        vscale = np.abs(g["vel1"][:, :3]).max()
+        assert np.abs(vel[:, :3] - g["vel1"][:, :3]).max() <= 2e-5 * vscale
+        assert np.array_equal(pos[:, 3], g["pos0"][:, 3])           # w = L/150 is carried along untouched
+        f64, fabs_sum, sc64 = oracle.forces_f64(g["pos1"], s.L, g["bc"])
+        assert abs(sc["V"] - g["s1"]["V"]) <= 5 * SCALAR_TOL * sc64["Vabs"]
+        assert abs(sc["K"] - g["s1"]["K"]) <= 1e-5 * g["s1"]["K"]
+        assert abs(sc["T"] - g["s1"]["T"]) <= 1e-5 * g["s1"]["T"]
+        assert abs(sc["U"] - g["s1"]["U"]) <= 5 * SCALAR_TOL * (sc64["Vabs"] + g["s1"]["K"])
+        assert sc["av_iters"] == g["steps"]
+        assert abs(sc["t"] - g["s1"]["t"]) < 1e-12
+        assert abs(sc["av_U_tot"] - g["s1"]["av_U_tot"]) <= 5 * SCALAR_TOL * g["steps"] * (sc64["Vabs"] + g["s1"]["K"])
+        assert abs(sc["av_T_tot"] - g["s1"]["av_T_tot"]) <= 1e-5 * g["s1"]["av_T_tot"]
+        # the RDF of the last evaluation, rebuilt lazily: equal to the golden one up to pairs that the
+        # 1e-7 trajectory difference moved across a bin edge
+        rdf = s.rdf_counts()
+        assert np.abs(rdf.astype(np.int64) - g["rdf1"]).sum() <= max(8, 2e-4 * g["rdf1"].sum())
+        assert rdf.sum() % 2 == 0
+
+
+def oracle_step_from(oracle, g, pos, vel, frc, dt, canonical, bc):
+    return oracle.integrate(g["N"], g["rho"], g["T0"], canonical, bc, dt, pos, vel, frc, nsteps=1, dr2=g["dr2"])
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_single_step_from_own_state_is_tight(pkg, oracle, gpu_lib, name):
+    """One Integrate from the GPU's own (pos, vel, force): the drift is bit-identical to the CPU's, so the
+    evaluation positions agree exactly, the post-step RDF is bit-exact and positions match to the bit."""
+    g = load_golden(name)
+    with make_system(pkg, g) as s:
+        s.set_state(g["pos0"], g["vel0"])
+        s.step(g["dt"], 2)
+        pos, vel, frc = s.get_state()
+        s.step(g["dt"], 1, rdf_every=1)
+        pos2, vel2, frc2 = s.get_state()
+        rdf2 = s.rdf_counts()
+        sc2 = s.scalars()
+        opos, ovel, ofrc, osc, ordf = oracle_step_from(oracle, g, pos, vel, frc, g["dt"], g["canonical"], g["bc"])
+        assert np.array_equal(pos2[:, :3], opos[:, :3]), "drift + boundary wrap must be bit-identical"
+        assert np.array_equal(rdf2, ordf), "post-step RDF must be bit-exact"
+        fscale = np.abs(ofrc[:, :3]).max()
+        assert np.abs(vel2[:, :3] - ovel[:, :3]).max() <= 1e-6 * max(1.0, g["dt"] * fscale)
+        f64, fabs_sum, sc64 = oracle.forces_f64(opos, s.L, g["bc"])
+        assert abs(sc2["K"] - osc["K"]) <= 1e-6 * osc["K"]
+        assert abs(sc2["V"] - osc["V"]) <= SCALAR_TOL * sc64["Vabs"]
+        acc, n = s.rdf_accum()
+        assert n == 1 and np.array_equal(acc, ordf.astype(np.int64))
+
+
+def test_tvn_chi_and_trial_temperature(pkg, oracle, gpu_lib):
+    g = load_golden("solid_tvn_periodic")
+    with make_system(pkg, g) as s:
+        s.set_state(g["pos0"], g["vel0"])
+        pos, vel, frc = s.get_state()
+        s.step(g["dt"], 1)
+        sc = s.scalars()
+        # restate MDSystem.cpp:484-499 on the host from the GPU's own forces
+        _, _, f1 = s.get_state(pos=False, vel=False)
+        tF = np.float32(0.5) * frc[:, :3] + np.float32(0.5) * f1[:, :3]
+        tV = (vel[:, :3].astype(np.float64) + g["dt"] * tF.astype(np.float64) / 2.0).astype(np.float32)
+        Tkin = float(oracle.lib.ljo_kinetic_temperature(g["N"], np.ascontiguousarray(
+            np.concatenate([tV, np.zeros((g["N"], 1), np.float32)], axis=1)).ctypes.data_as(C.c_void_p)))
+        assert abs(sc["Tkin_trial"] - Tkin) <= 1e-12 * Tkin
+        assert abs(sc["chi"] - np.sqrt(g["T0"] / Tkin)) <= 1e-12
+
+
+# ------------------------------------------------------------------ live oracle at larger N
+@pytest.mark.parametrize("N,T,rho,canonical,bc,kind", [
+    (4096, 1.0, 1.1, 1, 0, "lattice"),      # solid, C3-like
+    (4096, 1.0, 0.01, 0, 1, "lattice"),     # gas, hard wall, C4-like
+    (3000, 1.0, 0.3, 1, 0, "gas"),          # random placement, ragged N
+    (2048, 1.0, 0.0006, 0, 0, "gas"),       # L ~ 150: C5-sized box, sparse
+    (16384, 1.0, 0.85, 0, 0, "lattice"),    # C2 at full size (oracle ~10 s)
+])
+def test_evaluation_matches_oracle_live(pkg, oracle, gpu_lib, N, T, rho, canonical, bc, kind):
+    snap = pkg.snapshots
+    pos = snap.random_gas(N, rho, seed=11, periodic=bc == 0) if kind == "gas" else snap.lattice(N, rho, 0.05, seed=11)
+    vel = snap.velocities(N, T, seed=11)
+    with pkg.ljmd.LJSystem(N, T0=T, rho=rho, canonical=canonical, bc=bc) as s:
+        s.set_state(pos, vel)
+        _, _, frc = s.get_state()
+        check_forces(oracle, pos, s.L, bc, s.rdf_dr2, frc, s.scalars(), s.rdf_counts())
+
+
+@pytest.mark.parametrize("N", [2, 3, 33, 511, 512, 513, 1025, 2049])
+@pytest.mark.parametrize("bc", [0, 1])
+def test_ragged_sizes(pkg, oracle, gpu_lib, N, bc):
+    rho = 0.5
+    pos = pkg.snapshots.lattice(N, rho, 0.1, seed=N)
+    vel = pkg.snapshots.velocities(N, 1.2, seed=N) if N > 2 else np.zeros((N, 4), np.float32)
+    with pkg.ljmd.LJSystem(N, T0=1.2, rho=rho, canonical=0, bc=bc) as s:
+        s.set_state(pos, vel)
+        _, _, frc = s.get_state()
+        check_forces(oracle, pos, s.L, bc, s.rdf_dr2, frc, s.scalars(), s.rdf_counts())
+
+
+def test_positions_outside_the_box(pkg, oracle, gpu_lib):
+    """Unwrapped coordinates (up to several box lengths out): forces still follow the minimum image and the
+    RDF still reproduces fast_round() for |n| >= 2."""
+    N, rho = 700, 0.6
+    pos = pkg.snapshots.lattice(N, rho, 0.1, seed=5)
+    L = pkg.snapshots.box_length(N, rho)
+    shift = np.zeros((N, 3), np.float32)
+    shift[::3, 0] = np.float32(0.4 * L)
+    shift[1::5, 1] = np.float32(-1.3 * L)
+    shift[2::7, 2] = np.float32(3.0 * L)
+    pos[:, :3] += shift
+    with pkg.ljmd.LJSystem(N, T0=1.0, rho=rho, canonical=0, bc=0) as s:
+        s.set_state(pos, pkg.snapshots.velocities(N, 1.0))
+        _, _, frc = s.get_state()
+        f64, fabs_sum, sc64 = oracle.forces_f64(pos, s.L, 0)
+        err = np.abs(frc[:, :3].astype(np.float64) - f64).max(axis=1) / fabs_sum
+        assert err.max() <= FORCE_TOL
+        _, _, rdf_ref = oracle.forces(pos, s.L, 0, s.rdf_dr2)
+        assert np.array_equal(s.rdf_counts(), rdf_ref)
+
+
+# ------------------------------------------------------------------ API behaviour
+def test_integrate_host_equals_device_resident_step(pkg, gpu_lib):
+    g = load_golden("liquid_evn_periodic")
+    with make_system(pkg, g) as a, make_system(pkg, g) as b:
+        a.set_state(g["pos0"], g["vel0"])
+        b.set_state(g["pos0"], g["vel0"])
+        pos, vel = g["pos0"].copy(), g["vel0"].copy()
+        frc = np.zeros_like(pos)
+        for _ in range(3):
+            a.step(g["dt"], 1)
+            b.integrate_host(g["dt"], pos, vel, frc)
+        pa, va, fa = a.get_state()
+        assert np.array_equal(pa, pos) and np.array_equal(va, vel) and np.array_equal(fa, frc)
+        assert a.scalars() == b.scalars()
+
+
+def test_runs_are_deterministic(pkg, gpu_lib):
+    g = load_golden("mixed_tvn_periodic")
+    outs = []
+    for _ in range(2):
+        with make_system(pkg, g) as s:
+            s.set_state(g["pos0"], g["vel0"])
+            s.step(g["dt"], 25, rdf_every=5)
+            outs.append((s.get_state(), s.scalars(), s.rdf_accum()))
+    (s1, sc1, (r1, n1)), (s2, sc2, (r2, n2)) = outs
+    assert all(np.array_equal(x, y) for x, y in zip(s1, s2))
+    assert sc1 == sc2 and n1 == n2 == 5 and np.array_equal(r1, r2)
+
+
+def test_live_switches(pkg, oracle, gpu_lib):
+    """canonical / boundary / T0 flipped between steps, as semiGCEfluctuations.cpp:58,66 and the GUI do."""
+    g = load_golden("liquid_evn_periodic")
+    with make_system(pkg, g) as s:
+        s.set_state(g["pos0"], g["vel0"])
+        pos, vel, frc = s.get_state()
+        s.set_canonical(True)
+        s.set_T0(1.3)
+        s.step(g["dt"], 1)
+        g2 = dict(g, T0=1.3)
+        opos, ovel, ofrc, osc, _ = oracle_step_from(oracle, g2, pos, vel, frc, g["dt"], 1, 0)
+        p1, v1, f1 = s.get_state()
+        assert np.array_equal(p1[:, :3], opos[:, :3])
+        assert np.abs(v1[:, :3] - ovel[:, :3]).max() <= 1e-5
+        s.set_canonical(False)
+        s.set_boundary(1)
+        s.step(g["dt"], 1)
+        opos2, ovel2, _, _, _ = oracle_step_from(oracle, g, p1, v1, f1, g["dt"], 0, 1)
+        p2, v2, _ = s.get_state()
+        assert np.array_equal(p2[:, :3], opos2[:, :3])
+        assert np.abs(v2[:, :3] - ovel2[:, :3]).max() <= 1e-5
+        s.set_boundary(0)
+        s.compute_forces(with_rdf=True)
+        _, _, rdf_ref = oracle.forces(p2, s.L, 0, s.rdf_dr2)
+        assert np.array_equal(s.rdf_counts(), rdf_ref)
+
+
+def test_set_velocities_and_reset_averaging(pkg, oracle, gpu_lib):
+    g = load_golden("c1_gas_tvn_periodic")
+    with make_system(pkg, g) as s:
+        s.set_state(g["pos0"], g["vel0"])
+        s.step(g["dt"], 3)
+        assert s.scalars()["av_iters"] == 3
+        s.reset_averaging()
+        sc = s.scalars()
+        assert sc["av_iters"] == 0 and sc["av_U_tot"] == 0.0
+        _, vel, _ = s.get_state()
+        vel2 = vel.copy()
+        vel2[:, :3] *= np.float32(1.1)
+        s.set_velocities(vel2)
+        sc2 = s.scalars()
+        par = oracle.parameters(g["N"], g["rho"], vel2, sc["V"], sc["Pvirial"])
+        assert abs(sc2["K"] - par["K"]) <= 1e-9 * par["K"] and sc2["V"] == sc["V"]
+        assert abs(sc2["P"] - par["P"]) <= 1e-9 * abs(par["P"]) and sc2["av_iters"] == 0
+
+
+def test_legacy_seam(pkg, oracle, gpu_lib):
+    """The six symbols MDSystem.cpp links against (MDSystem.cpp:9-25), driven the way its GPU branch does
+    (MDSystem.cpp:240-251)."""
+    g = load_golden("liquid_evn_periodic")
+    N = g["N"]
+    L = oracle.box_length(N, g["rho"])
+    lib = gpu_lib
+    d_pos, d_frc = C.c_void_p(), C.c_void_p()
+    lib.allocateArray(C.byref(d_pos), N)
+    lib.allocateArray(C.byref(d_frc), N)
+    pos = np.ascontiguousarray(g["pos0"])
+    lib.copyArrayToDevice(d_pos, pos.ctypes.data_as(C.c_void_p), N)
+    pressure = C.c_float(0)
+    rdf = np.zeros(256, dtype=np.int32)
+    frc = np.zeros((N, 4), dtype=np.float32)
+    for periodic in (1, 0):
+        lib.calculateNForces(d_pos, d_frc, C.byref(pressure), N, C.c_float(L), periodic,
+                             rdf.ctypes.data_as(C.POINTER(C.c_int)), C.c_float(g["dr2"]), 256, 1)
+        lib.copyArrayFromDevice(frc.ctypes.data_as(C.c_void_p), d_frc, 0, N)
+        Lf = float(np.float32(L))                      # the seam carries L as float (MDSystem.cpp:246)
+        bc = 0 if periodic else 2
+        fr, sc, rdf_ref = oracle.forces(pos, Lf, bc, g["dr2"])
+        f64, fabs_sum, sc64 = oracle.forces_f64(pos, Lf, bc)
+        err = np.abs(frc[:, :3].astype(np.float64) - f64).max(axis=1) / fabs_sum
+        assert err.max() <= FORCE_TOL
+        assert np.array_equal(rdf, rdf_ref)
+        assert abs(pressure.value - sc["Pvirial"]) <= SCALAR_TOL * sc64["Pabs"]
+        assert abs(2.0 * frc[:, 3].astype(np.float64).sum() - sc["V"]) <= SCALAR_TOL * sc64["Vabs"]   # MDSystem.cpp:340-346
+    lib.deleteArray(d_pos)
+    lib.deleteArray(d_frc)
+    lib.threadExit()
+
+
+@pytest.mark.skipif(not reference_available(), reason="oracle/_ref/libljmd_ref.so not built")
+def test_long_run_statistics_match_reference(pkg, gpu_lib):
+    """EVN energy drift and TVN <T>, <P> over a few hundred steps next to the reference CPU path run on
+    the same snapshot (N = 500 liquid): same order of drift, averages within the run-to-run spread."""
+    g = load_golden("liquid_evn_periodic")
+    nsteps = 400
+    out = {}
+    for canonical in (0, 1):
+        ref = Reference(g["N"], g["T0"], g["rho"], canonical, 0)
+        ref.set_state(g["pos0"], g["vel0"])
+        u0 = ref.scalars()["U"]
+        ref.integrate(g["dt"], nsteps)
+        rs = ref.scalars()
+        with pkg.ljmd.LJSystem(g["N"], T0=g["T0"], rho=g["rho"], canonical=canonical, bc=0) as s:
+            s.set_state(g["pos0"], g["vel0"])
+            s.step(g["dt"], nsteps)
+            gs = s.scalars()
+        out[canonical] = (u0, rs, gs)
+    u0, rs, gs = out[0]
+    N = g["N"]
+    drift_ref, drift_gpu = abs(rs["U"] - u0) / N, abs(gs["U"] - u0) / N
+    assert drift_gpu <= max(3 * drift_ref, 2e-3)
+    assert abs(gs["av_U_tot"] - rs["av_U_tot"]) / nsteps / N <= 2e-3
+    u0, rs, gs = out[1]
+    assert abs(gs["av_T_tot"] - rs["av_T_tot"]) / nsteps <= 2e-3       # TVN holds T* ~ T0
+    assert abs(gs["T"] - g["T0"]) <= 5e-3
+    assert abs(gs["av_p_tot"] - rs["av_p_tot"]) / nsteps <= 0.05 * max(1.0, abs(rs["av_p_tot"]) / nsteps)
+
+
+# ------------------------------------------------------------------ full-size properties (no O(N^2) oracle)
+def test_full_size_properties_c3(pkg, gpu_lib):
+    """N = 65 536 solid (C3): Newton's third law, RDF against the k-d-tree restatement (bit-exact),
+    potential energy against a cutoff-free pair sum is out of reach, so V is cross-checked through the
+    identity V = 2 * sum_i force.w and through invariance under a lattice-vector relabelling."""
+    cfg = pkg.snapshots.CONFIGS["C3"]
+    N, rho = cfg["N"], cfg["rho"]
+    pos, vel = pkg.snapshots.make("C3")
+    with pkg.ljmd.LJSystem(N, T0=cfg["T"], rho=rho, canonical=1, bc=0) as s:
+        s.set_state(pos, vel)
+        _, _, frc = s.get_state()
+        sc = s.scalars()
+        f = frc[:, :3].astype(np.float64)
+        fabs = np.abs(f).sum()
+        assert np.abs(f.sum(axis=0)).max() <= 1e-6 * fabs          # sum of all forces vanishes
+        assert abs(2.0 * frc[:, 3].astype(np.float64).sum() - sc["V"]) <= 1e-6 * abs(sc["V"])
+        rdf = s.rdf_counts()
+        assert np.array_equal(rdf.astype(np.int64), rdf_numpy(pos, s.L, 0, s.rdf_dr2))
+        # relabel: reverse particle order -> same V, virial (to rounding), same RDF, forces permuted
+        s.set_state(pos[::-1].copy(), vel[::-1].copy())
+        _, _, frc_r = s.get_state()
+        sc_r = s.scalars()
+        assert abs(sc_r["V"] - sc["V"]) <= 1e-6 * abs(sc["V"])
+        assert abs(sc_r["Pvirial"] - sc["Pvirial"]) <= 1e-6 * abs(sc["Pvirial"])
+        assert np.array_equal(s.rdf_counts(), rdf)
+        scale = np.abs(f).max()
+        assert np.abs(frc_r[::-1, :3] - frc[:, :3]).max() <= 1e-4 * scale
+        # energy conservation over 20 EVN steps
+        s.set_canonical(False)
+        s.set_state(pos, vel)
+        u0 = s.scalars()["U"]
+        s.step(0.004, 20)
+        assert abs(s.scalars()["U"] - u0) / N <= 2e-3
+
+
+def test_full_size_hardwall_c4_slice(pkg, gpu_lib):
+    """Hard-wall gas at N = 262 144 (C4): forces vanish in sum, RDF equals the k-d-tree restatement."""
+    cfg = pkg.snapshots.CONFIGS["C4"]
+    N, rho = cfg["N"], cfg["rho"]
+    pos, vel = pkg.snapshots.make("C4")
+    with pkg.ljmd.LJSystem(N, T0=cfg["T"], rho=rho, canonical=0, bc=1) as s:
+        s.set_state(pos, vel)
+        _, _, frc = s.get_state()
+        f = frc[:, :3].astype(np.float64)
+        assert np.abs(f.sum(axis=0)).max() <= 1e-6 * max(np.abs(f).sum(), 1e-30)
+        assert np.array_equal(s.rdf_counts().astype(np.int64), rdf_numpy(pos, s.L, 1, s.rdf_dr2))
+        vh = s.velocity_histogram(0.12, 101)
+        assert vh.sum() == N

@@ -1,0 +1,261 @@
+// Developer tool (not part of the product library): A/B timings of force-kernel variants and a few
+// pipe-throughput microbenchmarks on the B200.  Build: make -C tools.  Run on the GPU box:
+//   tools/tune_force [N] [reps]
+// Prints one line per variant: ms per launch, ordered pairs/s, and the algorithmic TFLOP/s
+// (37 flop/pair periodic, 25 open).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../lennard-jones-cuda_b200/csrc/ljmd_force.cuh"
+using namespace ljmd;
+
+#define CK(x)                                                                         \
+  do {                                                                                \
+    cudaError_t e_ = (x);                                                             \
+    if (e_ != cudaSuccess) {                                                          \
+      fprintf(stderr, "%s:%d %s: %s\n", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); \
+      exit(1);                                                                        \
+    }                                                                                 \
+  } while (0)
+
+// ------------------------------------------------------------------ pipe microbenchmarks
+// 8 independent chains per thread; `iters` loop trips; results kept live through a final store.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_micro(float* out, int iters, float seed) {
+  float a[8], b[8];
+  int ia[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { a[k] = seed + k + threadIdx.x; b[k] = seed * 0.5f + k; ia[k] = (int)threadIdx.x * 7 + k; }
+  const float c = seed * 1.0001f, d = seed * 0.9999f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (MODE == 0) {            // FFMA (3 distinct source registers)
+        asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[k]) : "f"(c), "f"(d));
+        asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(b[k]) : "f"(c), "f"(d));
+      } else if (MODE == 1) {     // FFMA2: a[k],b[k] as one packed pair
+        unsigned long long v, cc, dd;
+        asm volatile("mov.b64 %0, {%1,%2};" : "=l"(v) : "f"(a[k]), "f"(b[k]));
+        asm volatile("mov.b64 %0, {%1,%1};" : "=l"(cc) : "f"(c));
+        asm volatile("mov.b64 %0, {%1,%1};" : "=l"(dd) : "f"(d));
+        asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(v) : "l"(cc), "l"(dd));
+        asm volatile("mov.b64 {%0,%1}, %2;" : "=f"(a[k]), "=f"(b[k]) : "l"(v));
+      } else if (MODE == 2) {     // I2FP + IADD (the conversion needs a changing integer)
+        asm volatile("add.s32 %0, %0, %1;" : "+r"(ia[k]) : "r"(it));
+        float t;
+        asm volatile("cvt.rn.f32.s32 %0, %1;" : "=f"(t) : "r"(ia[k]));
+        a[k] += t;                // FADD to keep the result live
+      } else if (MODE == 3) {     // MUFU.RCP
+        asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(a[k]));
+      } else if (MODE == 4) {     // IADD3 only
+        asm volatile("add.s32 %0, %0, %1;" : "+r"(ia[k]) : "r"(it));
+        asm volatile("sub.s32 %0, %0, %1;" : "+r"(ia[k]) : "r"(k));
+      } else if (MODE == 5) {     // LJ-like mix per 2 lanes: 7 FFMA2-class + 3*2 IADD + 3*2 I2FP + 2 MUFU (approx.)
+        unsigned long long v, cc;
+        asm volatile("mov.b64 %0, {%1,%2};" : "=l"(v) : "f"(a[k]), "f"(b[k]));
+        asm volatile("mov.b64 %0, {%1,%1};" : "=l"(cc) : "f"(c));
+#pragma unroll
+        for (int r = 0; r < 7; ++r) asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(v) : "l"(cc));
+        asm volatile("mov.b64 {%0,%1}, %2;" : "=f"(a[k]), "=f"(b[k]) : "l"(v));
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          asm volatile("sub.s32 %0, %0, %1;" : "+r"(ia[k]) : "r"(it + r));
+          float t;
+          asm volatile("cvt.rn.f32.s32 %0, %1;" : "=f"(t) : "r"(ia[k]));
+          if (r & 1) a[k] += t; else b[k] += t;
+        }
+        asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(a[k]));
+        asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(b[k]));
+      }
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += a[k] + b[k] + (float)ia[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <int MODE>
+static void run_micro(const char* name, double ops_per_iter_per_thread, int sms, float* d_out) {
+  const int iters = 4096, blocks = sms * 8, threads = 256;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  k_micro<MODE><<<blocks, threads>>>(d_out, 64, 1.0f);
+  CK(cudaDeviceSynchronize());
+  CK(cudaEventRecord(e0));
+  k_micro<MODE><<<blocks, threads>>>(d_out, iters, 1.0f);
+  CK(cudaEventRecord(e1));
+  CK(cudaEventSynchronize(e1));
+  float ms;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  const double ops = ops_per_iter_per_thread * iters * (double)blocks * threads;
+  printf("micro %-34s %8.3f ms  %8.2f Gop/s/SM  (= %6.1f thread-ops/clk/SM at 1.9 GHz)\n", name, ms,
+         ops / (ms * 1e-3) / sms / 1e9, ops / (ms * 1e-3) / sms / 1.9e9);
+}
+
+// ------------------------------------------------------------------ force-kernel variants
+struct Problem {
+  int N;
+  double L;
+  uint4* upos;
+  float4* posf;
+  float4* fpart;
+  double* blockW;
+  unsigned long long* rdf;
+  int sms;
+};
+
+static int pick_split(int n_it, int N, int sms, int minb) {
+  const double ovh = 128.;
+  const long long slots = (long long)sms * minb;
+  int best = 1;
+  double bc = 1e300;
+  for (int s = 1; s <= std::max(1, N / 64) && s <= 8 * sms; ++s) {
+    const long long waves = ((long long)n_it * s + slots - 1) / slots;
+    const double cost = (double)waves * ((double)N / s + ovh);
+    if (cost < bc * 0.999) { bc = cost; best = s; }
+  }
+  return best;
+}
+
+template <typename V, bool PERIODIC, bool RDF, int THREADS, int MINB, int NPAIR, int UNROLL>
+static void run_variant(const Problem& pb, const char* tag, int reps, int tile_j, std::vector<float4>* keep) {
+  auto kern = k_force<V, PERIODIC, RDF, THREADS, MINB, NPAIR, UNROLL>;
+  const size_t smem = force_smem_bytes(PERIODIC, RDF, tile_j, THREADS);
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaFuncAttributes fa;
+  CK(cudaFuncGetAttributes(&fa, kern));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
+  const int itile = THREADS * 2 * NPAIR;
+  const int n_it = (pb.N + itile - 1) / itile;
+  const int S = pick_split(n_it, pb.N, pb.sms, occ > 0 ? occ : MINB);
+  ForceParams fp;
+  memset(&fp, 0, sizeof(fp));
+  fp.jrec = PERIODIC ? pb.upos : reinterpret_cast<const uint4*>(pb.posf);
+  fp.posf = pb.posf; fp.fpart = pb.fpart; fp.blockW = pb.blockW; fp.rdf = pb.rdf;
+  fp.N = pb.N; fp.i_begin = 0; fp.i_end = pb.N; fp.ilocal_cap = pb.N; fp.tile_j = tile_j;
+  const double k2 = 4294967296.0 / pb.L;
+  fp.c2 = PERIODIC ? (float)(k2 * k2) : 1.f;
+  fp.fscale = PERIODIC ? (float)(4.0 * pb.L / 4294967296.0) : 4.f;
+  fp.cut_fast = (float)(PERIODIC ? 25.6 * 1.001 * k2 * k2 : 25.6 * 1.001);
+  fp.L = pb.L; fp.thr1 = (float)(0.5 * pb.L); fp.thr2 = (float)(1.5 * pb.L); fp.dr2 = 0.1f; fp.inv_dr2 = 10.f;
+  dim3 grid(n_it, S);
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  kern<<<grid, THREADS, smem>>>(fp);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  float best = 1e30f, sum = 0.f;
+  for (int r = 0; r < reps; ++r) {
+    CK(cudaEventRecord(e0));
+    kern<<<grid, THREADS, smem>>>(fp);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    best = std::min(best, ms);
+    sum += ms;
+  }
+  const double pairs = (double)pb.N * (pb.N - 1);
+  const double flop = PERIODIC ? 37. : 25.;
+  // checksum of the summed partial forces of particle 12345 against the first variant run
+  std::vector<float4> h((size_t)S * pb.N);
+  CK(cudaMemcpy(h.data(), pb.fpart, h.size() * 16, cudaMemcpyDeviceToHost));
+  std::vector<float4> f(pb.N);
+  for (int i = 0; i < pb.N; ++i) {
+    float4 a = h[i];
+    for (int s = 1; s < S; ++s) { float4 g = h[(size_t)s * pb.N + i]; a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w; }
+    f[i] = a;
+  }
+  double maxdiff = 0., scale = 0.;
+  if (keep->empty()) *keep = f;
+  for (int i = 0; i < pb.N; ++i) {
+    maxdiff = std::max(maxdiff, (double)fabsf(f[i].x - (*keep)[i].x));
+    scale = std::max(scale, (double)fabsf((*keep)[i].x));
+  }
+  printf("force %-44s regs %3d occ %d grid %4dx%-3d smem %6zu | best %8.4f ms avg %8.4f ms | %7.3f Gpairs/s %6.2f TFLOP/s "
+         "| maxdiff %.2e/%.2e\n",
+         tag, fa.numRegs, occ, n_it, S, smem, best, sum / reps, pairs / (best * 1e-3) / 1e9,
+         pairs * flop / (best * 1e-3) / 1e12, maxdiff, scale);
+  fflush(stdout);
+}
+
+int main(int argc, char** argv) {
+  const int N = argc > 1 ? atoi(argv[1]) : 65536;
+  const int reps = argc > 2 ? atoi(argv[2]) : 5;
+  const double rho = 1.1;
+  const double L = pow(N / rho, 1. / 3.);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, 0));
+  const int sms = prop.multiProcessorCount;
+  printf("device %s, %d SMs, clock %.0f MHz; N=%d L=%.4f\n", prop.name, sms, prop.clockRate / 1e3, N, L);
+
+  float* d_out;
+  CK(cudaMalloc(&d_out, (size_t)sms * 8 * 256 * 4));
+  run_micro<0>("FFMA x2 (scalar, 3-reg)", 16, sms, d_out);
+  run_micro<1>("FFMA2 x1 (2 lanes)", 16, sms, d_out);          // counted in scalar-FMA equivalents: 8 FFMA2 = 16
+  run_micro<2>("IADD + I2FP + FADD", 8, sms, d_out);           // counted in I2FP ops
+  run_micro<3>("MUFU.RCP", 8, sms, d_out);
+  run_micro<4>("IADD3 x2", 16, sms, d_out);
+  run_micro<5>("LJ mix (per 2 pairs: 7 FFMA2,6 IADD,6 I2FP,2 MUFU)", 16, sms, d_out);  // counted in pairs*... see source
+
+  // lattice + jitter, deterministic LCG
+  std::vector<float4> hp(N);
+  std::vector<uint4> hu(N);
+  const int ns = (int)ceil(pow((double)N, 1. / 3.));
+  const double dL = L / ns;
+  unsigned long long st = 88172645463325252ull;
+  auto rnd = [&]() { st = st * 6364136223846793005ull + 1442695040888963407ull; return (double)(st >> 11) / 9007199254740992.0; };
+  for (int i = 0; i < N; ++i) {
+    double x = ((i % ns) + 0.5 + 0.1 * (rnd() - 0.5)) * dL, y = (((i / ns) % ns) + 0.5 + 0.1 * (rnd() - 0.5)) * dL,
+           z = ((i / (ns * ns)) + 0.5 + 0.1 * (rnd() - 0.5)) * dL;
+    hp[i] = make_float4((float)x, (float)y, (float)z, 0.f);
+    const double sc = 4294967296.0 / L;
+    hu[i] = make_uint4((unsigned)(unsigned long long)llrint(hp[i].x * sc), (unsigned)(unsigned long long)llrint(hp[i].y * sc),
+                       (unsigned)(unsigned long long)llrint(hp[i].z * sc), 0u);
+  }
+  Problem pb;
+  pb.N = N; pb.L = L; pb.sms = sms;
+  CK(cudaMalloc(&pb.upos, (size_t)N * 16));
+  CK(cudaMalloc(&pb.posf, (size_t)N * 16));
+  const size_t smax = std::min<size_t>(8 * sms, std::max(1, N / 64));
+  CK(cudaMalloc(&pb.fpart, smax * N * 16));
+  CK(cudaMalloc(&pb.blockW, smax * (N / 64 + 1) * sizeof(double)));
+  CK(cudaMalloc(&pb.rdf, 256 * 8));
+  CK(cudaMemset(pb.rdf, 0, 256 * 8));
+  CK(cudaMemcpy(pb.upos, hu.data(), (size_t)N * 16, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(pb.posf, hp.data(), (size_t)N * 16, cudaMemcpyHostToDevice));
+
+  std::vector<float4> keepP, keepO;
+  //                 V   PER    RDF   THR MINB NPAIR UNROLL
+  run_variant<P2, true, false, 128, 4, 2, 4>(pb, "periodic P2 t128 b4 np2 u4 tile1024", reps, 1024, &keepP);
+  run_variant<S2, true, false, 128, 4, 2, 4>(pb, "periodic S2(scalar) t128 b4 np2 u4", reps, 1024, &keepP);
+  run_variant<P2, true, false, 128, 4, 2, 2>(pb, "periodic P2 t128 b4 np2 u2", reps, 1024, &keepP);
+  run_variant<P2, true, false, 128, 4, 2, 8>(pb, "periodic P2 t128 b4 np2 u8", reps, 1024, &keepP);
+  run_variant<P2, true, false, 128, 4, 2, 4>(pb, "periodic P2 t128 b4 np2 u4 tile512", reps, 512, &keepP);
+  run_variant<P2, true, false, 128, 4, 2, 4>(pb, "periodic P2 t128 b4 np2 u4 tile2048", reps, 2048, &keepP);
+  run_variant<P2, true, false, 256, 2, 2, 4>(pb, "periodic P2 t256 b2 np2 u4", reps, 1024, &keepP);
+  run_variant<P2, true, false, 128, 5, 2, 4>(pb, "periodic P2 t128 b5 np2 u4", reps, 1024, &keepP);
+  run_variant<P2, true, false, 128, 6, 1, 4>(pb, "periodic P2 t128 b6 np1 u4", reps, 1024, &keepP);
+  run_variant<P2, true, false, 128, 8, 1, 8>(pb, "periodic P2 t128 b8 np1 u8", reps, 1024, &keepP);
+  run_variant<P2, true, false, 128, 3, 3, 2>(pb, "periodic P2 t128 b3 np3 u2", reps, 1024, &keepP);
+  run_variant<P2, true, false, 128, 2, 4, 2>(pb, "periodic P2 t128 b2 np4 u2", reps, 1024, &keepP);
+  run_variant<P2, true, false, 64, 8, 2, 4>(pb, "periodic P2 t64 b8 np2 u4", reps, 1024, &keepP);
+  run_variant<P2, true, false, 512, 1, 2, 4>(pb, "periodic P2 t512 b1 np2 u4", reps, 1024, &keepP);
+  run_variant<P2, true, true, 128, 3, 2, 4>(pb, "periodic+RDF P2 t128 b3 np2 u4", reps, 1024, &keepP);
+  run_variant<P2, false, false, 128, 4, 2, 4>(pb, "open P2 t128 b4 np2 u4", reps, 1024, &keepO);
+  run_variant<S2, false, false, 128, 4, 2, 4>(pb, "open S2(scalar) t128 b4 np2 u4", reps, 1024, &keepO);
+  run_variant<P2, false, false, 128, 4, 2, 8>(pb, "open P2 t128 b4 np2 u8", reps, 1024, &keepO);
+  run_variant<P2, false, false, 128, 3, 3, 2>(pb, "open P2 t128 b3 np3 u2", reps, 1024, &keepO);
+  run_variant<P2, false, true, 128, 3, 2, 4>(pb, "open+RDF P2 t128 b3 np2 u4", reps, 1024, &keepO);
+  return 0;
+}
