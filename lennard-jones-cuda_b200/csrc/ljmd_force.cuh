@@ -237,6 +237,60 @@ __device__ __forceinline__ void pair_body(const uint4& uj, const PairI<V>& pi, P
   }
 }
 
+// ---- the same pair evaluation split in two stages for software pipelining -----------------------------
+// stage A (mostly ALU/XU pipes): separation, r^2, 1/r^2.  stage B (FMA pipe): LJ polynomial + accumulation.
+// The main loop runs stage A of batch b+1 next to stage B of batch b, so the packed-FMA work of one batch
+// and the integer subtract / I2FP / MUFU work of the next are independent instruction streams that the
+// scheduler can interleave (ptxas does not software-pipeline across loop iterations by itself).
+template <typename V>
+struct Stage {
+  V dx, dy, dz, y;
+  float2 r2s;  // only live in RDF variants
+};
+
+template <typename V, bool PERIODIC>
+__device__ __forceinline__ void stage_a(const uint4& uj, const PairI<V>& pi, Stage<V>& st) {
+  if (PERIODIC) {
+    st.dx = mk2<V>(__int2float_rn(pi.ax - (int)uj.x), __int2float_rn(pi.bx - (int)uj.x));
+    st.dy = mk2<V>(__int2float_rn(pi.ay - (int)uj.y), __int2float_rn(pi.by - (int)uj.y));
+    st.dz = mk2<V>(__int2float_rn(pi.az - (int)uj.z), __int2float_rn(pi.bz - (int)uj.z));
+  } else {
+    st.dx = sub2(pi.x2, bc2<V>(__uint_as_float(uj.x)));
+    st.dy = sub2(pi.y2, bc2<V>(__uint_as_float(uj.y)));
+    st.dz = sub2(pi.z2, bc2<V>(__uint_as_float(uj.z)));
+  }
+  const V r2 = fma2(st.dz, st.dz, fma2(st.dy, st.dy, mul2(st.dx, st.dx)));
+  st.r2s = upk(r2);
+  st.y = mk2<V>(rcp_approx(st.r2s.x), rcp_approx(st.r2s.y));
+}
+
+template <typename V, bool PERIODIC, bool RDF>
+__device__ __forceinline__ void stage_b(const Stage<V>& st, const PairI<V>& pi, PairAcc<V>& acc, const ForceParams& p,
+                                        const float4* pjf, unsigned int* hist) {
+  V x = st.y;
+  if (PERIODIC) x = mul2(x, bc2<V>(p.c2));
+  const V x2 = mul2(x, x);
+  const V r6 = mul2(x2, x);
+  const V t = fma2(r6, bc2<V>(12.f), bc2<V>(-6.f));
+  const V u = mul2(r6, t);
+  const V s = mul2(u, x);
+  acc.fx = fma2(st.dx, s, acc.fx);
+  acc.fy = fma2(st.dy, s, acc.fy);
+  acc.fz = fma2(st.dz, s, acc.fz);
+  acc.s6 = add2(acc.s6, r6);
+  acc.w = add2(acc.w, u);
+  if (RDF) {
+    if (st.r2s.x < p.cut_fast && pi.v_lo) {
+      const float2 xs = upk(pi.x2), ys = upk(pi.y2), zs = upk(pi.z2);
+      rdf_slow<PERIODIC>(xs.x, ys.x, zs.x, *pjf, p, hist);
+    }
+    if (st.r2s.y < p.cut_fast && pi.v_hi) {
+      const float2 xs = upk(pi.x2), ys = upk(pi.y2), zs = upk(pi.z2);
+      rdf_slow<PERIODIC>(xs.y, ys.y, zs.y, *pjf, p, hist);
+    }
+  }
+}
+
 template <int THREADS>
 __device__ __forceinline__ double block_sum(double v, double* red) {
 #pragma unroll
@@ -255,7 +309,9 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 
 // grid: (i-tiles, j-splits).  block: THREADS.  dyn smem: force_smem_bytes().
 // A thread owns 2*NPAIR i-particles: particle m is ibase + m*THREADS + tid; packed pair q = (2q, 2q+1).
-template <typename V, bool PERIODIC, bool RDF, int THREADS, int MINB, int NPAIR, int UNROLL>
+// UNROLL: j-loop unroll of the plain loop.  PIPE: 0 = plain loop; > 0 = software-pipelined main loop with
+// batches of PIPE j-records (stage A of the next batch beside stage B of the current one).
+template <typename V, bool PERIODIC, bool RDF, int THREADS, int MINB, int NPAIR, int UNROLL, int PIPE = 0>
 __global__ void __launch_bounds__(THREADS, MINB) k_force(const ForceParams p) {
   constexpr int IPT = 2 * NPAIR;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -298,7 +354,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force(const ForceParams p) {
 
   PairI<V> pi[NPAIR];
   PairAcc<V> acc[NPAIR];
-  V s6run[NPAIR], wrun[NPAIR];  // run-level sums (two-level float summation)
+  // run-level sums: every accumulator is folded per tile (two-level float summation), which keeps the
+  // rounding error of an N-term float sum at ~sqrt(tile)+sqrt(N/tile) ulps instead of sqrt(N)
+  V s6run[NPAIR], wrun[NPAIR], fxrun[NPAIR], fyrun[NPAIR], fzrun[NPAIR];
   const V zero2 = bc2<V>(0.f);
 #pragma unroll
   for (int q = 0; q < NPAIR; ++q) {
@@ -317,7 +375,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force(const ForceParams p) {
       pi[q].x2 = pi[q].y2 = pi[q].z2 = zero2;
     }
     acc[q].fx = acc[q].fy = acc[q].fz = acc[q].s6 = acc[q].w = zero2;
-    s6run[q] = wrun[q] = zero2;
+    s6run[q] = wrun[q] = fxrun[q] = fyrun[q] = fzrun[q] = zero2;
   }
   unsigned int* myhist = hist + (tid >> 5) * kRdfBins;
 
@@ -331,7 +389,49 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force(const ForceParams p) {
     const float4* tf = (RDF && PERIODIC) ? (tile_f + (size_t)st * TJ) : reinterpret_cast<const float4*>(tu);
     // does this tile contain any of this CTA's own particles?
     const bool diag = (j0 < ibase + THREADS * IPT) && (j0 + nj > ibase);
-    if (!diag) {
+    if (!diag && PIPE > 0) {
+      constexpr int UJ = PIPE > 0 ? PIPE : 1;
+      const int nb = nj / UJ;
+      Stage<V> sa[UJ][NPAIR], sb[UJ][NPAIR];
+      auto run_a = [&](int b, Stage<V>(&st)[UJ][NPAIR]) {
+#pragma unroll
+        for (int u = 0; u < UJ; ++u) {
+          const uint4 uj = tu[b * UJ + u];
+#pragma unroll
+          for (int q = 0; q < NPAIR; ++q) stage_a<V, PERIODIC>(uj, pi[q], st[u][q]);
+        }
+      };
+      auto run_b = [&](int b, Stage<V>(&st)[UJ][NPAIR]) {
+#pragma unroll
+        for (int u = 0; u < UJ; ++u)
+#pragma unroll
+          for (int q = 0; q < NPAIR; ++q)
+            stage_b<V, PERIODIC, RDF>(st[u][q], pi[q], acc[q], p, tf + b * UJ + u, myhist);
+      };
+      if (nb > 0) {
+        run_a(0, sa);
+        int b = 1;
+        for (; b + 1 < nb; b += 2) {  // ping-pong: no register copies between iterations
+          run_a(b, sb);
+          run_b(b - 1, sa);
+          run_a(b + 1, sa);
+          run_b(b, sb);
+        }
+        if (b < nb) {
+          run_a(b, sb);
+          run_b(b - 1, sa);
+          run_b(b, sb);
+        } else {
+          run_b(b - 1, sa);
+        }
+      }
+      for (int j = nb * UJ; j < nj; ++j) {  // remainder of a ragged tile
+        const uint4 uj = tu[j];
+#pragma unroll
+        for (int q = 0; q < NPAIR; ++q)
+          pair_body<V, PERIODIC, false, RDF>(uj, pi[q], acc[q], false, false, p, tf + j, myhist);
+      }
+    } else if (!diag) {
 #pragma unroll UNROLL
       for (int j = 0; j < nj; ++j) {
         const uint4 uj = tu[j];
@@ -355,8 +455,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force(const ForceParams p) {
     for (int q = 0; q < NPAIR; ++q) {
       s6run[q] = add2(s6run[q], acc[q].s6);
       wrun[q] = add2(wrun[q], acc[q].w);
-      acc[q].s6 = zero2;
-      acc[q].w = zero2;
+      fxrun[q] = add2(fxrun[q], acc[q].fx);
+      fyrun[q] = add2(fyrun[q], acc[q].fy);
+      fzrun[q] = add2(fzrun[q], acc[q].fz);
+      acc[q].s6 = acc[q].w = acc[q].fx = acc[q].fy = acc[q].fz = zero2;
     }
     __syncthreads();  // everyone is done with stage st before it is refilled
   }
@@ -367,7 +469,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force(const ForceParams p) {
   float4* out = p.fpart + (size_t)blockIdx.y * p.ilocal_cap;
 #pragma unroll
   for (int q = 0; q < NPAIR; ++q) {
-    const float2 fx = upk(acc[q].fx), fy = upk(acc[q].fy), fz = upk(acc[q].fz);
+    const float2 fx = upk(fxrun[q]), fy = upk(fyrun[q]), fz = upk(fzrun[q]);
     const float2 s6 = upk(s6run[q]), w = upk(wrun[q]);
     const int il = (ibase - p.i_begin) + (2 * q) * THREADS + tid;
     // r^-12 - r^-6 = u/12 - r^-6/2

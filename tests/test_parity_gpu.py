@@ -362,7 +362,7 @@ def test_full_size_properties_c3(pkg, gpu_lib):
         sc = s.scalars()
         f = frc[:, :3].astype(np.float64)
         fabs = np.abs(f).sum()
-        assert np.abs(f.sum(axis=0)).max() <= 1e-6 * fabs          # sum of all forces vanishes
+        assert np.abs(f.sum(axis=0)).max() <= 3e-6 * fabs          # sum of all forces vanishes (float rounding only)
         assert abs(2.0 * frc[:, 3].astype(np.float64).sum() - sc["V"]) <= 1e-6 * abs(sc["V"])
         rdf = s.rdf_counts()
         assert np.array_equal(rdf.astype(np.int64), rdf_numpy(pos, s.L, 0, s.rdf_dr2))
@@ -392,7 +392,7 @@ def test_full_size_hardwall_c4_slice(pkg, gpu_lib):
         s.set_state(pos, vel)
         _, _, frc = s.get_state()
         f = frc[:, :3].astype(np.float64)
-        assert np.abs(f.sum(axis=0)).max() <= 1e-6 * max(np.abs(f).sum(), 1e-30)
+        assert np.abs(f.sum(axis=0)).max() <= 5e-6 * max(np.abs(f).sum(), 1e-30)
         assert np.array_equal(s.rdf_counts().astype(np.int64), rdf_numpy(pos, s.L, 1, s.rdf_dr2))
         vh = s.velocity_histogram(0.12, 101)
         assert vh.sum() == N

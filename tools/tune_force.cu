@@ -125,9 +125,9 @@ static int pick_split(int n_it, int N, int sms, int minb) {
   return best;
 }
 
-template <typename V, bool PERIODIC, bool RDF, int THREADS, int MINB, int NPAIR, int UNROLL>
+template <typename V, bool PERIODIC, bool RDF, int THREADS, int MINB, int NPAIR, int UNROLL, int PIPE = 0>
 static void run_variant(const Problem& pb, const char* tag, int reps, int tile_j, std::vector<float4>* keep) {
-  auto kern = k_force<V, PERIODIC, RDF, THREADS, MINB, NPAIR, UNROLL>;
+  auto kern = k_force<V, PERIODIC, RDF, THREADS, MINB, NPAIR, UNROLL, PIPE>;
   const size_t smem = force_smem_bytes(PERIODIC, RDF, tile_j, THREADS);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaFuncAttributes fa;
@@ -236,26 +236,26 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(pb.posf, hp.data(), (size_t)N * 16, cudaMemcpyHostToDevice));
 
   std::vector<float4> keepP, keepO;
-  //                 V   PER    RDF   THR MINB NPAIR UNROLL
-  run_variant<P2, true, false, 128, 4, 2, 4>(pb, "periodic P2 t128 b4 np2 u4 tile1024", reps, 1024, &keepP);
-  run_variant<S2, true, false, 128, 4, 2, 4>(pb, "periodic S2(scalar) t128 b4 np2 u4", reps, 1024, &keepP);
-  run_variant<P2, true, false, 128, 4, 2, 2>(pb, "periodic P2 t128 b4 np2 u2", reps, 1024, &keepP);
-  run_variant<P2, true, false, 128, 4, 2, 8>(pb, "periodic P2 t128 b4 np2 u8", reps, 1024, &keepP);
-  run_variant<P2, true, false, 128, 4, 2, 4>(pb, "periodic P2 t128 b4 np2 u4 tile512", reps, 512, &keepP);
-  run_variant<P2, true, false, 128, 4, 2, 4>(pb, "periodic P2 t128 b4 np2 u4 tile2048", reps, 2048, &keepP);
-  run_variant<P2, true, false, 256, 2, 2, 4>(pb, "periodic P2 t256 b2 np2 u4", reps, 1024, &keepP);
-  run_variant<P2, true, false, 128, 5, 2, 4>(pb, "periodic P2 t128 b5 np2 u4", reps, 1024, &keepP);
-  run_variant<P2, true, false, 128, 6, 1, 4>(pb, "periodic P2 t128 b6 np1 u4", reps, 1024, &keepP);
-  run_variant<P2, true, false, 128, 8, 1, 8>(pb, "periodic P2 t128 b8 np1 u8", reps, 1024, &keepP);
-  run_variant<P2, true, false, 128, 3, 3, 2>(pb, "periodic P2 t128 b3 np3 u2", reps, 1024, &keepP);
-  run_variant<P2, true, false, 128, 2, 4, 2>(pb, "periodic P2 t128 b2 np4 u2", reps, 1024, &keepP);
-  run_variant<P2, true, false, 64, 8, 2, 4>(pb, "periodic P2 t64 b8 np2 u4", reps, 1024, &keepP);
-  run_variant<P2, true, false, 512, 1, 2, 4>(pb, "periodic P2 t512 b1 np2 u4", reps, 1024, &keepP);
+  //                 V   PER    RDF   THR MINB NPAIR UNROLL PIPE
+  run_variant<P2, true, false, 128, 4, 2, 4>(pb, "periodic P2 t128 b4 np2 u4 (baseline)", reps, 1024, &keepP);
+  run_variant<P2, true, false, 128, 4, 2, 4, 1>(pb, "periodic P2 t128 b4 np2 pipe1", reps, 1024, &keepP);
+  run_variant<P2, true, false, 128, 4, 2, 4, 2>(pb, "periodic P2 t128 b4 np2 pipe2", reps, 1024, &keepP);
+  run_variant<P2, true, false, 128, 3, 2, 4, 4>(pb, "periodic P2 t128 b3 np2 pipe4", reps, 1024, &keepP);
+  run_variant<P2, true, false, 128, 4, 2, 4, 4>(pb, "periodic P2 t128 b4 np2 pipe4", reps, 1024, &keepP);
+  run_variant<P2, true, false, 256, 2, 2, 4, 2>(pb, "periodic P2 t256 b2 np2 pipe2", reps, 1024, &keepP);
+  run_variant<P2, true, false, 128, 8, 1, 4, 2>(pb, "periodic P2 t128 b8 np1 pipe2 tile512", reps, 512, &keepP);
+  run_variant<P2, true, false, 128, 8, 1, 4, 4>(pb, "periodic P2 t128 b8 np1 pipe4 tile512", reps, 512, &keepP);
+  run_variant<P2, true, false, 128, 6, 1, 4, 4>(pb, "periodic P2 t128 b6 np1 pipe4 tile512", reps, 512, &keepP);
+  run_variant<P2, true, false, 128, 8, 1, 8>(pb, "periodic P2 t128 b8 np1 u8 tile512", reps, 512, &keepP);
+  run_variant<P2, true, false, 128, 3, 3, 2, 2>(pb, "periodic P2 t128 b3 np3 pipe2", reps, 1024, &keepP);
+  run_variant<P2, true, false, 128, 3, 3, 2, 1>(pb, "periodic P2 t128 b3 np3 pipe1", reps, 1024, &keepP);
+  run_variant<S2, true, false, 128, 4, 2, 4, 2>(pb, "periodic S2 t128 b4 np2 pipe2", reps, 1024, &keepP);
   run_variant<P2, true, true, 128, 3, 2, 4>(pb, "periodic+RDF P2 t128 b3 np2 u4", reps, 1024, &keepP);
-  run_variant<P2, false, false, 128, 4, 2, 4>(pb, "open P2 t128 b4 np2 u4", reps, 1024, &keepO);
-  run_variant<S2, false, false, 128, 4, 2, 4>(pb, "open S2(scalar) t128 b4 np2 u4", reps, 1024, &keepO);
-  run_variant<P2, false, false, 128, 4, 2, 8>(pb, "open P2 t128 b4 np2 u8", reps, 1024, &keepO);
-  run_variant<P2, false, false, 128, 3, 3, 2>(pb, "open P2 t128 b3 np3 u2", reps, 1024, &keepO);
-  run_variant<P2, false, true, 128, 3, 2, 4>(pb, "open+RDF P2 t128 b3 np2 u4", reps, 1024, &keepO);
+  run_variant<P2, true, true, 128, 3, 2, 4, 2>(pb, "periodic+RDF P2 t128 b3 np2 pipe2", reps, 1024, &keepP);
+  run_variant<P2, false, false, 128, 4, 2, 4>(pb, "open P2 t128 b4 np2 u4 (baseline)", reps, 1024, &keepO);
+  run_variant<P2, false, false, 128, 4, 2, 4, 2>(pb, "open P2 t128 b4 np2 pipe2", reps, 1024, &keepO);
+  run_variant<P2, false, false, 128, 4, 2, 4, 4>(pb, "open P2 t128 b4 np2 pipe4", reps, 1024, &keepO);
+  run_variant<P2, false, false, 128, 8, 1, 4, 4>(pb, "open P2 t128 b8 np1 pipe4 tile512", reps, 512, &keepO);
+  run_variant<P2, false, true, 128, 3, 2, 4, 2>(pb, "open+RDF P2 t128 b3 np2 pipe2", reps, 1024, &keepO);
   return 0;
 }
