@@ -106,6 +106,10 @@ int ljmd_set_T0(ljmd_system* s, double T0);
  */
 int ljmd_set_state(ljmd_system* s, const float* pos4, const float* vel4);
 
+/* Plain upload of host arrays (either may be NULL) without any evaluation: what the reference does when
+ * a caller edits h_Pos / h_Vel in place (copyArrayToDevice, MDSystem.cu:212-216). */
+int ljmd_upload(ljmd_system* s, const float* pos4, const float* vel4);
+
 /* Upload only velocities (after a host-side rescale, MDSystem.cpp:375-404) and
  * recompute K, T, P, U without touching the av_* accumulators or forces. */
 int ljmd_set_velocities(ljmd_system* s, const float* vel4);

@@ -545,6 +545,15 @@ extern "C" int ljmd_set_state(ljmd_system* s, const float* pos4, const float* ve
   return sync_scalars(s);
 }
 
+extern "C" int ljmd_upload(ljmd_system* s, const float* pos4, const float* vel4) {
+  CHECK_S(s);
+  int rc = upload_state(s, pos4, vel4);
+  if (rc) return rc;
+  if (pos4) s->rdf_valid = 0;
+  CU(cudaStreamSynchronize(s->stream));
+  return LJMD_OK;
+}
+
 extern "C" int ljmd_set_velocities(ljmd_system* s, const float* vel4) {
   CHECK_S(s);
   if (!vel4) return set_err(LJMD_ERR_ARG, "vel4 must not be NULL");

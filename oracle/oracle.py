@@ -16,6 +16,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_LIB = os.path.join(HERE, "libljmd_oracle.so")
 REF_LIB = os.path.join(HERE, "_ref", "libljmd_ref.so")
+REF_LEGACY_LIB = os.path.join(HERE, "_ref", "libljmd_ref_legacy.so")
 RDF_BINS = 256
 
 
@@ -125,16 +126,22 @@ def reference_available():
 
 
 class Reference:
-    """The unmodified reference MDSystem (CPU path) behind oracle/ref_shim.cpp."""
+    """The unmodified reference MDSystem behind oracle/ref_shim.cpp.
 
-    _lib = None
+    legacy=False: its CPU path (the oracle).  legacy=True: the same host code built with
+    -DUSE_CUDA_TOOLKIT and linked against the product's legacy C seam, i.e. the reference host layer
+    driving the new kernels (needs a GPU; used by the drop-in tests only).
+    """
+
+    _libs = {}
 
     @classmethod
-    def lib(cls):
-        if cls._lib is None:
-            if not os.path.exists(REF_LIB):
-                raise RuntimeError(f"{REF_LIB} missing: run `make -C oracle` where /root/reference exists")
-            lib = C.CDLL(REF_LIB)
+    def lib(cls, legacy=False):
+        if legacy not in cls._libs:
+            path = REF_LEGACY_LIB if legacy else REF_LIB
+            if not os.path.exists(path):
+                raise RuntimeError(f"{path} missing: run `make -C oracle ref ref_legacy` where /root/reference exists")
+            lib = C.CDLL(path)
             vp = C.c_void_p
             lib.ljref_create.restype = vp
             lib.ljref_create.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]
@@ -157,12 +164,12 @@ class Reference:
             lib.ljref_renormalize_velocities.argtypes = [vp, C.c_int]
             lib.ljref_kinetic_temperature.restype = C.c_double
             lib.ljref_kinetic_temperature.argtypes = [vp]
-            cls._lib = lib
-        return cls._lib
+            cls._libs[legacy] = lib
+        return cls._libs[legacy]
 
-    def __init__(self, N, T0, rho, canonical, bc):
+    def __init__(self, N, T0, rho, canonical, bc, legacy=False):
         self.N = N
-        self._l = self.lib()
+        self._l = self.lib(legacy)
         self._h = self._l.ljref_create(N, T0, rho, int(canonical), bc)
 
     def close(self):

@@ -23,7 +23,13 @@ void* ljref_create(int N, double T0, double rho, int canonical, int bc)
   cfg.N = N; cfg.T0 = T0; cfg.rho = rho;
   cfg.canonical = canonical != 0;
   cfg.boundaryConditions = bc;
+#ifdef LJREF_ALLOW_CUDA
+  // libljmd_ref_legacy.so: the reference host layer built with -DUSE_CUDA_TOOLKIT on top of the product's
+  // legacy C seam — its GPU branch (MDSystem.cpp:240-251) then runs the sm_100a kernels.
+  cfg.useCUDA = true;
+#else
   cfg.useCUDA = false;
+#endif
   s->Reinitialize(cfg);                         // one O(N^2) evaluation
   return s;
 }
