@@ -217,11 +217,9 @@ def main_reference(args, pkg):
 # ------------------------------------------------------------------------------------------ our arm
 def main_ours(args, pkg):
     import torch
-    import torch.distributed as dist
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    D = pkg.dist
+    rank, world, local_rank = D.env_rank_world()
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     if not torch.cuda.is_available():
@@ -229,24 +227,9 @@ def main_ours(args, pkg):
                          "(use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local_rank)
     ljmd = pkg.ljmd
-    uid = None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        box = [ljmd.LJSystem.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
-        uid = box[0]
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    D.init("nccl")
+    uid = D.share_unique_id(ljmd.LJSystem.nccl_unique_id) if world > 1 else None
+    barrier, max_over_ranks = D.barrier, D.max_over_ranks
 
     cfg, pos, vel = workload(pkg, args.config)
     N = cfg["N"]
@@ -344,8 +327,7 @@ def main_ours(args, pkg):
                           f"cost is N(N-1) pair evaluations per step); {host_description()}"}
         print(json.dumps(line))
     sysm.close()
-    if world > 1:
-        dist.destroy_process_group()
+    D.finalize()
     return 0
 
 

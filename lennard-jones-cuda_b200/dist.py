@@ -1,0 +1,80 @@
+"""One-process-per-GPU plumbing over torch.distributed (NCCL on GPUs, gloo in CPU tests).
+
+The data path never goes through torch: each rank's C-ABI handle owns its own NCCL communicator
+(ljmd_create_distributed) and issues the per-step all-gather of positions and all-reduce of the
+energy / virial / kinetic sums itself.  torch.distributed only carries the 128-byte ncclUniqueId from
+rank 0 to the others, the barriers around timed regions, and the max-over-ranks of timings.
+"""
+import os
+
+
+def env_rank_world():
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+            int(os.environ.get("LOCAL_RANK", "0")))
+
+
+def shard_bounds(N, rank, world):
+    """Contiguous i-shard of `rank`: the same rule as the library (ljmd_plan / create_impl)."""
+    cnt = (N + world - 1) // world
+    return min(N, rank * cnt), min(N, (rank + 1) * cnt)
+
+
+def init(backend=None):
+    """Initialise the default process group from the torchrun environment.  Returns (rank, world, local_rank)."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world, local_rank = env_rank_world()
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            kw["device_id"] = torch.device("cuda", local_rank)
+        dist.init_process_group(backend, **kw)
+    return rank, world, local_rank
+
+
+def share_unique_id(make_id):
+    """Rank 0 calls make_id() (-> 128 bytes); every rank returns the same bytes."""
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return make_id()
+    box = [make_id() if dist.get_rank() == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    uid = bytes(box[0])
+    if len(uid) != 128:
+        raise ValueError(f"ncclUniqueId must be 128 bytes, got {len(uid)}")
+    return uid
+
+
+def barrier():
+    import torch
+    import torch.distributed as dist
+
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+
+
+def max_over_ranks(x):
+    """Timings are reported as the max over ranks (the slowest rank defines the step)."""
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(x)
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def finalize():
+    import torch.distributed as dist
+
+    if dist.is_initialized():
+        dist.destroy_process_group()
