@@ -178,18 +178,20 @@ int ljmd_last_step_timing(ljmd_system* s, double* force_ms, double* total_ms, in
  * stream before every step, evicting the previous step's lines from the 126 MB L2. */
 int ljmd_set_l2_flush(ljmd_system* s, long long bytes);
 
-/* Static facts for rooflines: out[0]=SM count, out[1]=i-tile size, out[2]=j-splits,
- * out[3]=force CTAs per launch, out[4]=world size, out[5]=local particles. */
-int ljmd_get_launch_info(ljmd_system* s, int* out6);
+/* Static facts for rooflines: out[0]=SM count, out[1]=i-tile size, out[2]=splits per i-tile,
+ * out[3]=force CTAs per launch, out[4]=world size, out[5]=local particles, out[6]=1 if the Newton-3 kernel
+ * (each unordered pair evaluated once) is in use, out[7]=reserved. */
+int ljmd_get_launch_info(ljmd_system* s, int* out8);
 
 /* Host-only helpers (no device needed), exported so the launch plan and the exact-RDF constants can
  * be checked without a GPU.
  * ljmd_image_threshold: smallest positive float d for which the reference's
  *   fast_round((float)(d / L)) (MDSystem.cpp:274,732-739) is >= k.
- * ljmd_plan: out[0..1] = i-shard [begin,end) of `rank`, out[2] = i-tiles, out[3] = j-splits,
- *   out[4] = force CTAs per launch, out[5] = i-particles per CTA, for `num_sms` SMs. */
+ * ljmd_plan: out[0..1] = i-shard [begin,end) of `rank` (whole 512-particle blocks), out[2] = i-tiles,
+ *   out[3] = splits per i-tile, out[4] = force CTAs per launch, out[5] = i-particles per CTA,
+ *   out[6] = 1 when the Newton-3 kernel is used, out[7] = partner blocks per i-tile, for `num_sms` SMs. */
 float ljmd_image_threshold(double L, int k);
-int ljmd_plan(int N, int rank, int world, int num_sms, int* out6);
+int ljmd_plan(int N, int rank, int world, int num_sms, int* out8);
 
 /* ------------------------------------------------- B. legacy seam ---------
  * The six symbols MDSystem.cpp calls (MDSystem.cpp:9-25; definitions replaced:

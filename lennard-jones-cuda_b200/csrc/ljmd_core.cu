@@ -16,7 +16,7 @@
 #include <nccl.h>
 #endif
 
-#include "ljmd_force.cuh"
+#include "ljmd_force_sym.cuh"
 #include "ljmd_step.cuh"
 
 using namespace ljmd;
@@ -55,6 +55,8 @@ constexpr int kITile = kForceThreads * 2 * kNPair;  // i-particles per CTA
 constexpr int kTileJ = 1024;                  // j-records per smem stage
 constexpr int kMinBlocks = 4;                 // resident CTAs/SM the non-RDF kernel is built for
 constexpr int kMinBlocksRdf = 3;
+constexpr int kSymBJ = 256;                   // j-records per work unit of the Newton-3 kernel
+constexpr int kSymMinBlocksN = 16;            // use the Newton-3 kernel from this many 512-particle blocks on
 
 struct ljmd_system {
   int N = 0, bc = 0, canonical = 0;
@@ -66,6 +68,12 @@ struct ljmd_system {
   int npad = 0;     // world*cnt
   int num_sms = 148;
   int nsplit = 1, n_itiles = 1;
+  int nblk = 1;     // global number of kITile-blocks
+  int use_sym = 0;  // Newton-3 kernel (k_force_sym) instead of the ordered one (k_force)
+  int hmax = 0;     // partner offsets per i-tile (rows of the partner window)
+  float4* rpart = nullptr;   // [n_itiles][hmax*kITile] reaction rows
+  float4* rsum = nullptr;    // [npad] rank-local column sums of the reaction rows (world > 1)
+  float4* rshard = nullptr;  // [cnt]  reaction totals of this rank's particles after the reduce-scatter
   float thr1 = 0.f, thr2 = 0.f;
   cudaStream_t stream = nullptr;
   float4 *pos = nullptr, *posA = nullptr, *vel = nullptr, *force = nullptr, *tforce = nullptr, *fpart = nullptr;
@@ -115,23 +123,54 @@ static float image_threshold(double L, int k) {
   return d;
 }
 
-// j-split heuristic (DESIGN.md §grid sizing).  The grid is n_itiles x S CTAs of equal work and the SM
-// holds kMinBlocks of them, so the launch runs in ceil(n_itiles*S / (SMs*kMinBlocks)) waves of
-// (N/S + overhead) j-iterations each; pick the S that minimises that product, smallest S on ties
-// (fewer partial-force rows to write and re-read).
-static int choose_split(int n_itiles, int N, int num_sms, int nloc) {
+// Split heuristic (DESIGN.md §grid sizing).  The grid is n_itiles x S CTAs of equal work and the SM holds
+// `resident` of them, so the launch runs in ceil(n_itiles*S / (SMs*resident)) waves of (work/S + overhead)
+// j-iterations each; pick the S that minimises that product, smallest S on ties (fewer partial rows).
+// `work` is the number of j-iterations of one i-tile (N for the ordered kernel, its units x BJ for Newton-3),
+// `smax` the finest split that still leaves whole work units.
+static int choose_split(int n_itiles, long long work, int smax, int num_sms, int resident, int nloc) {
   const double ovh = 128.;  // per-CTA fixed cost (prologue, first tile latency, epilogue) in j-iterations
-  const long long slots = (long long)num_sms * kMinBlocks;
+  const long long slots = (long long)num_sms * resident;
   int best = 1;
   double best_cost = 1e300;
-  const int smax = std::max(1, std::min(N / 64, 8 * num_sms));
+  smax = std::max(1, std::min(smax, 8 * num_sms));
   for (int s = 1; s <= smax; ++s) {
     if ((double)s * nloc * 16. > 1.5e9) break;  // partial-force buffer cap
     const long long waves = ((long long)n_itiles * s + slots - 1) / slots;
-    const double cost = (double)waves * ((double)N / s + ovh);
+    const double cost = (double)waves * ((double)work / s + ovh);
     if (cost < best_cost * 0.999) { best_cost = cost; best = s; }
   }
   return best;
+}
+
+struct Plan {
+  int nblk, bpr, cnt, i_begin, i_end, nloc, n_itiles, use_sym, hmax, nsplit;
+};
+// Shards are whole kITile-blocks so that an i-tile never straddles two ranks (the Newton-3 block pairing
+// needs global block indices).  LJMD_KERNEL=ordered|sym overrides the kernel choice.
+static Plan make_plan(int N, int rank, int world, int num_sms) {
+  Plan pl;
+  pl.nblk = (N + kITile - 1) / kITile;
+  pl.bpr = (pl.nblk + world - 1) / world;
+  pl.cnt = pl.bpr * kITile;
+  pl.i_begin = std::min(N, rank * pl.cnt);
+  pl.i_end = std::min(N, (rank + 1) * pl.cnt);
+  pl.nloc = pl.i_end - pl.i_begin;
+  pl.n_itiles = (pl.nloc + kITile - 1) / kITile;
+  pl.use_sym = pl.nblk >= kSymMinBlocksN ? 1 : 0;
+  if (const char* e = getenv("LJMD_KERNEL")) {
+    if (!strcmp(e, "ordered")) pl.use_sym = 0;
+    if (!strcmp(e, "sym")) pl.use_sym = 1;
+  }
+  pl.hmax = std::max(1, sym_max_partner_count(pl.nblk));
+  if (pl.nloc <= 0) { pl.nsplit = 0; return pl; }
+  if (pl.use_sym) {
+    const int units = (sym_max_partner_count(pl.nblk) + 1) * (kITile / kSymBJ);
+    pl.nsplit = choose_split(pl.n_itiles, (long long)units * kSymBJ, units, num_sms, kMinBlocks, pl.cnt);
+  } else {
+    pl.nsplit = choose_split(pl.n_itiles, N, N / 64, num_sms, kMinBlocks, pl.cnt);
+  }
+  return pl;
 }
 
 static StepParams make_step_params(ljmd_system* s, double dt) {
@@ -143,6 +182,8 @@ static StepParams make_step_params(ljmd_system* s, double dt) {
   p.fix_scale = 4294967296.0 / s->L;
   p.pos = s->pos; p.posA = s->posA; p.upos = s->upos; p.vel = s->vel; p.force = s->force; p.tforce = s->tforce;
   p.fpart = s->fpart; p.blockW = s->blockW; p.part = s->part; p.counter = s->counter; p.sc = s->sc;
+  p.use_sym = s->use_sym; p.nblk = s->nblk; p.blk0 = s->i_begin / kITile; p.n_itiles = s->n_itiles;
+  p.rp_stride = s->hmax * kITile; p.rpart = s->rpart; p.rsum = s->rsum; p.rshard = s->rshard; p.npad = s->npad;
   return p;
 }
 
@@ -161,6 +202,22 @@ static cudaError_t launch_force_t(ljmd_system* s, const ForceParams& fp) {
   }
   dim3 grid(s->n_itiles, s->nsplit);
   kern<<<grid, kForceThreads, smem, s->stream>>>(fp);
+  return cudaGetLastError();
+}
+
+template <bool PERIODIC, bool RDF>
+static cudaError_t launch_force_sym_t(ljmd_system* s, const SymParams& sp) {
+  constexpr int MINB = RDF ? kMinBlocksRdf : kMinBlocks;
+  auto kern = k_force_sym<P2, PERIODIC, RDF, kForceThreads, MINB, kNPair>;
+  const size_t smem = force_sym_smem_bytes(PERIODIC, RDF, kSymBJ, kForceThreads);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  dim3 grid(s->n_itiles, s->nsplit);
+  kern<<<grid, kForceThreads, smem, s->stream>>>(sp);
   return cudaGetLastError();
 }
 
@@ -188,7 +245,14 @@ static int launch_force(ljmd_system* s, bool rdf) {
     CU(cudaEventRecord(e0, s->stream));
   }
   cudaError_t e;
-  if (periodic) e = rdf ? launch_force_t<true, true>(s, fp) : launch_force_t<true, false>(s, fp);
+  if (s->use_sym) {
+    SymParams sp;
+    sp.f = fp;
+    sp.f.tile_j = kSymBJ;
+    sp.rpart = s->rpart; sp.ncols = s->hmax * kITile; sp.nblk = s->nblk; sp.bj = kSymBJ;
+    if (periodic) e = rdf ? launch_force_sym_t<true, true>(s, sp) : launch_force_sym_t<true, false>(s, sp);
+    else e = rdf ? launch_force_sym_t<false, true>(s, sp) : launch_force_sym_t<false, false>(s, sp);
+  } else if (periodic) e = rdf ? launch_force_t<true, true>(s, fp) : launch_force_t<true, false>(s, fp);
   else e = rdf ? launch_force_t<false, true>(s, fp) : launch_force_t<false, false>(s, fp);
   if (e != cudaSuccess) return set_err(LJMD_ERR_CUDA, "force kernel launch: %s", cudaGetErrorString(e));
   if (s->timing) {
@@ -229,6 +293,15 @@ static int evaluate(ljmd_system* s, const StepParams& p, int mode, bool rdf, int
   if (rc) return rc;
   const int g = step_grid(s);
   const int fin = (s->world == 1) ? 1 : 0;
+#ifdef LJMD_WITH_NCCL
+  if (s->use_sym && s->world > 1) {
+    // reaction forces land on particles of every rank: column sums of the local rows, then a reduce-scatter
+    k_reduce_reaction<<<(s->npad + kStepThreads - 1) / kStepThreads, kStepThreads, 0, s->stream>>>(p);
+    CU(cudaGetLastError());
+    s->launches += 1;
+    NC(ncclReduceScatter(s->rsum, s->rshard, (size_t)s->cnt * 4, ncclFloat, ncclSum, s->comm, s->stream));
+  }
+#endif
   if (mode == GATHER_EVAL) k_gather<GATHER_EVAL><<<g, kStepThreads, 0, s->stream>>>(p, fin, accumulate);
   else if (mode == GATHER_EVN) k_gather<GATHER_EVN><<<g, kStepThreads, 0, s->stream>>>(p, fin, accumulate);
   else k_gather<GATHER_TVN><<<g, kStepThreads, 0, s->stream>>>(p, fin, accumulate);
@@ -320,14 +393,12 @@ extern "C" int ljmd_nccl_unique_id(void* out128) {
 
 extern "C" float ljmd_image_threshold(double L, int k) { return image_threshold(L, k); }
 
-extern "C" int ljmd_plan(int N, int rank, int world, int num_sms, int* out6) {
-  if (!out6 || N < 2 || world < 1 || rank < 0 || rank >= world || num_sms < 1)
+extern "C" int ljmd_plan(int N, int rank, int world, int num_sms, int* out8) {
+  if (!out8 || N < 2 || world < 1 || rank < 0 || rank >= world || num_sms < 1)
     return set_err(LJMD_ERR_ARG, "bad arguments to ljmd_plan");
-  const int cnt = (N + world - 1) / world;
-  const int b = std::min(N, rank * cnt), e = std::min(N, (rank + 1) * cnt);
-  const int nit = (e - b + kITile - 1) / kITile;
-  const int ns = (e > b) ? choose_split(nit, N, num_sms, cnt) : 0;
-  out6[0] = b; out6[1] = e; out6[2] = nit; out6[3] = ns; out6[4] = nit * ns; out6[5] = kITile;
+  const Plan pl = make_plan(N, rank, world, num_sms);
+  out8[0] = pl.i_begin; out8[1] = pl.i_end; out8[2] = pl.n_itiles; out8[3] = pl.nsplit;
+  out8[4] = pl.n_itiles * pl.nsplit; out8[5] = kITile; out8[6] = pl.use_sym; out8[7] = pl.use_sym ? pl.hmax : 0;
   return LJMD_OK;
 }
 
@@ -342,6 +413,7 @@ static int destroy_impl(ljmd_system* s) {
   cudaFree(s->fpart); cudaFree(s->gath); cudaFree(s->upos); cudaFree(s->blockW); cudaFree(s->part);
   cudaFree(s->counter); cudaFree(s->velh); cudaFree(s->sc); cudaFree(s->rdf_cur); cudaFree(s->rdf_acc);
   cudaFree(s->flush_buf);
+  cudaFree(s->rpart); cudaFree(s->rsum); cudaFree(s->rshard);
   cudaFreeHost(s->h_sc); cudaFreeHost(s->h_rdf);
   for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
   if (s->ev_begin) cudaEventDestroy(s->ev_begin);
@@ -372,11 +444,15 @@ static int create_impl(ljmd_system** out, int N, double rho_or_negL, double T0, 
   s->device = device; s->rank = rank; s->world = world;
   if (rho_or_negL > 0.) { s->rho = rho_or_negL; s->L = pow(N / s->rho, 1. / 3.); }   // MDSystem.cpp:70
   else { s->L = -rho_or_negL; s->rho = N / (s->L * s->L * s->L); }
-  s->cnt = (N + world - 1) / world;
-  s->npad = s->cnt * world;
-  s->i_begin = std::min(N, rank * s->cnt);
-  s->i_end = std::min(N, (rank + 1) * s->cnt);
-  s->nloc = s->i_end - s->i_begin;
+  // (the device properties are needed for the plan; queried again below for the arch check)
+  {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const Plan pl = make_plan(N, rank, world, sms);
+    s->nblk = pl.nblk; s->cnt = pl.cnt; s->npad = pl.cnt * world; s->i_begin = pl.i_begin; s->i_end = pl.i_end;
+    s->nloc = pl.nloc; s->n_itiles = pl.n_itiles; s->use_sym = pl.use_sym; s->hmax = pl.hmax; s->nsplit = pl.nsplit;
+    s->num_sms = sms;
+  }
   if (s->nloc < 1) { delete s; return set_err(LJMD_ERR_ARG, "rank %d of %d has no particles for N=%d", rank, world, N); }
   cudaDeviceProp prop;
   cudaError_t pe = cudaGetDeviceProperties(&prop, device);
@@ -387,8 +463,6 @@ static int create_impl(ljmd_system** out, int N, double rho_or_negL, double T0, 
                    prop.minor);
   }
   s->num_sms = prop.multiProcessorCount;
-  s->n_itiles = (s->nloc + kITile - 1) / kITile;
-  s->nsplit = choose_split(s->n_itiles, N, s->num_sms, s->cnt);
   s->thr1 = image_threshold(s->L, 1);
   s->thr2 = image_threshold(s->L, 2);
 
@@ -412,6 +486,17 @@ static int create_impl(ljmd_system** out, int N, double rho_or_negL, double T0, 
   CUC(cudaMalloc(&s->tforce, (size_t)s->cnt * b16));
   CUC(cudaMalloc(&s->fpart, (size_t)s->nsplit * s->cnt * b16));
   CUC(cudaMalloc(&s->blockW, (size_t)s->n_itiles * s->nsplit * sizeof(double)));
+  if (s->use_sym) {
+    // reaction rows: one partner window (hmax blocks) per local i-tile; entries no unit ever writes
+    // (the antipodal block of the upper half, ragged last block) must read as zero forever
+    const size_t rp = (size_t)s->n_itiles * s->hmax * kITile * b16;
+    CUC(cudaMalloc(&s->rpart, rp));
+    CUC(cudaMemsetAsync(s->rpart, 0, rp, s->stream));
+    if (world > 1) {
+      CUC(cudaMalloc(&s->rsum, (size_t)s->npad * b16));
+      CUC(cudaMalloc(&s->rshard, (size_t)s->cnt * b16));
+    }
+  }
   CUC(cudaMalloc(&s->part, (size_t)2 * (step_grid(s) + 1) * sizeof(double)));
   CUC(cudaMalloc(&s->counter, sizeof(unsigned int)));
   CUC(cudaMalloc(&s->velh, 65536 * sizeof(unsigned int)));
@@ -766,11 +851,11 @@ extern "C" int ljmd_last_step_timing(ljmd_system* s, double* force_ms, double* t
   if (force_launches) *force_launches = s->last_force_launches;
   return LJMD_OK;
 }
-extern "C" int ljmd_get_launch_info(ljmd_system* s, int* out6) {
+extern "C" int ljmd_get_launch_info(ljmd_system* s, int* out8) {
   CHECK_S(s);
-  if (!out6) return set_err(LJMD_ERR_ARG, "out6 is NULL");
-  out6[0] = s->num_sms; out6[1] = kITile; out6[2] = s->nsplit; out6[3] = s->n_itiles * s->nsplit;
-  out6[4] = s->world; out6[5] = s->nloc;
+  if (!out8) return set_err(LJMD_ERR_ARG, "out8 is NULL");
+  out8[0] = s->num_sms; out8[1] = kITile; out8[2] = s->nsplit; out8[3] = s->n_itiles * s->nsplit;
+  out8[4] = s->world; out8[5] = s->nloc; out8[6] = s->use_sym; out8[7] = 0;
   return LJMD_OK;
 }
 

@@ -169,13 +169,13 @@ __device__ __forceinline__ float image_exact(float d, const ForceParams& p) {
 
 template <bool PERIODIC>
 __device__ __forceinline__ void rdf_slow(float xi, float yi, float zi, const float4& pj, const ForceParams& p,
-                                         unsigned int* hist) {
+                                         unsigned int* hist, unsigned int inc = 1u) {
   float rx = __fsub_rn(xi, pj.x), ry = __fsub_rn(yi, pj.y), rz = __fsub_rn(zi, pj.z);
   if (PERIODIC) { rx = image_exact(rx, p); ry = image_exact(ry, p); rz = image_exact(rz, p); }
   // MDSystem.cpp:279 in float, un-fused, left to right
   float r2 = __fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz));
   int b = rdf_bin_exact(r2, p.dr2, p.inv_dr2);
-  if ((unsigned)b < (unsigned)kRdfBins) atomicAdd(&hist[b], 1u);
+  if ((unsigned)b < (unsigned)kRdfBins) atomicAdd(&hist[b], inc);
 }
 
 // One pair of i-particles (two lanes of V).

@@ -1,0 +1,346 @@
+// Newton's-third-law variant of the all-pairs force kernel: every unordered pair {i,j} is evaluated ONCE and
+// applied to both particles, which halves the pair evaluations of the reference's ordered double loop
+// (/root/reference/src/library/MDSystem.cpp:260-302, MDSystem.cu:60-111 evaluate (i,j) and (j,i)).
+//
+// Work decomposition: particles are cut in blocks of B = 2*NPAIR*THREADS.  Block I interacts
+// with itself (ordered loop, self pair excluded) and with the next h blocks cyclically, h = (n-1)/2 (+ the
+// antipodal block for the lower half when the block count n is even): every unordered block pair appears
+// exactly once and every i-tile has the same amount of work.  A CTA owns one i-tile (its i-particles live in
+// registers, as in k_force) and a contiguous share of that tile's (partner block, j-chunk) units.
+//
+// Reaction forces without atomics: inside a warp the 32 j-records of a chunk ROTATE through the lanes, so at
+// every step each lane works on a different j: lane l handles record (l + k) mod 32 at step k.  The record is
+// read from a per-warp staging copy of the chunk that is stored twice back to back, so the read address is
+// base + (l + k) with no wrap arithmetic and does not depend on the previous step; the three reaction
+// accumulators travel with their j through one shuffle each per step.  After 32 steps a packet is home and has
+// met all 32 lanes x 2*NPAIR i-particles; the warps' packets go to per-warp shared-memory slices, are summed in
+// warp order and written as one row of rpart[partner offset][j]; the gather kernel adds the rows in a fixed
+// order.  No floating-point atomics anywhere: runs are bit-reproducible.
+// Measured alternatives at N = 65 536 periodic (profiles/r01_tune_force_sym_*.log): ordered kernel 2.82 ms;
+// rotating positions and accumulators by shuffle (6 SHFL per step) 1.92 ms; broadcast j + 5-level butterfly
+// sum of the reaction (15 SHFL + 15 FADD per j) 2.37 ms.
+#pragma once
+#include "ljmd_force.cuh"
+
+namespace ljmd {
+
+struct SymParams {
+  ForceParams f;   // jrec, posf, fpart, blockW, rdf, N, i_begin (multiple of B), i_end, ilocal_cap, constants
+  float4* rpart;   // [local i-tiles][ncols] reaction rows (fx,fy,fz,0): row = i-tile of this rank, column =
+                   // (partner offset - 1) * B + index inside the partner block (the tile's partner window)
+  int ncols;       // row stride = hmax * B
+  int nblk;        // global number of blocks = ceil(N / B)
+  int bj;          // j-records per unit (multiple of 32, divides B)
+};
+
+// number of partner offsets of global block g among n blocks
+__host__ __device__ inline int sym_partner_count(int g, int n) {
+  if (n & 1) return (n - 1) / 2;
+  return n / 2 - 1 + (g < n / 2 ? 1 : 0);
+}
+inline int sym_max_partner_count(int n) { return (n & 1) ? (n - 1) / 2 : n / 2; }
+
+// One pair of i-particles (two lanes of V) against the broadcast j-record; also accumulates this lane's
+// reaction on j.  KILL: per-lane flags zero the interaction (clamped duplicate i's of a ragged last tile).
+template <typename V, bool PERIODIC, bool KILL, bool RDF>
+__device__ __forceinline__ void pair_sym(const uint4& uj, const PairI<V>& pi, PairAcc<V>& acc, bool kill_lo,
+                                         bool kill_hi, float& rjx, float& rjy, float& rjz, const ForceParams& p,
+                                         const float4* pjf, unsigned int* hist) {
+  V dx, dy, dz;
+  if (PERIODIC) {
+    dx = mk2<V>(__int2float_rn(pi.ax - (int)uj.x), __int2float_rn(pi.bx - (int)uj.x));
+    dy = mk2<V>(__int2float_rn(pi.ay - (int)uj.y), __int2float_rn(pi.by - (int)uj.y));
+    dz = mk2<V>(__int2float_rn(pi.az - (int)uj.z), __int2float_rn(pi.bz - (int)uj.z));
+  } else {
+    dx = sub2(pi.x2, bc2<V>(__uint_as_float(uj.x)));
+    dy = sub2(pi.y2, bc2<V>(__uint_as_float(uj.y)));
+    dz = sub2(pi.z2, bc2<V>(__uint_as_float(uj.z)));
+  }
+  const V r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+  const float2 r2s = upk(r2);
+  float inv0 = rcp_approx(r2s.x), inv1 = rcp_approx(r2s.y);
+  if (KILL) {
+    if (kill_lo) inv0 = 0.f;
+    if (kill_hi) inv1 = 0.f;
+  }
+  V x = mk2<V>(inv0, inv1);
+  if (PERIODIC) x = mul2(x, bc2<V>(p.c2));
+  const V x2 = mul2(x, x);
+  const V r6 = mul2(x2, x);
+  const V t = fma2(r6, bc2<V>(12.f), bc2<V>(-6.f));
+  const V u = mul2(r6, t);
+  const V s = mul2(u, x);
+  acc.fx = fma2(dx, s, acc.fx);
+  acc.fy = fma2(dy, s, acc.fy);
+  acc.fz = fma2(dz, s, acc.fz);
+  acc.s6 = add2(acc.s6, r6);
+  acc.w = add2(acc.w, u);
+  // reaction on j: -(d*s) of both lanes, scalar FMAs into this lane's partial
+  const float2 sx = upk(s), ddx = upk(dx), ddy = upk(dy), ddz = upk(dz);
+  rjx = __fmaf_rn(-ddx.x, sx.x, rjx); rjx = __fmaf_rn(-ddx.y, sx.y, rjx);
+  rjy = __fmaf_rn(-ddy.x, sx.x, rjy); rjy = __fmaf_rn(-ddy.y, sx.y, rjy);
+  rjz = __fmaf_rn(-ddz.x, sx.x, rjz); rjz = __fmaf_rn(-ddz.y, sx.y, rjz);
+  if (RDF) {
+    // the reference counts (i,j) and (j,i); its float sequence is odd in the separation, so both land in the
+    // same bin: one exact evaluation, increment 2
+    if (r2s.x < p.cut_fast && !(KILL && kill_lo)) {
+      const float2 xs = upk(pi.x2), ys = upk(pi.y2), zs = upk(pi.z2);
+      rdf_slow<PERIODIC>(xs.x, ys.x, zs.x, *pjf, p, hist, 2u);
+    }
+    if (r2s.y < p.cut_fast && !(KILL && kill_hi)) {
+      const float2 xs = upk(pi.x2), ys = upk(pi.y2), zs = upk(pi.z2);
+      rdf_slow<PERIODIC>(xs.y, ys.y, zs.y, *pjf, p, hist, 2u);
+    }
+  }
+}
+
+// grid: (i-tiles of this rank, splits).  block: THREADS.  dyn smem: force_sym_smem_bytes().
+template <typename V, bool PERIODIC, bool RDF, int THREADS, int MINB, int NPAIR>
+__global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp) {
+  constexpr int IPT = 2 * NPAIR;
+  constexpr int B = THREADS * IPT;
+  constexpr int NW = THREADS / 32;
+  const ForceParams& p = sp.f;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int BJ = sp.bj;
+  uint4* tile_u = reinterpret_cast<uint4*>(smem_raw);                          // [2][BJ]
+  float4* tile_f = reinterpret_cast<float4*>(smem_raw + (size_t)2 * BJ * 16);  // [2][BJ] (RDF && PERIODIC)
+  unsigned char* after_tiles = smem_raw + (size_t)((RDF && PERIODIC) ? 4 : 2) * BJ * 16;
+  float4* slices = reinterpret_cast<float4*>(after_tiles);                     // [NW][BJ]
+  uint4* stage = reinterpret_cast<uint4*>(after_tiles + (size_t)NW * BJ * 16);  // [NW][64]
+  unsigned char* tail = after_tiles + (size_t)NW * BJ * 16 + (size_t)NW * 64 * 16;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);          // [2]
+  double* red = reinterpret_cast<double*>(tail + 16);          // [NW]
+  unsigned int* hist = reinterpret_cast<unsigned int*>(tail + 16 + 8 * NW);  // [NW][256] (RDF)
+
+  const int ibase = p.i_begin + blockIdx.x * B;
+  const int gI = ibase / B;  // global block index (i_begin is a multiple of B)
+  const int n = sp.nblk;
+  const int h = sym_partner_count(gI, n);
+  const int cpb = B / BJ;
+  const int U = (h + 1) * cpb;  // off-diagonal units first, then the diagonal block's chunks
+  const int ub = (int)(((long long)U * blockIdx.y) / gridDim.y);
+  const int ue = (int)(((long long)U * (blockIdx.y + 1)) / gridDim.y);
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  if (RDF) {
+    for (int k = tid; k < NW * kRdfBins; k += THREADS) hist[k] = 0u;
+  }
+  __syncthreads();
+
+  // unit -> (first j, count, partner offset or 0 for the diagonal)
+  auto unit_j0 = [&](int u, int& o) {
+    const int ob = u / cpb, q = u - ob * cpb;
+    o = (ob < h) ? ob + 1 : 0;
+    int J = gI + o;
+    if (J >= n) J -= n;
+    return J * B + q * BJ;
+  };
+  auto unit_nj = [&](int j0) {
+    const int blk_end = min(p.N, (j0 / B + 1) * B);
+    return min(BJ, blk_end - j0);
+  };
+  auto next_nonempty = [&](int u) {
+    while (u < ue) {
+      int o;
+      if (unit_nj(unit_j0(u, o)) > 0) break;
+      ++u;
+    }
+    return u;
+  };
+  auto issue = [&](int u, int st) {
+    int o;
+    const int j0 = unit_j0(u, o);
+    const uint32_t bytes = (uint32_t)unit_nj(j0) * 16u;
+    mbar_expect_tx(&bars[st], (RDF && PERIODIC) ? 2u * bytes : bytes);
+    bulk_g2s(tile_u + (size_t)st * BJ, p.jrec + j0, bytes, &bars[st]);
+    if (RDF && PERIODIC) bulk_g2s(tile_f + (size_t)st * BJ, p.posf + j0, bytes, &bars[st]);
+  };
+
+  int cur = next_nonempty(ub);
+  int nload = 0, ncons = 0;
+  if (cur < ue) {
+    if (tid == 0) issue(cur, 0);
+    nload = 1;
+  }
+
+  PairI<V> pi[NPAIR];
+  PairAcc<V> acc[NPAIR];
+  V s6run[NPAIR], wrun[NPAIR], fxrun[NPAIR], fyrun[NPAIR], fzrun[NPAIR];
+  const V zero2 = bc2<V>(0.f);
+  bool all_valid = true;
+#pragma unroll
+  for (int q = 0; q < NPAIR; ++q) {
+    int i0 = ibase + (2 * q) * THREADS + tid, i1 = i0 + THREADS;
+    pi[q].v_lo = i0 < p.i_end;
+    pi[q].v_hi = i1 < p.i_end;
+    all_valid = all_valid && pi[q].v_lo && pi[q].v_hi;
+    if (!pi[q].v_lo) i0 = p.i_end - 1;
+    if (!pi[q].v_hi) i1 = p.i_end - 1;
+    const uint4 r0 = p.jrec[i0], r1 = p.jrec[i1];
+    pi[q].ax = (int)r0.x; pi[q].ay = (int)r0.y; pi[q].az = (int)r0.z;
+    pi[q].bx = (int)r1.x; pi[q].by = (int)r1.y; pi[q].bz = (int)r1.z;
+    if (!PERIODIC || RDF) {
+      const float4 f0 = p.posf[i0], f1 = p.posf[i1];
+      pi[q].x2 = mk2<V>(f0.x, f1.x); pi[q].y2 = mk2<V>(f0.y, f1.y); pi[q].z2 = mk2<V>(f0.z, f1.z);
+    } else {
+      pi[q].x2 = pi[q].y2 = pi[q].z2 = zero2;
+    }
+    acc[q].fx = acc[q].fy = acc[q].fz = acc[q].s6 = acc[q].w = zero2;
+    s6run[q] = wrun[q] = fxrun[q] = fyrun[q] = fzrun[q] = zero2;
+  }
+  // is every lane of this warp holding real particles? (warp-uniform choice of the unmasked fast path)
+  const bool warp_all_valid = __all_sync(0xffffffffu, all_valid);
+  unsigned int* myhist = hist + warp * kRdfBins;
+  float4* myslice = slices + (size_t)warp * BJ;
+  uint4* mystage = stage + warp * 64;
+
+  while (cur < ue) {
+    const int nxt = next_nonempty(cur + 1);
+    if (nxt < ue) {
+      if (tid == 0) issue(nxt, nload & 1);
+      ++nload;
+    }
+    const int st = ncons & 1;
+    mbar_wait(&bars[st], (uint32_t)((ncons >> 1) & 1));
+    ++ncons;
+    int o;
+    const int j0 = unit_j0(cur, o);
+    const int nj = unit_nj(j0);
+    const uint4* tu = tile_u + (size_t)st * BJ;
+    const float4* tf = (RDF && PERIODIC) ? (tile_f + (size_t)st * BJ) : reinterpret_cast<const float4*>(tu);
+    float wgt;
+    if (o == 0) {
+      // ---- diagonal block: ordered loop over its own particles, self pair excluded ----
+      wgt = 1.f;
+      const int jrel0 = j0 - ibase - tid;
+#pragma unroll 2
+      for (int j = 0; j < nj; ++j) {
+        const uint4 uj = tu[j];
+        const int jr = jrel0 + j;
+#pragma unroll
+        for (int q = 0; q < NPAIR; ++q)
+          pair_body<V, PERIODIC, true, RDF>(uj, pi[q], acc[q], jr == (2 * q) * THREADS, jr == (2 * q + 1) * THREADS,
+                                            p, tf + j, myhist);
+      }
+    } else {
+      // ---- partner block: each unordered pair once, reaction accumulators travel with the rotating j ----
+      wgt = 2.f;
+      const int nchunk = (nj + 31) >> 5;
+      for (int c = 0; c < nchunk; ++c) {
+        const int jl = (c << 5) + lane;
+        // stage the chunk twice back to back: step k reads entry lane + k, no wrap arithmetic
+        const uint4 rec = tu[min(jl, nj - 1)];
+        __syncwarp();
+        mystage[lane] = rec;
+        mystage[lane + 32] = rec;
+        __syncwarp();
+        const uint4* sp_l = mystage + lane;
+        float rjx = 0.f, rjy = 0.f, rjz = 0.f;
+        const bool full = warp_all_valid && ((c << 5) + 32 <= nj);
+        const unsigned nxt_lane = (lane + 1) & 31;
+        if (full) {
+#pragma unroll 4
+          for (int k = 0; k < 32; ++k) {
+            const uint4 uj = sp_l[k];
+            const float4* pjf = tf + (c << 5) + ((lane + k) & 31);
+#pragma unroll
+            for (int q = 0; q < NPAIR; ++q)
+              pair_sym<V, PERIODIC, false, RDF>(uj, pi[q], acc[q], false, false, rjx, rjy, rjz, p, pjf, myhist);
+            rjx = __shfl_sync(0xffffffffu, rjx, nxt_lane);
+            rjy = __shfl_sync(0xffffffffu, rjy, nxt_lane);
+            rjz = __shfl_sync(0xffffffffu, rjz, nxt_lane);
+          }
+        } else {
+          for (int k = 0; k < 32; ++k) {
+            const uint4 uj = sp_l[k];
+            const int hl = (lane + k) & 31;               // home lane of the j I work on now
+            const bool jdead = ((c << 5) + hl) >= nj;
+            const float4* pjf = tf + min((c << 5) + hl, nj - 1);
+#pragma unroll
+            for (int q = 0; q < NPAIR; ++q)
+              pair_sym<V, PERIODIC, true, RDF>(uj, pi[q], acc[q], jdead || !pi[q].v_lo, jdead || !pi[q].v_hi, rjx,
+                                               rjy, rjz, p, pjf, myhist);
+            rjx = __shfl_sync(0xffffffffu, rjx, nxt_lane);
+            rjy = __shfl_sync(0xffffffffu, rjy, nxt_lane);
+            rjz = __shfl_sync(0xffffffffu, rjz, nxt_lane);
+          }
+        }
+        myslice[jl] = make_float4(rjx, rjy, rjz, 0.f);  // the accumulators are home again; jl < BJ always
+      }
+    }
+    // fold the unit's tile-level accumulators into the run-level ones (two-level float summation);
+    // an unordered pair of a partner block stands for two ordered pairs in the potential / virial sums
+    const V w2 = bc2<V>(wgt);
+#pragma unroll
+    for (int q = 0; q < NPAIR; ++q) {
+      s6run[q] = fma2(acc[q].s6, w2, s6run[q]);
+      wrun[q] = fma2(acc[q].w, w2, wrun[q]);
+      fxrun[q] = add2(fxrun[q], acc[q].fx);
+      fyrun[q] = add2(fyrun[q], acc[q].fy);
+      fzrun[q] = add2(fzrun[q], acc[q].fz);
+      acc[q].s6 = acc[q].w = acc[q].fx = acc[q].fy = acc[q].fz = zero2;
+    }
+    __syncthreads();  // slices complete; stage st free for the load after next
+    if (o != 0) {
+      // reaction row of this unit: sum the warps' slices in warp order, scale, one coalesced store per j
+      float4* row = sp.rpart + (size_t)blockIdx.x * sp.ncols + (size_t)(o - 1) * B + (j0 % B);
+      const float fs = p.fscale;
+      for (int jj = tid; jj < nj; jj += THREADS) {
+        float4 a = slices[jj];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) {
+          const float4 b = slices[(size_t)w * BJ + jj];
+          a.x += b.x; a.y += b.y; a.z += b.z;
+        }
+        row[jj] = make_float4(a.x * fs, a.y * fs, a.z * fs, 0.f);
+      }
+      __syncthreads();  // slices are rewritten by the next partner unit
+    }
+    cur = nxt;
+  }
+
+  // ---- epilogue: direct forces of my i-particles, per-particle potential, virial partial ----
+  const float fs = p.fscale;
+  double wsum = 0.;
+  float4* out = p.fpart + (size_t)blockIdx.y * p.ilocal_cap;
+#pragma unroll
+  for (int q = 0; q < NPAIR; ++q) {
+    const float2 fx = upk(fxrun[q]), fy = upk(fyrun[q]), fz = upk(fzrun[q]);
+    const float2 s6 = upk(s6run[q]), w = upk(wrun[q]);
+    const int il = (ibase - p.i_begin) + (2 * q) * THREADS + tid;
+    if (pi[q].v_lo) {
+      out[il] = make_float4(fx.x * fs, fy.x * fs, fz.x * fs, w.x * (1.f / 12.f) - 0.5f * s6.x);
+      wsum += (double)w.x;
+    }
+    if (pi[q].v_hi) {
+      out[il + THREADS] = make_float4(fx.y * fs, fy.y * fs, fz.y * fs, w.y * (1.f / 12.f) - 0.5f * s6.y);
+      wsum += (double)w.y;
+    }
+  }
+  const double wtot = block_sum<THREADS>(wsum, red);
+  if (tid == 0) p.blockW[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = wtot;
+  if (RDF) {
+    __syncthreads();
+    for (int b = tid; b < kRdfBins; b += THREADS) {
+      unsigned int c = 0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) c += hist[w * kRdfBins + b];
+      if (c) atomicAdd(&p.rdf[b], (unsigned long long)c);
+    }
+  }
+}
+
+inline size_t force_sym_smem_bytes(bool periodic, bool rdf, int bj, int threads) {
+  size_t b = (size_t)((rdf && periodic) ? 4 : 2) * bj * 16 + (size_t)(threads / 32) * (bj + 64) * 16 + 16 +
+             8 * (threads / 32);
+  if (rdf) b += (size_t)(threads / 32) * kRdfBins * 4;
+  return b;
+}
+
+}  // namespace ljmd

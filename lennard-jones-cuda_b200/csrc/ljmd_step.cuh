@@ -51,7 +51,49 @@ struct StepParams {
   double* part;     // [2][gridDim.x] per-block partial sums
   unsigned int* counter;  // last-block ticket
   DevScalars* sc;
+  // Newton-3 kernel: reaction rows (ljmd_force_sym.cuh)
+  int use_sym;      // reaction rows are in use
+  int nblk;         // global number of 512-particle blocks
+  int blk0;         // global index of this rank's first block
+  int n_itiles;     // i-tiles (rows) of this rank
+  int rp_stride;    // row stride of rpart = hmax * 512
+  int npad;         // padded particle count (world * shard capacity)
+  const float4* rpart;    // [n_itiles][rp_stride]
+  float4* rsum;           // [npad] rank-local column sums (world > 1)
+  const float4* rshard;   // [nloc] reaction totals after the reduce-scatter (world > 1)
 };
+
+constexpr int kBlockParticles = 512;   // = kITile of ljmd_core.cu / B of k_force_sym
+
+__host__ __device__ inline int partner_count(int g, int n) {
+  if (n & 1) return (n - 1) / 2;
+  return n / 2 - 1 + (g < n / 2 ? 1 : 0);
+}
+
+// Sum of the reaction rows that hold contributions for global particle j: i-tile I (global block gI) wrote
+// its reaction on block J = j / 512 at window slot o - 1, o = (J - gI) mod n, when 1 <= o <= partner_count(gI).
+// Fixed ascending tile order: deterministic.
+__device__ __forceinline__ float4 reaction_sum(const StepParams& p, int j) {
+  const int J = j / kBlockParticles, jj = j - J * kBlockParticles;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = 0; t < p.n_itiles; ++t) {
+    const int gI = p.blk0 + t;
+    int o = J - gI;
+    if (o < 0) o += p.nblk;
+    if (o >= 1 && o <= partner_count(gI, p.nblk)) {
+      const float4 g = p.rpart[(size_t)t * p.rp_stride + (size_t)(o - 1) * kBlockParticles + jj];
+      a.x += g.x; a.y += g.y; a.z += g.z;
+    }
+  }
+  return a;
+}
+
+// world > 1: column sums over this rank's rows for every particle (input of the reduce-scatter)
+__global__ void __launch_bounds__(256) k_reduce_reaction(const StepParams p) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= p.npad) return;
+  p.rsum[j] = (j < p.N) ? reaction_sum(p, j) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
 
 __device__ __forceinline__ uint32_t to_fixed(float x, double fix_scale) {
   // box fraction in 32-bit fixed point; the cast to 32 bits is the periodic wrap
@@ -219,6 +261,10 @@ __global__ void __launch_bounds__(kStepThreads) k_gather(const StepParams p, int
     for (int s = 1; s < p.nsplit; ++s) {
       const float4 g = p.fpart[(size_t)s * p.ilocal_cap + il];
       f.x += g.x; f.y += g.y; f.z += g.z; f.w += g.w;
+    }
+    if (p.use_sym) {   // Newton-3 kernel: add the reaction of every pair this particle was the j of
+      const float4 r = (p.world == 1) ? reaction_sum(p, p.i_begin + il) : p.rshard[il];
+      f.x += r.x; f.y += r.y; f.z += r.z;
     }
     pe = (double)f.w;
     float4 v = p.vel[il];

@@ -13,9 +13,13 @@ def env_rank_world():
             int(os.environ.get("LOCAL_RANK", "0")))
 
 
+BLOCK = 512   # particles per block of the force kernels (kITile in csrc/ljmd_core.cu)
+
+
 def shard_bounds(N, rank, world):
-    """Contiguous i-shard of `rank`: the same rule as the library (ljmd_plan / create_impl)."""
-    cnt = (N + world - 1) // world
+    """Contiguous i-shard of `rank`, in whole 512-particle blocks: the same rule as the library (ljmd_plan)."""
+    nblk = (N + BLOCK - 1) // BLOCK
+    cnt = ((nblk + world - 1) // world) * BLOCK
     return min(N, rank * cnt), min(N, (rank + 1) * cnt)
 
 

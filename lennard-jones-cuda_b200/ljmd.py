@@ -257,9 +257,10 @@ class LJSystem:
         return dict(force_ms=f.value, total_ms=t.value, force_launches=n.value)
 
     def launch_info(self):
-        buf = (C.c_int * 6)()
+        buf = (C.c_int * 8)()
         self._check(self._lib.ljmd_get_launch_info(self._h, buf))
-        return dict(num_sms=buf[0], i_tile=buf[1], j_splits=buf[2], force_ctas=buf[3], world=buf[4], n_local=buf[5])
+        return dict(num_sms=buf[0], i_tile=buf[1], j_splits=buf[2], force_ctas=buf[3], world=buf[4], n_local=buf[5],
+                    newton3=bool(buf[6]))
 
 
 def image_threshold(L, k=1):
@@ -269,11 +270,12 @@ def image_threshold(L, k=1):
 def plan(N, rank=0, world=1, num_sms=148):
     """Launch plan of the force kernel (host logic only; no device needed)."""
     lib = load_library()
-    buf = (C.c_int * 6)()
+    buf = (C.c_int * 8)()
     rc = lib.ljmd_plan(int(N), int(rank), int(world), int(num_sms), buf)
     if rc != 0:
         raise LJMDError(lib.ljmd_last_error().decode())
-    return dict(i_begin=buf[0], i_end=buf[1], i_tiles=buf[2], j_splits=buf[3], force_ctas=buf[4], i_tile=buf[5])
+    return dict(i_begin=buf[0], i_end=buf[1], i_tiles=buf[2], j_splits=buf[3], force_ctas=buf[4], i_tile=buf[5],
+                newton3=bool(buf[6]), partner_blocks=buf[7])
 
 
 def rdf_curve(N, L, dr2, counts):

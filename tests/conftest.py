@@ -45,6 +45,17 @@ def load_golden(name):
     return g
 
 
+@pytest.fixture(params=["default", "ordered", "sym"])
+def kernel(request, monkeypatch):
+    """Force-kernel choice for systems created inside the test: the library's own (ordered below 16 blocks,
+    Newton-3 above), or one of the two forced through LJMD_KERNEL (read at ljmd_create)."""
+    if request.param == "default":
+        monkeypatch.delenv("LJMD_KERNEL", raising=False)
+    else:
+        monkeypatch.setenv("LJMD_KERNEL", request.param)
+    return request.param
+
+
 @pytest.fixture(scope="session")
 def gpu_lib(pkg):
     """The CUDA library with a device behind it — GPU tests must never run on a fallback."""

@@ -63,7 +63,7 @@ def check_forces(oracle, pos, L, bc, dr2, f_gpu, sc_gpu, rdf_gpu=None, ref_force
 
 # ------------------------------------------------------------------ golden fixtures (reference outputs)
 @pytest.mark.parametrize("name", golden_names())
-def test_evaluation_matches_golden(pkg, oracle, gpu_lib, name):
+def test_evaluation_matches_golden(pkg, oracle, gpu_lib, kernel, name):
     g = load_golden(name)
     with make_system(pkg, g) as s:
         assert s.L == g["s0"]["L"] and s.rdf_dr2 == g["dr2"]
@@ -119,7 +119,7 @@ def oracle_step_from(oracle, g, pos, vel, frc, dt, canonical, bc):
 
 
 @pytest.mark.parametrize("name", golden_names())
-def test_single_step_from_own_state_is_tight(pkg, oracle, gpu_lib, name):
+def test_single_step_from_own_state_is_tight(pkg, oracle, gpu_lib, kernel, name):
     """One Integrate from the GPU's own (pos, vel, force): the drift is bit-identical to the CPU's, so the
     evaluation positions agree exactly, the post-step RDF is bit-exact and positions match to the bit."""
     g = load_golden(name)
@@ -168,7 +168,9 @@ def test_tvn_chi_and_trial_temperature(pkg, oracle, gpu_lib):
     (2048, 1.0, 0.0006, 0, 0, "gas"),       # L ~ 150: C5-sized box, sparse
     (16384, 1.0, 0.85, 0, 0, "lattice"),    # C2 at full size (oracle ~10 s)
 ])
-def test_evaluation_matches_oracle_live(pkg, oracle, gpu_lib, N, T, rho, canonical, bc, kind):
+def test_evaluation_matches_oracle_live(pkg, oracle, gpu_lib, kernel, N, T, rho, canonical, bc, kind):
+    if kernel == "default" and N >= 16384:
+        pytest.skip("default == sym at this size")
     snap = pkg.snapshots
     pos = snap.random_gas(N, rho, seed=11, periodic=bc == 0) if kind == "gas" else snap.lattice(N, rho, 0.05, seed=11)
     vel = snap.velocities(N, T, seed=11)
@@ -180,7 +182,7 @@ def test_evaluation_matches_oracle_live(pkg, oracle, gpu_lib, N, T, rho, canonic
 
 @pytest.mark.parametrize("N", [2, 3, 33, 511, 512, 513, 1025, 2049])
 @pytest.mark.parametrize("bc", [0, 1])
-def test_ragged_sizes(pkg, oracle, gpu_lib, N, bc):
+def test_ragged_sizes(pkg, oracle, gpu_lib, kernel, N, bc):
     rho = 0.5
     pos = pkg.snapshots.lattice(N, rho, 0.1, seed=N)
     vel = pkg.snapshots.velocities(N, 1.2, seed=N) if N > 2 else np.zeros((N, 4), np.float32)
@@ -190,7 +192,7 @@ def test_ragged_sizes(pkg, oracle, gpu_lib, N, bc):
         check_forces(oracle, pos, s.L, bc, s.rdf_dr2, frc, s.scalars(), s.rdf_counts())
 
 
-def test_positions_outside_the_box(pkg, oracle, gpu_lib):
+def test_positions_outside_the_box(pkg, oracle, gpu_lib, kernel):
     """Unwrapped coordinates (up to several box lengths out): forces still follow the minimum image and the
     RDF still reproduces fast_round() for |n| >= 2."""
     N, rho = 700, 0.6
@@ -227,7 +229,7 @@ def test_integrate_host_equals_device_resident_step(pkg, gpu_lib):
         assert a.scalars() == b.scalars()
 
 
-def test_runs_are_deterministic(pkg, gpu_lib):
+def test_runs_are_deterministic(pkg, gpu_lib, kernel):
     g = load_golden("mixed_tvn_periodic")
     outs = []
     for _ in range(2):

@@ -12,7 +12,7 @@
 #include <algorithm>
 #include <vector>
 
-#include "../lennard-jones-cuda_b200/csrc/ljmd_force.cuh"
+#include "../lennard-jones-cuda_b200/csrc/ljmd_force_sym.cuh"
 using namespace ljmd;
 
 #define CK(x)                                                                         \
@@ -109,6 +109,8 @@ struct Problem {
   float4* fpart;
   double* blockW;
   unsigned long long* rdf;
+  float4* rpart;   // [n][hmax*B] reaction rows for the symmetric kernel (B = 512)
+  int hmax;
   int sms;
 };
 
@@ -189,6 +191,96 @@ static void run_variant(const Problem& pb, const char* tag, int reps, int tile_j
   fflush(stdout);
 }
 
+template <typename V, bool PERIODIC, bool RDF, int THREADS, int MINB, int NPAIR>
+static void run_sym(const Problem& pb, const char* tag, int reps, int bj, std::vector<float4>* keep) {
+  auto kern = k_force_sym<V, PERIODIC, RDF, THREADS, MINB, NPAIR>;
+  const size_t smem = force_sym_smem_bytes(PERIODIC, RDF, bj, THREADS);
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaFuncAttributes fa;
+  CK(cudaFuncGetAttributes(&fa, kern));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
+  const int B = THREADS * 2 * NPAIR;
+  const int n = (pb.N + B - 1) / B;
+  const int units = (sym_max_partner_count(n) + 1) * (B / bj);
+  // splits: fill the machine with whole waves of equal-work CTAs
+  const long long slots = (long long)pb.sms * (occ > 0 ? occ : MINB);
+  int S = 1;
+  double bc = 1e300;
+  for (int s = 1; s <= units; ++s) {
+    const long long waves = ((long long)n * s + slots - 1) / slots;
+    const double cost = (double)waves * (ceil((double)units / s) + 0.5);
+    if (cost < bc * 0.999) { bc = cost; S = s; }
+  }
+  SymParams sp;
+  memset(&sp, 0, sizeof(sp));
+  ForceParams& fp = sp.f;
+  fp.jrec = PERIODIC ? pb.upos : reinterpret_cast<const uint4*>(pb.posf);
+  fp.posf = pb.posf; fp.fpart = pb.fpart; fp.blockW = pb.blockW; fp.rdf = pb.rdf;
+  fp.N = pb.N; fp.i_begin = 0; fp.i_end = pb.N; fp.ilocal_cap = pb.N; fp.tile_j = bj;
+  const double k2 = 4294967296.0 / pb.L;
+  fp.c2 = PERIODIC ? (float)(k2 * k2) : 1.f;
+  fp.fscale = PERIODIC ? (float)(4.0 * pb.L / 4294967296.0) : 4.f;
+  fp.cut_fast = (float)(PERIODIC ? 25.6 * 1.001 * k2 * k2 : 25.6 * 1.001);
+  fp.L = pb.L; fp.thr1 = (float)(0.5 * pb.L); fp.thr2 = (float)(1.5 * pb.L); fp.dr2 = 0.1f; fp.inv_dr2 = 10.f;
+  sp.rpart = pb.rpart; sp.ncols = pb.hmax * B; sp.nblk = n; sp.bj = bj;
+  dim3 grid(n, S);
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  const size_t rp_elems = (size_t)n * pb.hmax * B;
+  CK(cudaMemset(pb.rpart, 0, rp_elems * 16));
+  kern<<<grid, THREADS, smem>>>(sp);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  float best = 1e30f, sum = 0.f;
+  for (int r = 0; r < reps; ++r) {
+    CK(cudaEventRecord(e0));
+    kern<<<grid, THREADS, smem>>>(sp);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    best = std::min(best, ms);
+    sum += ms;
+  }
+  const double pairs = (double)pb.N * (pb.N - 1);
+  const double flop = PERIODIC ? 37. : 25.;
+  std::vector<float4> h((size_t)S * pb.N), hr(rp_elems);
+  CK(cudaMemcpy(h.data(), pb.fpart, h.size() * 16, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hr.data(), pb.rpart, hr.size() * 16, cudaMemcpyDeviceToHost));
+  double maxdiff = 0., scale = 0., maxw = 0.;
+  for (int i = 0; i < pb.N; ++i) {
+    float4 a = h[i];
+    for (int s = 1; s < S; ++s) { float4 g = h[(size_t)s * pb.N + i]; a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w; }
+    {
+      const int J = i / B, jj = i % B;
+      for (int I = 0; I < n; ++I) {
+        int o = J - I;
+        if (o < 0) o += n;
+        if (o >= 1 && o <= sym_partner_count(I, n)) {
+          float4 g = hr[(size_t)I * pb.hmax * B + (size_t)(o - 1) * B + jj];
+          a.x += g.x; a.y += g.y; a.z += g.z;
+        }
+      }
+    }
+    if (!keep->empty()) {
+      maxdiff = std::max(maxdiff, (double)fabsf(a.x - (*keep)[i].x));
+      maxdiff = std::max(maxdiff, (double)fabsf(a.y - (*keep)[i].y));
+      maxdiff = std::max(maxdiff, (double)fabsf(a.z - (*keep)[i].z));
+      scale = std::max(scale, (double)fabsf((*keep)[i].x));
+    }
+    maxw += a.w;
+  }
+  double wref = 0.;
+  for (int i = 0; i < pb.N && !keep->empty(); ++i) wref += (*keep)[i].w;
+  printf("sym   %-44s regs %3d occ %d grid %4dx%-3d smem %6zu | best %8.4f ms avg %8.4f ms | %7.3f Gpairs/s %6.2f TFLOP/s(alg) "
+         "| maxdiff %.2e/%.2e sum_pe %.6e vs %.6e\n",
+         tag, fa.numRegs, occ, n, S, smem, best, sum / reps, pairs / (best * 1e-3) / 1e9,
+         pairs * flop / (best * 1e-3) / 1e12, maxdiff, scale, maxw, wref);
+  fflush(stdout);
+}
+
 int main(int argc, char** argv) {
   const int N = argc > 1 ? atoi(argv[1]) : 65536;
   const int reps = argc > 2 ? atoi(argv[2]) : 5;
@@ -199,14 +291,6 @@ int main(int argc, char** argv) {
   const int sms = prop.multiProcessorCount;
   printf("device %s, %d SMs, clock %.0f MHz; N=%d L=%.4f\n", prop.name, sms, prop.clockRate / 1e3, N, L);
 
-  float* d_out;
-  CK(cudaMalloc(&d_out, (size_t)sms * 8 * 256 * 4));
-  run_micro<0>("FFMA x2 (scalar, 3-reg)", 16, sms, d_out);
-  run_micro<1>("FFMA2 x1 (2 lanes)", 16, sms, d_out);          // counted in scalar-FMA equivalents: 8 FFMA2 = 16
-  run_micro<2>("IADD + I2FP + FADD", 8, sms, d_out);           // counted in I2FP ops
-  run_micro<3>("MUFU.RCP", 8, sms, d_out);
-  run_micro<4>("IADD3 x2", 16, sms, d_out);
-  run_micro<5>("LJ mix (per 2 pairs: 7 FFMA2,6 IADD,6 I2FP,2 MUFU)", 16, sms, d_out);  // counted in pairs*... see source
 
   // lattice + jitter, deterministic LCG
   std::vector<float4> hp(N);
@@ -231,31 +315,27 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&pb.fpart, smax * N * 16));
   CK(cudaMalloc(&pb.blockW, smax * (N / 64 + 1) * sizeof(double)));
   CK(cudaMalloc(&pb.rdf, 256 * 8));
+  pb.hmax = sym_max_partner_count((N + 511) / 512);
+  if (pb.hmax < 1) pb.hmax = 1;
+  CK(cudaMalloc(&pb.rpart, (size_t)((N + 511) / 512) * pb.hmax * 512 * 16));
   CK(cudaMemset(pb.rdf, 0, 256 * 8));
   CK(cudaMemcpy(pb.upos, hu.data(), (size_t)N * 16, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(pb.posf, hp.data(), (size_t)N * 16, cudaMemcpyHostToDevice));
 
   std::vector<float4> keepP, keepO;
   //                 V   PER    RDF   THR MINB NPAIR UNROLL PIPE
-  run_variant<P2, true, false, 128, 4, 2, 4>(pb, "periodic P2 t128 b4 np2 u4 (baseline)", reps, 1024, &keepP);
-  run_variant<P2, true, false, 128, 4, 2, 4, 1>(pb, "periodic P2 t128 b4 np2 pipe1", reps, 1024, &keepP);
-  run_variant<P2, true, false, 128, 4, 2, 4, 2>(pb, "periodic P2 t128 b4 np2 pipe2", reps, 1024, &keepP);
-  run_variant<P2, true, false, 128, 3, 2, 4, 4>(pb, "periodic P2 t128 b3 np2 pipe4", reps, 1024, &keepP);
-  run_variant<P2, true, false, 128, 4, 2, 4, 4>(pb, "periodic P2 t128 b4 np2 pipe4", reps, 1024, &keepP);
-  run_variant<P2, true, false, 256, 2, 2, 4, 2>(pb, "periodic P2 t256 b2 np2 pipe2", reps, 1024, &keepP);
-  run_variant<P2, true, false, 128, 8, 1, 4, 2>(pb, "periodic P2 t128 b8 np1 pipe2 tile512", reps, 512, &keepP);
-  run_variant<P2, true, false, 128, 8, 1, 4, 4>(pb, "periodic P2 t128 b8 np1 pipe4 tile512", reps, 512, &keepP);
-  run_variant<P2, true, false, 128, 6, 1, 4, 4>(pb, "periodic P2 t128 b6 np1 pipe4 tile512", reps, 512, &keepP);
-  run_variant<P2, true, false, 128, 8, 1, 8>(pb, "periodic P2 t128 b8 np1 u8 tile512", reps, 512, &keepP);
-  run_variant<P2, true, false, 128, 3, 3, 2, 2>(pb, "periodic P2 t128 b3 np3 pipe2", reps, 1024, &keepP);
-  run_variant<P2, true, false, 128, 3, 3, 2, 1>(pb, "periodic P2 t128 b3 np3 pipe1", reps, 1024, &keepP);
-  run_variant<S2, true, false, 128, 4, 2, 4, 2>(pb, "periodic S2 t128 b4 np2 pipe2", reps, 1024, &keepP);
-  run_variant<P2, true, true, 128, 3, 2, 4>(pb, "periodic+RDF P2 t128 b3 np2 u4", reps, 1024, &keepP);
-  run_variant<P2, true, true, 128, 3, 2, 4, 2>(pb, "periodic+RDF P2 t128 b3 np2 pipe2", reps, 1024, &keepP);
-  run_variant<P2, false, false, 128, 4, 2, 4>(pb, "open P2 t128 b4 np2 u4 (baseline)", reps, 1024, &keepO);
-  run_variant<P2, false, false, 128, 4, 2, 4, 2>(pb, "open P2 t128 b4 np2 pipe2", reps, 1024, &keepO);
-  run_variant<P2, false, false, 128, 4, 2, 4, 4>(pb, "open P2 t128 b4 np2 pipe4", reps, 1024, &keepO);
-  run_variant<P2, false, false, 128, 8, 1, 4, 4>(pb, "open P2 t128 b8 np1 pipe4 tile512", reps, 512, &keepO);
-  run_variant<P2, false, true, 128, 3, 2, 4, 2>(pb, "open+RDF P2 t128 b3 np2 pipe2", reps, 1024, &keepO);
+  run_variant<P2, true, false, 128, 4, 2, 4>(pb, "periodic ordered P2 t128 b4 np2 u4 (baseline)", reps, 1024, &keepP);
+  run_sym<P2, true, false, 128, 4, 2>(pb, "periodic sym P2 t128 b4 np2 bj256", reps, 256, &keepP);
+  run_sym<P2, true, false, 128, 3, 2>(pb, "periodic sym P2 t128 b3 np2 bj256", reps, 256, &keepP);
+  run_sym<P2, true, false, 128, 4, 2>(pb, "periodic sym P2 t128 b4 np2 bj128", reps, 128, &keepP);
+  run_sym<P2, true, false, 128, 4, 2>(pb, "periodic sym P2 t128 b4 np2 bj512", reps, 512, &keepP);
+  run_sym<S2, true, false, 128, 4, 2>(pb, "periodic sym S2 t128 b4 np2 bj256", reps, 256, &keepP);
+  run_sym<P2, true, false, 256, 2, 2>(pb, "periodic sym P2 t256 b2 np2 bj256", reps, 256, &keepP);
+  run_variant<P2, true, true, 128, 3, 2, 4>(pb, "periodic+RDF ordered P2 t128 b3 np2 u4", reps, 1024, &keepP);
+  run_sym<P2, true, true, 128, 3, 2>(pb, "periodic+RDF sym P2 t128 b3 np2 bj256", reps, 256, &keepP);
+  run_variant<P2, false, false, 128, 4, 2, 4>(pb, "open ordered P2 t128 b4 np2 u4 (baseline)", reps, 1024, &keepO);
+  run_sym<P2, false, false, 128, 4, 2>(pb, "open sym P2 t128 b4 np2 bj256", reps, 256, &keepO);
+  run_sym<P2, false, false, 128, 3, 2>(pb, "open sym P2 t128 b3 np2 bj256", reps, 256, &keepO);
+  run_sym<P2, false, true, 128, 3, 2>(pb, "open+RDF sym P2 t128 b3 np2 bj256", reps, 256, &keepO);
   return 0;
 }
