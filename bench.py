@@ -24,8 +24,9 @@ sys.path.insert(0, ROOT)
 import ljpkg  # noqa: E402
 
 DT = 0.004                      # GUI/task default (reference src/gui/mainwindow.cpp:150, input/*)
-FLOP_PER_PAIR = {0: 37, 1: 25, 2: 25}   # periodic / open
-INSTR_PER_PAIR = {0: 29, 1: 20, 2: 20}  # SURVEY.md §8d minimal FP32-pipe instruction counts
+FLOP_PER_PAIR = {0: 37, 1: 25, 2: 25}   # flops of one ORDERED pair evaluation, periodic / open
+REACTION_FLOP = 6                        # Newton-3 kernel: 3 more FMAs per unordered pair put -f_ij on particle j
+INSTR_PER_PAIR = {0: 29, 1: 20, 2: 20}  # SURVEY.md §8d minimal FP32-pipe instruction counts per ordered pair
 SM_COUNT, FP32_LANES = 148, 128
 
 
@@ -286,19 +287,28 @@ def main_ours(args, pkg):
     peaks = measured_peaks()
     sm_max = float(peaks.get("sm_max_mhz", 1965.0))
     fp32_peak = SM_COUNT * FP32_LANES * 2 * sm_max * 1e6 / 1e12      # TFLOP/s at max clock
-    flops_per_launch = FLOP_PER_PAIR[cfg["bc"]] * pairs_per_step / world
+    # The Newton-3 kernel evaluates every UNORDERED pair once (37 + 6 flops periodic) where the reference's
+    # double loop evaluates both orders (2 x 37): `achieved` counts the flops the kernel's own algorithm
+    # executes; `ordered_pair_equivalent` is the same launch priced at the reference's algorithm.
+    newton3 = bool(info.get("newton3"))
+    fpp = FLOP_PER_PAIR[cfg["bc"]]
+    evals_per_launch = pairs_per_step / world / (2.0 if newton3 else 1.0)
+    flops_per_launch = (fpp + (REACTION_FLOP if newton3 else 0)) * evals_per_launch
     achieved = flops_per_launch / (force_ms * 1e-3) / 1e12
+    ordered_equiv = fpp * pairs_per_step / world / (force_ms * 1e-3) / 1e12
     clk = (clocks or {}).get("sm_mhz") or sm_max
-    pipe_util = (INSTR_PER_PAIR[cfg["bc"]] * pairs_per_step / world / (force_ms * 1e-3)) / (SM_COUNT * FP32_LANES * clk * 1e6)
     roofline = {
         "bound": "fp32",
-        "kernel": "k_force (all-pairs LJ force/potential/virial)",
+        "kernel": ("k_force_sym (all-pairs LJ force/potential/virial, each unordered pair once)" if newton3
+                   else "k_force (all-pairs LJ force/potential/virial, ordered pairs)"),
         "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
         "peak_source": f"148 SMs x 128 FP32 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz; that file holds "
                        "no FP32 CUDA-core figure — the kernel is FP32-issue bound, not HBM or tensor bound)",
-        "flop_per_pair": FLOP_PER_PAIR[cfg["bc"]], "pairs_per_launch": pairs_per_step / world,
+        "flop_per_pair_evaluation": fpp + (REACTION_FLOP if newton3 else 0),
+        "pair_evaluations_per_launch": evals_per_launch,
+        "ordered_pair_equivalent": {"tflops": ordered_equiv, "frac": ordered_equiv / fp32_peak,
+                                    "note": "same launch priced as the reference's ordered double loop (37/25 flop x N(N-1))"},
         "kernel_ms": force_ms, "kernel_share_of_step": force_ms * args.steps / dev_ms,
-        "fp32_pipe_util_at_sampled_clock": pipe_util,
         "traffic": None,
     }
     if rank == 0:
