@@ -95,7 +95,7 @@ __device__ __forceinline__ void pair_sym(const uint4& uj, const PairI<V>& pi, Pa
 }
 
 // grid: (i-tiles of this rank, splits).  block: THREADS.  dyn smem: force_sym_smem_bytes().
-template <typename V, bool PERIODIC, bool RDF, int THREADS, int MINB, int NPAIR>
+template <typename V, bool PERIODIC, bool RDF, int THREADS, int MINB, int NPAIR, int UNROLLK = 4>
 __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp) {
   constexpr int IPT = 2 * NPAIR;
   constexpr int B = THREADS * IPT;
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
         const bool full = warp_all_valid && ((c << 5) + 32 <= nj);
         const unsigned nxt_lane = (lane + 1) & 31;
         if (full) {
-#pragma unroll 4
+#pragma unroll UNROLLK
           for (int k = 0; k < 32; ++k) {
             const uint4 uj = sp_l[k];
             const float4* pjf = tf + (c << 5) + ((lane + k) & 31);

@@ -191,9 +191,9 @@ static void run_variant(const Problem& pb, const char* tag, int reps, int tile_j
   fflush(stdout);
 }
 
-template <typename V, bool PERIODIC, bool RDF, int THREADS, int MINB, int NPAIR>
+template <typename V, bool PERIODIC, bool RDF, int THREADS, int MINB, int NPAIR, int UNROLLK = 4>
 static void run_sym(const Problem& pb, const char* tag, int reps, int bj, std::vector<float4>* keep) {
-  auto kern = k_force_sym<V, PERIODIC, RDF, THREADS, MINB, NPAIR>;
+  auto kern = k_force_sym<V, PERIODIC, RDF, THREADS, MINB, NPAIR, UNROLLK>;
   const size_t smem = force_sym_smem_bytes(PERIODIC, RDF, bj, THREADS);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaFuncAttributes fa;
@@ -223,12 +223,13 @@ static void run_sym(const Problem& pb, const char* tag, int reps, int bj, std::v
   fp.fscale = PERIODIC ? (float)(4.0 * pb.L / 4294967296.0) : 4.f;
   fp.cut_fast = (float)(PERIODIC ? 25.6 * 1.001 * k2 * k2 : 25.6 * 1.001);
   fp.L = pb.L; fp.thr1 = (float)(0.5 * pb.L); fp.thr2 = (float)(1.5 * pb.L); fp.dr2 = 0.1f; fp.inv_dr2 = 10.f;
-  sp.rpart = pb.rpart; sp.ncols = pb.hmax * B; sp.nblk = n; sp.bj = bj;
+  const int hmax = std::max(1, sym_max_partner_count(n));
+  sp.rpart = pb.rpart; sp.ncols = hmax * B; sp.nblk = n; sp.bj = bj;
   dim3 grid(n, S);
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
-  const size_t rp_elems = (size_t)n * pb.hmax * B;
+  const size_t rp_elems = (size_t)n * std::max(1, sym_max_partner_count(n)) * B;
   CK(cudaMemset(pb.rpart, 0, rp_elems * 16));
   kern<<<grid, THREADS, smem>>>(sp);
   CK(cudaGetLastError());
@@ -259,7 +260,7 @@ static void run_sym(const Problem& pb, const char* tag, int reps, int bj, std::v
         int o = J - I;
         if (o < 0) o += n;
         if (o >= 1 && o <= sym_partner_count(I, n)) {
-          float4 g = hr[(size_t)I * pb.hmax * B + (size_t)(o - 1) * B + jj];
+          float4 g = hr[(size_t)I * hmax * B + (size_t)(o - 1) * B + jj];
           a.x += g.x; a.y += g.y; a.z += g.z;
         }
       }
@@ -317,7 +318,7 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&pb.rdf, 256 * 8));
   pb.hmax = sym_max_partner_count((N + 511) / 512);
   if (pb.hmax < 1) pb.hmax = 1;
-  CK(cudaMalloc(&pb.rpart, (size_t)((N + 511) / 512) * pb.hmax * 512 * 16));
+  CK(cudaMalloc(&pb.rpart, ((size_t)N * N / 256 + 4096) * 16));   // enough for blocks of 256 and up
   CK(cudaMemset(pb.rdf, 0, 256 * 8));
   CK(cudaMemcpy(pb.upos, hu.data(), (size_t)N * 16, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(pb.posf, hp.data(), (size_t)N * 16, cudaMemcpyHostToDevice));
@@ -325,17 +326,22 @@ int main(int argc, char** argv) {
   std::vector<float4> keepP, keepO;
   //                 V   PER    RDF   THR MINB NPAIR UNROLL PIPE
   run_variant<P2, true, false, 128, 4, 2, 4>(pb, "periodic ordered P2 t128 b4 np2 u4 (baseline)", reps, 1024, &keepP);
-  run_sym<P2, true, false, 128, 4, 2>(pb, "periodic sym P2 t128 b4 np2 bj256", reps, 256, &keepP);
-  run_sym<P2, true, false, 128, 3, 2>(pb, "periodic sym P2 t128 b3 np2 bj256", reps, 256, &keepP);
-  run_sym<P2, true, false, 128, 4, 2>(pb, "periodic sym P2 t128 b4 np2 bj128", reps, 128, &keepP);
-  run_sym<P2, true, false, 128, 4, 2>(pb, "periodic sym P2 t128 b4 np2 bj512", reps, 512, &keepP);
-  run_sym<S2, true, false, 128, 4, 2>(pb, "periodic sym S2 t128 b4 np2 bj256", reps, 256, &keepP);
-  run_sym<P2, true, false, 256, 2, 2>(pb, "periodic sym P2 t256 b2 np2 bj256", reps, 256, &keepP);
-  run_variant<P2, true, true, 128, 3, 2, 4>(pb, "periodic+RDF ordered P2 t128 b3 np2 u4", reps, 1024, &keepP);
-  run_sym<P2, true, true, 128, 3, 2>(pb, "periodic+RDF sym P2 t128 b3 np2 bj256", reps, 256, &keepP);
+  run_sym<P2, true, false, 128, 4, 2, 4>(pb, "periodic sym t128 b4 np2 uk4 bj256", reps, 256, &keepP);
+  run_sym<P2, true, false, 128, 3, 2, 4>(pb, "periodic sym t128 b3 np2 uk4 bj256", reps, 256, &keepP);
+  run_sym<P2, true, false, 128, 3, 2, 2>(pb, "periodic sym t128 b3 np2 uk2 bj256", reps, 256, &keepP);
+  run_sym<P2, true, false, 128, 3, 2, 8>(pb, "periodic sym t128 b3 np2 uk8 bj256", reps, 256, &keepP);
+  run_sym<P2, true, false, 128, 4, 2, 2>(pb, "periodic sym t128 b4 np2 uk2 bj256", reps, 256, &keepP);
+  run_sym<P2, true, false, 128, 4, 2, 8>(pb, "periodic sym t128 b4 np2 uk8 bj256", reps, 256, &keepP);
+  run_sym<P2, true, false, 128, 2, 3, 2>(pb, "periodic sym t128 b2 np3 uk2 bj384", reps, 384, &keepP);
+  run_sym<P2, true, false, 128, 3, 3, 2>(pb, "periodic sym t128 b3 np3 uk2 bj384", reps, 384, &keepP);
+  run_sym<P2, true, false, 128, 2, 4, 2>(pb, "periodic sym t128 b2 np4 uk2 bj256", reps, 256, &keepP);
+  run_sym<P2, true, false, 64, 6, 2, 4>(pb, "periodic sym t64 b6 np2 uk4 bj256", reps, 256, &keepP);
+  run_sym<P2, true, false, 64, 8, 2, 4>(pb, "periodic sym t64 b8 np2 uk4 bj256", reps, 256, &keepP);
+  run_sym<P2, true, false, 256, 1, 2, 4>(pb, "periodic sym t256 b1 np2 uk4 bj256", reps, 256, &keepP);
+  run_sym<P2, true, false, 128, 6, 1, 4>(pb, "periodic sym t128 b6 np1 uk4 bj256", reps, 256, &keepP);
   run_variant<P2, false, false, 128, 4, 2, 4>(pb, "open ordered P2 t128 b4 np2 u4 (baseline)", reps, 1024, &keepO);
-  run_sym<P2, false, false, 128, 4, 2>(pb, "open sym P2 t128 b4 np2 bj256", reps, 256, &keepO);
-  run_sym<P2, false, false, 128, 3, 2>(pb, "open sym P2 t128 b3 np2 bj256", reps, 256, &keepO);
-  run_sym<P2, false, true, 128, 3, 2>(pb, "open+RDF sym P2 t128 b3 np2 bj256", reps, 256, &keepO);
+  run_sym<P2, false, false, 128, 4, 2, 4>(pb, "open sym t128 b4 np2 uk4 bj256", reps, 256, &keepO);
+  run_sym<P2, false, false, 128, 3, 2, 4>(pb, "open sym t128 b3 np2 uk4 bj256", reps, 256, &keepO);
+  run_sym<P2, false, false, 128, 3, 3, 2>(pb, "open sym t128 b3 np3 uk2 bj384", reps, 384, &keepO);
   return 0;
 }
