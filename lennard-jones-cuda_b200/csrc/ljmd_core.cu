@@ -194,7 +194,7 @@ template <bool PERIODIC, bool RDF>
 static cudaError_t launch_force_t(ljmd_system* s, const ForceParams& fp) {
   constexpr int MINB = RDF ? kMinBlocksRdf : kMinBlocks;
   auto kern = k_force<P2, PERIODIC, RDF, kForceThreads, MINB, kNPair, kUnroll>;
-  const size_t smem = force_smem_bytes(PERIODIC, RDF, kTileJ, kForceThreads);
+  const size_t smem = force_smem_bytes(RDF, kTileJ, kForceThreads);
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -210,7 +210,7 @@ template <bool PERIODIC, bool RDF>
 static cudaError_t launch_force_sym_t(ljmd_system* s, const SymParams& sp) {
   constexpr int MINB = RDF ? kMinBlocksRdf : kSymMinBlocks;
   auto kern = k_force_sym<P2, PERIODIC, RDF, kForceThreads, MINB, kNPair>;
-  const size_t smem = force_sym_smem_bytes(PERIODIC, RDF, kSymBJ, kForceThreads);
+  const size_t smem = force_sym_smem_bytes(RDF, kSymBJ, kForceThreads);
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -15,9 +15,11 @@
 //  * open / hard-wall boxes: j-records are the float positions, FADD2 differences.
 //  * potential and virial are two packed accumulators per pair (sum r^-6 and
 //    sum u, u = 12 r^-12 - 6 r^-6), reduced by warp shuffles to one double per CTA.
-//  * RDF (on request): pairs whose fast r^2 is within the histogram range re-derive
-//    r^2 with the reference CPU path's exact float/double sequence and hit a
-//    per-warp shared-memory histogram; bins are bit-exact with MDSystem.cpp:269-285.
+//  * RDF (on request): pairs whose fast r^2 is within the histogram range are pushed
+//    (ballot + popc compaction) on a per-warp shared-memory queue; whenever 32 are
+//    waiting, all 32 lanes re-derive r^2 with the reference CPU path's exact
+//    float/double sequence and hit a per-warp shared-memory histogram; bins are
+//    bit-exact with MDSystem.cpp:269-285.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -167,15 +169,54 @@ __device__ __forceinline__ float image_exact(float d, const ForceParams& p) {
   return (float)__dadd_rn((double)d, -__dmul_rn(p.L, nn));
 }
 
+// ---- RDF: per-warp compaction queue -----------------------------------------------------------------
+// In-range pairs are rare (543 rho* of N neighbours), so evaluating the exact sequence inside the pair loop
+// leaves most lanes idle.  Instead each warp queues (i, j) index pairs in shared memory and drains them 32 at
+// a time with every lane busy.  Bit 31 of the i index marks an unordered pair of the Newton-3 kernel, which
+// stands for (i,j) and (j,i): both fall in the same bin (the reference sequence is odd in the separation).
+constexpr int kRdfQueueCap = 128;   // < 32 waiting + at most 64 pushed by one call
+struct RdfCtx {
+  uint2* q;            // this warp's queue
+  unsigned int* hist;  // this warp's 256-bin histogram
+  int n;               // queue length (warp-uniform)
+};
+
 template <bool PERIODIC>
-__device__ __forceinline__ void rdf_slow(float xi, float yi, float zi, const float4& pj, const ForceParams& p,
-                                         unsigned int* hist, unsigned int inc = 1u) {
-  float rx = __fsub_rn(xi, pj.x), ry = __fsub_rn(yi, pj.y), rz = __fsub_rn(zi, pj.z);
+__device__ __forceinline__ void rdf_exact_one(const uint2 e, const ForceParams& p, unsigned int* hist) {
+  const float4 a = p.posf[e.x & 0x7fffffffu], b = p.posf[e.y];
+  float rx = __fsub_rn(a.x, b.x), ry = __fsub_rn(a.y, b.y), rz = __fsub_rn(a.z, b.z);   // MDSystem.cpp:269-271
   if (PERIODIC) { rx = image_exact(rx, p); ry = image_exact(ry, p); rz = image_exact(rz, p); }
   // MDSystem.cpp:279 in float, un-fused, left to right
-  float r2 = __fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz));
-  int b = rdf_bin_exact(r2, p.dr2, p.inv_dr2);
-  if ((unsigned)b < (unsigned)kRdfBins) atomicAdd(&hist[b], inc);
+  const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz));
+  const int bin = rdf_bin_exact(r2, p.dr2, p.inv_dr2);
+  if ((unsigned)bin < (unsigned)kRdfBins) atomicAdd(&hist[bin], 1u + (e.x >> 31));
+}
+
+// drain whole groups of 32 (all == false) or everything (all == true)
+template <bool PERIODIC>
+__device__ __forceinline__ void rdf_drain(RdfCtx& R, const ForceParams& p, bool all) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  while (R.n >= 32 || (all && R.n > 0)) {
+    const int cnt = min(32, R.n);
+    if (lane < cnt) rdf_exact_one<PERIODIC>(R.q[R.n - cnt + lane], p, R.hist);
+    R.n -= cnt;
+  }
+  __syncwarp();
+}
+
+// c_lo / c_hi: this lane's lo / hi pair is inside the histogram range (by the fast r^2, with margin)
+template <bool PERIODIC>
+__device__ __forceinline__ void rdf_push(RdfCtx& R, bool c_lo, bool c_hi, unsigned i_lo, unsigned i_hi, unsigned j,
+                                         const ForceParams& p) {
+  const unsigned m_lo = __ballot_sync(0xffffffffu, c_lo), m_hi = __ballot_sync(0xffffffffu, c_hi);
+  if ((m_lo | m_hi) == 0u) return;   // warp-uniform: the common case costs two votes and a branch
+  const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
+  if (c_lo) R.q[R.n + __popc(m_lo & lt)] = make_uint2(i_lo, j);
+  R.n += __popc(m_lo);
+  if (c_hi) R.q[R.n + __popc(m_hi & lt)] = make_uint2(i_hi, j);
+  R.n += __popc(m_hi);
+  if (R.n >= 32) rdf_drain<PERIODIC>(R, p, false);
 }
 
 // One pair of i-particles (two lanes of V).
@@ -187,13 +228,16 @@ struct PairAcc {
 template <typename V>
 struct PairI {
   int ax, ay, az, bx, by, bz;  // fixed-point coordinates of the two particles (periodic)
-  V x2, y2, z2;                // float coordinates (open boxes; RDF slow path)
+  V x2, y2, z2;                // float coordinates (open boxes)
+  unsigned i_lo, i_hi;         // global indices (RDF queue entries)
   bool v_lo, v_hi;             // lane holds a real particle (not a clamped duplicate)
 };
 
+// ORDERED evaluation of (i_lo, j) and (i_hi, j): force, potential and virial land on the i side only.
+// DIAG: the tile overlaps this CTA's own particles, self_* flags exclude the self pair.
 template <typename V, bool PERIODIC, bool DIAG, bool RDF>
 __device__ __forceinline__ void pair_body(const uint4& uj, const PairI<V>& pi, PairAcc<V>& acc, bool self_lo,
-                                          bool self_hi, const ForceParams& p, const float4* pjf, unsigned int* hist) {
+                                          bool self_hi, const ForceParams& p, unsigned jglobal, RdfCtx& R) {
   V dx, dy, dz;
   if (PERIODIC) {
     // the wrap of the 32-bit subtract IS the minimum image
@@ -226,68 +270,8 @@ __device__ __forceinline__ void pair_body(const uint4& uj, const PairI<V>& pi, P
   acc.w = add2(acc.w, u);
   if (RDF) {
     // clamped duplicate lanes (v_* false) and the self pair never count
-    if (r2s.x < p.cut_fast && pi.v_lo && !(DIAG && self_lo)) {
-      const float2 xs = upk(pi.x2), ys = upk(pi.y2), zs = upk(pi.z2);
-      rdf_slow<PERIODIC>(xs.x, ys.x, zs.x, *pjf, p, hist);
-    }
-    if (r2s.y < p.cut_fast && pi.v_hi && !(DIAG && self_hi)) {
-      const float2 xs = upk(pi.x2), ys = upk(pi.y2), zs = upk(pi.z2);
-      rdf_slow<PERIODIC>(xs.y, ys.y, zs.y, *pjf, p, hist);
-    }
-  }
-}
-
-// ---- the same pair evaluation split in two stages for software pipelining -----------------------------
-// stage A (mostly ALU/XU pipes): separation, r^2, 1/r^2.  stage B (FMA pipe): LJ polynomial + accumulation.
-// The main loop runs stage A of batch b+1 next to stage B of batch b, so the packed-FMA work of one batch
-// and the integer subtract / I2FP / MUFU work of the next are independent instruction streams that the
-// scheduler can interleave (ptxas does not software-pipeline across loop iterations by itself).
-template <typename V>
-struct Stage {
-  V dx, dy, dz, y;
-  float2 r2s;  // only live in RDF variants
-};
-
-template <typename V, bool PERIODIC>
-__device__ __forceinline__ void stage_a(const uint4& uj, const PairI<V>& pi, Stage<V>& st) {
-  if (PERIODIC) {
-    st.dx = mk2<V>(__int2float_rn(pi.ax - (int)uj.x), __int2float_rn(pi.bx - (int)uj.x));
-    st.dy = mk2<V>(__int2float_rn(pi.ay - (int)uj.y), __int2float_rn(pi.by - (int)uj.y));
-    st.dz = mk2<V>(__int2float_rn(pi.az - (int)uj.z), __int2float_rn(pi.bz - (int)uj.z));
-  } else {
-    st.dx = sub2(pi.x2, bc2<V>(__uint_as_float(uj.x)));
-    st.dy = sub2(pi.y2, bc2<V>(__uint_as_float(uj.y)));
-    st.dz = sub2(pi.z2, bc2<V>(__uint_as_float(uj.z)));
-  }
-  const V r2 = fma2(st.dz, st.dz, fma2(st.dy, st.dy, mul2(st.dx, st.dx)));
-  st.r2s = upk(r2);
-  st.y = mk2<V>(rcp_approx(st.r2s.x), rcp_approx(st.r2s.y));
-}
-
-template <typename V, bool PERIODIC, bool RDF>
-__device__ __forceinline__ void stage_b(const Stage<V>& st, const PairI<V>& pi, PairAcc<V>& acc, const ForceParams& p,
-                                        const float4* pjf, unsigned int* hist) {
-  V x = st.y;
-  if (PERIODIC) x = mul2(x, bc2<V>(p.c2));
-  const V x2 = mul2(x, x);
-  const V r6 = mul2(x2, x);
-  const V t = fma2(r6, bc2<V>(12.f), bc2<V>(-6.f));
-  const V u = mul2(r6, t);
-  const V s = mul2(u, x);
-  acc.fx = fma2(st.dx, s, acc.fx);
-  acc.fy = fma2(st.dy, s, acc.fy);
-  acc.fz = fma2(st.dz, s, acc.fz);
-  acc.s6 = add2(acc.s6, r6);
-  acc.w = add2(acc.w, u);
-  if (RDF) {
-    if (st.r2s.x < p.cut_fast && pi.v_lo) {
-      const float2 xs = upk(pi.x2), ys = upk(pi.y2), zs = upk(pi.z2);
-      rdf_slow<PERIODIC>(xs.x, ys.x, zs.x, *pjf, p, hist);
-    }
-    if (st.r2s.y < p.cut_fast && pi.v_hi) {
-      const float2 xs = upk(pi.x2), ys = upk(pi.y2), zs = upk(pi.z2);
-      rdf_slow<PERIODIC>(xs.y, ys.y, zs.y, *pjf, p, hist);
-    }
+    rdf_push<PERIODIC>(R, r2s.x < p.cut_fast && pi.v_lo && !(DIAG && self_lo),
+                       r2s.y < p.cut_fast && pi.v_hi && !(DIAG && self_hi), pi.i_lo, pi.i_hi, jglobal, p);
   }
 }
 
@@ -307,163 +291,41 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return t;  // valid in thread 0
 }
 
-// grid: (i-tiles, j-splits).  block: THREADS.  dyn smem: force_smem_bytes().
-// A thread owns 2*NPAIR i-particles: particle m is ibase + m*THREADS + tid; packed pair q = (2q, 2q+1).
-// UNROLL: j-loop unroll of the plain loop.  PIPE: 0 = plain loop; > 0 = software-pipelined main loop with
-// batches of PIPE j-records (stage A of the next batch beside stage B of the current one).
-template <typename V, bool PERIODIC, bool RDF, int THREADS, int MINB, int NPAIR, int UNROLL, int PIPE = 0>
-__global__ void __launch_bounds__(THREADS, MINB) k_force(const ForceParams p) {
-  constexpr int IPT = 2 * NPAIR;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int tid = threadIdx.x;
-  const int TJ = p.tile_j;
-  uint4* tile_u = reinterpret_cast<uint4*>(smem_raw);                          // [2][TJ]
-  float4* tile_f = reinterpret_cast<float4*>(smem_raw + (size_t)2 * TJ * 16);  // [2][TJ] (RDF && PERIODIC)
-  unsigned char* tail = smem_raw + (size_t)((RDF && PERIODIC) ? 4 : 2) * TJ * 16;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);          // [2]
-  double* red = reinterpret_cast<double*>(tail + 16);          // [THREADS/32]
-  unsigned int* hist = reinterpret_cast<unsigned int*>(tail + 16 + 8 * (THREADS / 32));  // [THREADS/32][256] (RDF)
-
-  const int ibase = p.i_begin + blockIdx.x * (THREADS * IPT);
-  // j-split: near-equal contiguous chunks
-  const int ns = gridDim.y;
-  const int jb = (int)(((long long)p.N * blockIdx.y) / ns);
-  const int je = (int)(((long long)p.N * (blockIdx.y + 1)) / ns);
-  const int ntiles = (je - jb + TJ - 1) / TJ;
-
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    mbar_fence_init();
-  }
-  if (RDF) {
-    for (int k = tid; k < (THREADS / 32) * kRdfBins; k += THREADS) hist[k] = 0u;
-  }
-  __syncthreads();
-
-  auto issue = [&](int t) {
-    const int j0 = jb + t * TJ;
-    const int nj = min(TJ, je - j0);
-    const int st = t & 1;
-    const uint32_t bytes = (uint32_t)nj * 16u;
-    mbar_expect_tx(&bars[st], (RDF && PERIODIC) ? 2u * bytes : bytes);
-    bulk_g2s(tile_u + (size_t)st * TJ, p.jrec + j0, bytes, &bars[st]);
-    if (RDF && PERIODIC) bulk_g2s(tile_f + (size_t)st * TJ, p.posf + j0, bytes, &bars[st]);
-  };
-  if (tid == 0 && ntiles > 0) issue(0);
-
-  PairI<V> pi[NPAIR];
-  PairAcc<V> acc[NPAIR];
-  // run-level sums: every accumulator is folded per tile (two-level float summation), which keeps the
-  // rounding error of an N-term float sum at ~sqrt(tile)+sqrt(N/tile) ulps instead of sqrt(N)
-  V s6run[NPAIR], wrun[NPAIR], fxrun[NPAIR], fyrun[NPAIR], fzrun[NPAIR];
-  const V zero2 = bc2<V>(0.f);
+// Load the thread's 2*NPAIR i-particles: particle m is ibase + m*THREADS + tid, pair q = (2q, 2q+1).
+template <typename V, bool PERIODIC, int THREADS, int NPAIR>
+__device__ __forceinline__ bool load_i_particles(const ForceParams& p, int ibase, PairI<V> (&pi)[NPAIR]) {
+  bool all_valid = true;
 #pragma unroll
   for (int q = 0; q < NPAIR; ++q) {
-    int i0 = ibase + (2 * q) * THREADS + tid, i1 = i0 + THREADS;
+    int i0 = ibase + (2 * q) * THREADS + (int)threadIdx.x, i1 = i0 + THREADS;
     pi[q].v_lo = i0 < p.i_end;
     pi[q].v_hi = i1 < p.i_end;
+    all_valid = all_valid && pi[q].v_lo && pi[q].v_hi;
     if (!pi[q].v_lo) i0 = p.i_end - 1;
     if (!pi[q].v_hi) i1 = p.i_end - 1;
+    pi[q].i_lo = (unsigned)i0;
+    pi[q].i_hi = (unsigned)i1;
     const uint4 r0 = p.jrec[i0], r1 = p.jrec[i1];
     pi[q].ax = (int)r0.x; pi[q].ay = (int)r0.y; pi[q].az = (int)r0.z;
     pi[q].bx = (int)r1.x; pi[q].by = (int)r1.y; pi[q].bz = (int)r1.z;
-    if (!PERIODIC || RDF) {
+    if (!PERIODIC) {
       const float4 f0 = p.posf[i0], f1 = p.posf[i1];
       pi[q].x2 = mk2<V>(f0.x, f1.x); pi[q].y2 = mk2<V>(f0.y, f1.y); pi[q].z2 = mk2<V>(f0.z, f1.z);
     } else {
-      pi[q].x2 = pi[q].y2 = pi[q].z2 = zero2;
+      pi[q].x2 = pi[q].y2 = pi[q].z2 = bc2<V>(0.f);
     }
-    acc[q].fx = acc[q].fy = acc[q].fz = acc[q].s6 = acc[q].w = zero2;
-    s6run[q] = wrun[q] = fxrun[q] = fyrun[q] = fzrun[q] = zero2;
   }
-  unsigned int* myhist = hist + (tid >> 5) * kRdfBins;
+  return all_valid;
+}
 
-  for (int t = 0; t < ntiles; ++t) {
-    if (tid == 0 && t + 1 < ntiles) issue(t + 1);
-    const int st = t & 1;
-    mbar_wait(&bars[st], (uint32_t)((t >> 1) & 1));
-    const int j0 = jb + t * TJ;
-    const int nj = min(TJ, je - j0);
-    const uint4* tu = tile_u + (size_t)st * TJ;
-    const float4* tf = (RDF && PERIODIC) ? (tile_f + (size_t)st * TJ) : reinterpret_cast<const float4*>(tu);
-    // does this tile contain any of this CTA's own particles?
-    const bool diag = (j0 < ibase + THREADS * IPT) && (j0 + nj > ibase);
-    if (!diag && PIPE > 0) {
-      constexpr int UJ = PIPE > 0 ? PIPE : 1;
-      const int nb = nj / UJ;
-      Stage<V> sa[UJ][NPAIR], sb[UJ][NPAIR];
-      auto run_a = [&](int b, Stage<V>(&st)[UJ][NPAIR]) {
-#pragma unroll
-        for (int u = 0; u < UJ; ++u) {
-          const uint4 uj = tu[b * UJ + u];
-#pragma unroll
-          for (int q = 0; q < NPAIR; ++q) stage_a<V, PERIODIC>(uj, pi[q], st[u][q]);
-        }
-      };
-      auto run_b = [&](int b, Stage<V>(&st)[UJ][NPAIR]) {
-#pragma unroll
-        for (int u = 0; u < UJ; ++u)
-#pragma unroll
-          for (int q = 0; q < NPAIR; ++q)
-            stage_b<V, PERIODIC, RDF>(st[u][q], pi[q], acc[q], p, tf + b * UJ + u, myhist);
-      };
-      if (nb > 0) {
-        run_a(0, sa);
-        int b = 1;
-        for (; b + 1 < nb; b += 2) {  // ping-pong: no register copies between iterations
-          run_a(b, sb);
-          run_b(b - 1, sa);
-          run_a(b + 1, sa);
-          run_b(b, sb);
-        }
-        if (b < nb) {
-          run_a(b, sb);
-          run_b(b - 1, sa);
-          run_b(b, sb);
-        } else {
-          run_b(b - 1, sa);
-        }
-      }
-      for (int j = nb * UJ; j < nj; ++j) {  // remainder of a ragged tile
-        const uint4 uj = tu[j];
-#pragma unroll
-        for (int q = 0; q < NPAIR; ++q)
-          pair_body<V, PERIODIC, false, RDF>(uj, pi[q], acc[q], false, false, p, tf + j, myhist);
-      }
-    } else if (!diag) {
-#pragma unroll UNROLL
-      for (int j = 0; j < nj; ++j) {
-        const uint4 uj = tu[j];
-#pragma unroll
-        for (int q = 0; q < NPAIR; ++q)
-          pair_body<V, PERIODIC, false, RDF>(uj, pi[q], acc[q], false, false, p, tf + j, myhist);
-      }
-    } else {
-      const int jrel0 = j0 - ibase - tid;  // j-index relative to my particle m = 0
-#pragma unroll 2
-      for (int j = 0; j < nj; ++j) {
-        const uint4 uj = tu[j];
-        const int jr = jrel0 + j;
-#pragma unroll
-        for (int q = 0; q < NPAIR; ++q)
-          pair_body<V, PERIODIC, true, RDF>(uj, pi[q], acc[q], jr == (2 * q) * THREADS, jr == (2 * q + 1) * THREADS,
-                                            p, tf + j, myhist);
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < NPAIR; ++q) {
-      s6run[q] = add2(s6run[q], acc[q].s6);
-      wrun[q] = add2(wrun[q], acc[q].w);
-      fxrun[q] = add2(fxrun[q], acc[q].fx);
-      fyrun[q] = add2(fyrun[q], acc[q].fy);
-      fzrun[q] = add2(fzrun[q], acc[q].fz);
-      acc[q].s6 = acc[q].w = acc[q].fx = acc[q].fy = acc[q].fz = zero2;
-    }
-    __syncthreads();  // everyone is done with stage st before it is refilled
-  }
-
-  // ---- epilogue: scale, store partial forces + per-particle potential, reduce the virial sum ----
+// Shared tail of both force kernels: scale and store the direct partial forces + per-particle potential,
+// reduce the virial sum to one double per CTA, merge the per-warp RDF histograms.
+template <typename V, bool PERIODIC, bool RDF, int THREADS, int NPAIR>
+__device__ __forceinline__ void force_epilogue(const ForceParams& p, int ibase, const PairI<V> (&pi)[NPAIR],
+                                               const V (&fxrun)[NPAIR], const V (&fyrun)[NPAIR],
+                                               const V (&fzrun)[NPAIR], const V (&s6run)[NPAIR],
+                                               const V (&wrun)[NPAIR], double* red, unsigned int* hist, RdfCtx& R) {
+  const int tid = threadIdx.x;
   const float fs = p.fscale;
   double wsum = 0.;
   float4* out = p.fpart + (size_t)blockIdx.y * p.ilocal_cap;
@@ -485,6 +347,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force(const ForceParams p) {
   const double wtot = block_sum<THREADS>(wsum, red);
   if (tid == 0) p.blockW[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = wtot;
   if (RDF) {
+    rdf_drain<PERIODIC>(R, p, true);
     __syncthreads();
     for (int b = tid; b < kRdfBins; b += THREADS) {
       unsigned int c = 0;
@@ -495,10 +358,117 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force(const ForceParams p) {
   }
 }
 
-inline size_t force_smem_bytes(bool periodic, bool rdf, int tile_j, int threads) {
-  size_t b = (size_t)((rdf && periodic) ? 4 : 2) * tile_j * 16 + 16 + 8 * (threads / 32);
-  if (rdf) b += (size_t)(threads / 32) * kRdfBins * 4;
-  return b;
+// RDF scratch per CTA: per-warp histograms + per-warp queues
+inline size_t rdf_smem_bytes(int threads) {
+  return (size_t)(threads / 32) * (kRdfBins * 4 + kRdfQueueCap * 8);
+}
+
+// grid: (i-tiles, j-splits).  block: THREADS.  dyn smem: force_smem_bytes().
+// UNROLL: j-loop unroll.  (A software-pipelined main loop — stage A of batch b+1 beside stage B of batch b —
+// was measured 2-10 % slower and removed: profiles/r01_tune_force_65536_pipelined.log.)
+template <typename V, bool PERIODIC, bool RDF, int THREADS, int MINB, int NPAIR, int UNROLL>
+__global__ void __launch_bounds__(THREADS, MINB) k_force(const ForceParams p) {
+  constexpr int IPT = 2 * NPAIR;
+  constexpr int NW = THREADS / 32;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  const int TJ = p.tile_j;
+  uint4* tile_u = reinterpret_cast<uint4*>(smem_raw);  // [2][TJ]
+  unsigned char* tail = smem_raw + (size_t)2 * TJ * 16;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);  // [2]
+  double* red = reinterpret_cast<double*>(tail + 16);  // [NW]
+  unsigned int* hist = reinterpret_cast<unsigned int*>(tail + 16 + 8 * NW);         // [NW][256]   (RDF)
+  uint2* queues = reinterpret_cast<uint2*>(tail + 16 + 8 * NW + NW * kRdfBins * 4);  // [NW][cap]   (RDF)
+
+  const int ibase = p.i_begin + blockIdx.x * (THREADS * IPT);
+  // j-split: near-equal contiguous chunks
+  const int ns = gridDim.y;
+  const int jb = (int)(((long long)p.N * blockIdx.y) / ns);
+  const int je = (int)(((long long)p.N * (blockIdx.y + 1)) / ns);
+  const int ntiles = (je - jb + TJ - 1) / TJ;
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  if (RDF) {
+    for (int k = tid; k < NW * kRdfBins; k += THREADS) hist[k] = 0u;
+  }
+  __syncthreads();
+
+  auto issue = [&](int t) {
+    const int j0 = jb + t * TJ;
+    const int nj = min(TJ, je - j0);
+    const int st = t & 1;
+    const uint32_t bytes = (uint32_t)nj * 16u;
+    mbar_expect_tx(&bars[st], bytes);
+    bulk_g2s(tile_u + (size_t)st * TJ, p.jrec + j0, bytes, &bars[st]);
+  };
+  if (tid == 0 && ntiles > 0) issue(0);
+
+  PairI<V> pi[NPAIR];
+  PairAcc<V> acc[NPAIR];
+  // run-level sums: every accumulator is folded per tile (two-level float summation), which keeps the
+  // rounding error of an N-term float sum at ~sqrt(tile)+sqrt(N/tile) ulps instead of sqrt(N)
+  V s6run[NPAIR], wrun[NPAIR], fxrun[NPAIR], fyrun[NPAIR], fzrun[NPAIR];
+  const V zero2 = bc2<V>(0.f);
+  load_i_particles<V, PERIODIC, THREADS, NPAIR>(p, ibase, pi);
+#pragma unroll
+  for (int q = 0; q < NPAIR; ++q) {
+    acc[q].fx = acc[q].fy = acc[q].fz = acc[q].s6 = acc[q].w = zero2;
+    s6run[q] = wrun[q] = fxrun[q] = fyrun[q] = fzrun[q] = zero2;
+  }
+  RdfCtx R;
+  R.q = queues + (tid >> 5) * kRdfQueueCap;
+  R.hist = hist + (tid >> 5) * kRdfBins;
+  R.n = 0;
+
+  for (int t = 0; t < ntiles; ++t) {
+    if (tid == 0 && t + 1 < ntiles) issue(t + 1);
+    const int st = t & 1;
+    mbar_wait(&bars[st], (uint32_t)((t >> 1) & 1));
+    const int j0 = jb + t * TJ;
+    const int nj = min(TJ, je - j0);
+    const uint4* tu = tile_u + (size_t)st * TJ;
+    // does this tile contain any of this CTA's own particles?
+    const bool diag = (j0 < ibase + THREADS * IPT) && (j0 + nj > ibase);
+    if (!diag) {
+#pragma unroll UNROLL
+      for (int j = 0; j < nj; ++j) {
+        const uint4 uj = tu[j];
+#pragma unroll
+        for (int q = 0; q < NPAIR; ++q)
+          pair_body<V, PERIODIC, false, RDF>(uj, pi[q], acc[q], false, false, p, (unsigned)(j0 + j), R);
+      }
+    } else {
+      const int jrel0 = j0 - ibase - tid;  // j-index relative to my particle m = 0
+#pragma unroll 2
+      for (int j = 0; j < nj; ++j) {
+        const uint4 uj = tu[j];
+        const int jr = jrel0 + j;
+#pragma unroll
+        for (int q = 0; q < NPAIR; ++q)
+          pair_body<V, PERIODIC, true, RDF>(uj, pi[q], acc[q], jr == (2 * q) * THREADS, jr == (2 * q + 1) * THREADS,
+                                            p, (unsigned)(j0 + j), R);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NPAIR; ++q) {
+      s6run[q] = add2(s6run[q], acc[q].s6);
+      wrun[q] = add2(wrun[q], acc[q].w);
+      fxrun[q] = add2(fxrun[q], acc[q].fx);
+      fyrun[q] = add2(fyrun[q], acc[q].fy);
+      fzrun[q] = add2(fzrun[q], acc[q].fz);
+      acc[q].s6 = acc[q].w = acc[q].fx = acc[q].fy = acc[q].fz = zero2;
+    }
+    __syncthreads();  // everyone is done with stage st before it is refilled
+  }
+  force_epilogue<V, PERIODIC, RDF, THREADS, NPAIR>(p, ibase, pi, fxrun, fyrun, fzrun, s6run, wrun, red, hist, R);
+}
+
+inline size_t force_smem_bytes(bool rdf, int tile_j, int threads) {
+  return (size_t)2 * tile_j * 16 + 16 + 8 * (threads / 32) + (rdf ? rdf_smem_bytes(threads) : 0);
 }
 
 }  // namespace ljmd

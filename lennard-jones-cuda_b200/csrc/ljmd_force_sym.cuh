@@ -45,7 +45,7 @@ inline int sym_max_partner_count(int n) { return (n & 1) ? (n - 1) / 2 : n / 2; 
 template <typename V, bool PERIODIC, bool KILL, bool RDF>
 __device__ __forceinline__ void pair_sym(const uint4& uj, const PairI<V>& pi, PairAcc<V>& acc, bool kill_lo,
                                          bool kill_hi, float& rjx, float& rjy, float& rjz, const ForceParams& p,
-                                         const float4* pjf, unsigned int* hist) {
+                                         unsigned jglobal, RdfCtx& R) {
   V dx, dy, dz;
   if (PERIODIC) {
     dx = mk2<V>(__int2float_rn(pi.ax - (int)uj.x), __int2float_rn(pi.bx - (int)uj.x));
@@ -82,15 +82,9 @@ __device__ __forceinline__ void pair_sym(const uint4& uj, const PairI<V>& pi, Pa
   rjz = __fmaf_rn(-ddz.x, sx.x, rjz); rjz = __fmaf_rn(-ddz.y, sx.y, rjz);
   if (RDF) {
     // the reference counts (i,j) and (j,i); its float sequence is odd in the separation, so both land in the
-    // same bin: one exact evaluation, increment 2
-    if (r2s.x < p.cut_fast && !(KILL && kill_lo)) {
-      const float2 xs = upk(pi.x2), ys = upk(pi.y2), zs = upk(pi.z2);
-      rdf_slow<PERIODIC>(xs.x, ys.x, zs.x, *pjf, p, hist, 2u);
-    }
-    if (r2s.y < p.cut_fast && !(KILL && kill_hi)) {
-      const float2 xs = upk(pi.x2), ys = upk(pi.y2), zs = upk(pi.z2);
-      rdf_slow<PERIODIC>(xs.y, ys.y, zs.y, *pjf, p, hist, 2u);
-    }
+    // same bin: one queue entry with the "counts twice" bit (31) set
+    rdf_push<PERIODIC>(R, r2s.x < p.cut_fast && !(KILL && kill_lo), r2s.y < p.cut_fast && !(KILL && kill_hi),
+                       pi.i_lo | 0x80000000u, pi.i_hi | 0x80000000u, jglobal, p);
   }
 }
 
@@ -104,15 +98,15 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int BJ = sp.bj;
-  uint4* tile_u = reinterpret_cast<uint4*>(smem_raw);                          // [2][BJ]
-  float4* tile_f = reinterpret_cast<float4*>(smem_raw + (size_t)2 * BJ * 16);  // [2][BJ] (RDF && PERIODIC)
-  unsigned char* after_tiles = smem_raw + (size_t)((RDF && PERIODIC) ? 4 : 2) * BJ * 16;
+  uint4* tile_u = reinterpret_cast<uint4*>(smem_raw);  // [2][BJ]
+  unsigned char* after_tiles = smem_raw + (size_t)2 * BJ * 16;
   float4* slices = reinterpret_cast<float4*>(after_tiles);                     // [NW][BJ]
   uint4* stage = reinterpret_cast<uint4*>(after_tiles + (size_t)NW * BJ * 16);  // [NW][64]
   unsigned char* tail = after_tiles + (size_t)NW * BJ * 16 + (size_t)NW * 64 * 16;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);          // [2]
   double* red = reinterpret_cast<double*>(tail + 16);          // [NW]
-  unsigned int* hist = reinterpret_cast<unsigned int*>(tail + 16 + 8 * NW);  // [NW][256] (RDF)
+  unsigned int* hist = reinterpret_cast<unsigned int*>(tail + 16 + 8 * NW);         // [NW][256] (RDF)
+  uint2* queues = reinterpret_cast<uint2*>(tail + 16 + 8 * NW + NW * kRdfBins * 4);  // [NW][cap] (RDF)
 
   const int ibase = p.i_begin + blockIdx.x * B;
   const int gI = ibase / B;  // global block index (i_begin is a multiple of B)
@@ -157,9 +151,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
     int o;
     const int j0 = unit_j0(u, o);
     const uint32_t bytes = (uint32_t)unit_nj(j0) * 16u;
-    mbar_expect_tx(&bars[st], (RDF && PERIODIC) ? 2u * bytes : bytes);
+    mbar_expect_tx(&bars[st], bytes);
     bulk_g2s(tile_u + (size_t)st * BJ, p.jrec + j0, bytes, &bars[st]);
-    if (RDF && PERIODIC) bulk_g2s(tile_f + (size_t)st * BJ, p.posf + j0, bytes, &bars[st]);
   };
 
   int cur = next_nonempty(ub);
@@ -173,30 +166,18 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
   PairAcc<V> acc[NPAIR];
   V s6run[NPAIR], wrun[NPAIR], fxrun[NPAIR], fyrun[NPAIR], fzrun[NPAIR];
   const V zero2 = bc2<V>(0.f);
-  bool all_valid = true;
+  const bool all_valid = load_i_particles<V, PERIODIC, THREADS, NPAIR>(p, ibase, pi);
 #pragma unroll
   for (int q = 0; q < NPAIR; ++q) {
-    int i0 = ibase + (2 * q) * THREADS + tid, i1 = i0 + THREADS;
-    pi[q].v_lo = i0 < p.i_end;
-    pi[q].v_hi = i1 < p.i_end;
-    all_valid = all_valid && pi[q].v_lo && pi[q].v_hi;
-    if (!pi[q].v_lo) i0 = p.i_end - 1;
-    if (!pi[q].v_hi) i1 = p.i_end - 1;
-    const uint4 r0 = p.jrec[i0], r1 = p.jrec[i1];
-    pi[q].ax = (int)r0.x; pi[q].ay = (int)r0.y; pi[q].az = (int)r0.z;
-    pi[q].bx = (int)r1.x; pi[q].by = (int)r1.y; pi[q].bz = (int)r1.z;
-    if (!PERIODIC || RDF) {
-      const float4 f0 = p.posf[i0], f1 = p.posf[i1];
-      pi[q].x2 = mk2<V>(f0.x, f1.x); pi[q].y2 = mk2<V>(f0.y, f1.y); pi[q].z2 = mk2<V>(f0.z, f1.z);
-    } else {
-      pi[q].x2 = pi[q].y2 = pi[q].z2 = zero2;
-    }
     acc[q].fx = acc[q].fy = acc[q].fz = acc[q].s6 = acc[q].w = zero2;
     s6run[q] = wrun[q] = fxrun[q] = fyrun[q] = fzrun[q] = zero2;
   }
   // is every lane of this warp holding real particles? (warp-uniform choice of the unmasked fast path)
   const bool warp_all_valid = __all_sync(0xffffffffu, all_valid);
-  unsigned int* myhist = hist + warp * kRdfBins;
+  RdfCtx R;
+  R.q = queues + warp * kRdfQueueCap;
+  R.hist = hist + warp * kRdfBins;
+  R.n = 0;
   float4* myslice = slices + (size_t)warp * BJ;
   uint4* mystage = stage + warp * 64;
 
@@ -213,7 +194,6 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
     const int j0 = unit_j0(cur, o);
     const int nj = unit_nj(j0);
     const uint4* tu = tile_u + (size_t)st * BJ;
-    const float4* tf = (RDF && PERIODIC) ? (tile_f + (size_t)st * BJ) : reinterpret_cast<const float4*>(tu);
     float wgt;
     if (o == 0) {
       // ---- diagonal block: ordered loop over its own particles, self pair excluded ----
@@ -226,7 +206,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
 #pragma unroll
         for (int q = 0; q < NPAIR; ++q)
           pair_body<V, PERIODIC, true, RDF>(uj, pi[q], acc[q], jr == (2 * q) * THREADS, jr == (2 * q + 1) * THREADS,
-                                            p, tf + j, myhist);
+                                            p, (unsigned)(j0 + j), R);
       }
     } else {
       // ---- partner block: each unordered pair once, reaction accumulators travel with the rotating j ----
@@ -248,10 +228,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
 #pragma unroll UNROLLK
           for (int k = 0; k < 32; ++k) {
             const uint4 uj = sp_l[k];
-            const float4* pjf = tf + (c << 5) + ((lane + k) & 31);
+            const unsigned jg = (unsigned)(j0 + (c << 5) + ((lane + k) & 31));   // only live in RDF variants
 #pragma unroll
             for (int q = 0; q < NPAIR; ++q)
-              pair_sym<V, PERIODIC, false, RDF>(uj, pi[q], acc[q], false, false, rjx, rjy, rjz, p, pjf, myhist);
+              pair_sym<V, PERIODIC, false, RDF>(uj, pi[q], acc[q], false, false, rjx, rjy, rjz, p, jg, R);
             rjx = __shfl_sync(0xffffffffu, rjx, nxt_lane);
             rjy = __shfl_sync(0xffffffffu, rjy, nxt_lane);
             rjz = __shfl_sync(0xffffffffu, rjz, nxt_lane);
@@ -261,11 +241,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
             const uint4 uj = sp_l[k];
             const int hl = (lane + k) & 31;               // home lane of the j I work on now
             const bool jdead = ((c << 5) + hl) >= nj;
-            const float4* pjf = tf + min((c << 5) + hl, nj - 1);
+            const unsigned jg = (unsigned)(j0 + min((c << 5) + hl, nj - 1));
 #pragma unroll
             for (int q = 0; q < NPAIR; ++q)
               pair_sym<V, PERIODIC, true, RDF>(uj, pi[q], acc[q], jdead || !pi[q].v_lo, jdead || !pi[q].v_hi, rjx,
-                                               rjy, rjz, p, pjf, myhist);
+                                               rjy, rjz, p, jg, R);
             rjx = __shfl_sync(0xffffffffu, rjx, nxt_lane);
             rjy = __shfl_sync(0xffffffffu, rjy, nxt_lane);
             rjz = __shfl_sync(0xffffffffu, rjz, nxt_lane);
@@ -305,42 +285,12 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
     cur = nxt;
   }
 
-  // ---- epilogue: direct forces of my i-particles, per-particle potential, virial partial ----
-  const float fs = p.fscale;
-  double wsum = 0.;
-  float4* out = p.fpart + (size_t)blockIdx.y * p.ilocal_cap;
-#pragma unroll
-  for (int q = 0; q < NPAIR; ++q) {
-    const float2 fx = upk(fxrun[q]), fy = upk(fyrun[q]), fz = upk(fzrun[q]);
-    const float2 s6 = upk(s6run[q]), w = upk(wrun[q]);
-    const int il = (ibase - p.i_begin) + (2 * q) * THREADS + tid;
-    if (pi[q].v_lo) {
-      out[il] = make_float4(fx.x * fs, fy.x * fs, fz.x * fs, w.x * (1.f / 12.f) - 0.5f * s6.x);
-      wsum += (double)w.x;
-    }
-    if (pi[q].v_hi) {
-      out[il + THREADS] = make_float4(fx.y * fs, fy.y * fs, fz.y * fs, w.y * (1.f / 12.f) - 0.5f * s6.y);
-      wsum += (double)w.y;
-    }
-  }
-  const double wtot = block_sum<THREADS>(wsum, red);
-  if (tid == 0) p.blockW[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = wtot;
-  if (RDF) {
-    __syncthreads();
-    for (int b = tid; b < kRdfBins; b += THREADS) {
-      unsigned int c = 0;
-#pragma unroll
-      for (int w = 0; w < NW; ++w) c += hist[w * kRdfBins + b];
-      if (c) atomicAdd(&p.rdf[b], (unsigned long long)c);
-    }
-  }
+  force_epilogue<V, PERIODIC, RDF, THREADS, NPAIR>(p, ibase, pi, fxrun, fyrun, fzrun, s6run, wrun, red, hist, R);
 }
 
-inline size_t force_sym_smem_bytes(bool periodic, bool rdf, int bj, int threads) {
-  size_t b = (size_t)((rdf && periodic) ? 4 : 2) * bj * 16 + (size_t)(threads / 32) * (bj + 64) * 16 + 16 +
-             8 * (threads / 32);
-  if (rdf) b += (size_t)(threads / 32) * kRdfBins * 4;
-  return b;
+inline size_t force_sym_smem_bytes(bool rdf, int bj, int threads) {
+  return (size_t)2 * bj * 16 + (size_t)(threads / 32) * (bj + 64) * 16 + 16 + 8 * (threads / 32) +
+         (rdf ? rdf_smem_bytes(threads) : 0);
 }
 
 }  // namespace ljmd

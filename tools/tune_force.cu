@@ -127,10 +127,10 @@ static int pick_split(int n_it, int N, int sms, int minb) {
   return best;
 }
 
-template <typename V, bool PERIODIC, bool RDF, int THREADS, int MINB, int NPAIR, int UNROLL, int PIPE = 0>
+template <typename V, bool PERIODIC, bool RDF, int THREADS, int MINB, int NPAIR, int UNROLL>
 static void run_variant(const Problem& pb, const char* tag, int reps, int tile_j, std::vector<float4>* keep) {
-  auto kern = k_force<V, PERIODIC, RDF, THREADS, MINB, NPAIR, UNROLL, PIPE>;
-  const size_t smem = force_smem_bytes(PERIODIC, RDF, tile_j, THREADS);
+  auto kern = k_force<V, PERIODIC, RDF, THREADS, MINB, NPAIR, UNROLL>;
+  const size_t smem = force_smem_bytes(RDF, tile_j, THREADS);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaFuncAttributes fa;
   CK(cudaFuncGetAttributes(&fa, kern));
@@ -194,7 +194,7 @@ static void run_variant(const Problem& pb, const char* tag, int reps, int tile_j
 template <typename V, bool PERIODIC, bool RDF, int THREADS, int MINB, int NPAIR, int UNROLLK = 4>
 static void run_sym(const Problem& pb, const char* tag, int reps, int bj, std::vector<float4>* keep) {
   auto kern = k_force_sym<V, PERIODIC, RDF, THREADS, MINB, NPAIR, UNROLLK>;
-  const size_t smem = force_sym_smem_bytes(PERIODIC, RDF, bj, THREADS);
+  const size_t smem = force_sym_smem_bytes(RDF, bj, THREADS);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaFuncAttributes fa;
   CK(cudaFuncGetAttributes(&fa, kern));
@@ -324,24 +324,16 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(pb.posf, hp.data(), (size_t)N * 16, cudaMemcpyHostToDevice));
 
   std::vector<float4> keepP, keepO;
-  //                 V   PER    RDF   THR MINB NPAIR UNROLL PIPE
-  run_variant<P2, true, false, 128, 4, 2, 4>(pb, "periodic ordered P2 t128 b4 np2 u4 (baseline)", reps, 1024, &keepP);
-  run_sym<P2, true, false, 128, 4, 2, 4>(pb, "periodic sym t128 b4 np2 uk4 bj256", reps, 256, &keepP);
+  //                 V   PER    RDF   THR MINB NPAIR UNROLL
+  run_variant<P2, true, false, 128, 4, 2, 4>(pb, "periodic ordered P2 t128 b4 np2 u4", reps, 1024, &keepP);
+  run_variant<S2, true, false, 128, 4, 2, 4>(pb, "periodic ordered S2(scalar) t128 b4 np2 u4", reps, 1024, &keepP);
   run_sym<P2, true, false, 128, 3, 2, 4>(pb, "periodic sym t128 b3 np2 uk4 bj256", reps, 256, &keepP);
-  run_sym<P2, true, false, 128, 3, 2, 2>(pb, "periodic sym t128 b3 np2 uk2 bj256", reps, 256, &keepP);
-  run_sym<P2, true, false, 128, 3, 2, 8>(pb, "periodic sym t128 b3 np2 uk8 bj256", reps, 256, &keepP);
-  run_sym<P2, true, false, 128, 4, 2, 2>(pb, "periodic sym t128 b4 np2 uk2 bj256", reps, 256, &keepP);
-  run_sym<P2, true, false, 128, 4, 2, 8>(pb, "periodic sym t128 b4 np2 uk8 bj256", reps, 256, &keepP);
-  run_sym<P2, true, false, 128, 2, 3, 2>(pb, "periodic sym t128 b2 np3 uk2 bj384", reps, 384, &keepP);
-  run_sym<P2, true, false, 128, 3, 3, 2>(pb, "periodic sym t128 b3 np3 uk2 bj384", reps, 384, &keepP);
-  run_sym<P2, true, false, 128, 2, 4, 2>(pb, "periodic sym t128 b2 np4 uk2 bj256", reps, 256, &keepP);
-  run_sym<P2, true, false, 64, 6, 2, 4>(pb, "periodic sym t64 b6 np2 uk4 bj256", reps, 256, &keepP);
-  run_sym<P2, true, false, 64, 8, 2, 4>(pb, "periodic sym t64 b8 np2 uk4 bj256", reps, 256, &keepP);
-  run_sym<P2, true, false, 256, 1, 2, 4>(pb, "periodic sym t256 b1 np2 uk4 bj256", reps, 256, &keepP);
-  run_sym<P2, true, false, 128, 6, 1, 4>(pb, "periodic sym t128 b6 np1 uk4 bj256", reps, 256, &keepP);
-  run_variant<P2, false, false, 128, 4, 2, 4>(pb, "open ordered P2 t128 b4 np2 u4 (baseline)", reps, 1024, &keepO);
-  run_sym<P2, false, false, 128, 4, 2, 4>(pb, "open sym t128 b4 np2 uk4 bj256", reps, 256, &keepO);
+  run_sym<P2, true, false, 128, 4, 2, 4>(pb, "periodic sym t128 b4 np2 uk4 bj256", reps, 256, &keepP);
+  run_variant<P2, true, true, 128, 3, 2, 4>(pb, "periodic+RDF ordered t128 b3 np2 u4", reps, 1024, &keepP);
+  run_sym<P2, true, true, 128, 3, 2, 4>(pb, "periodic+RDF sym t128 b3 np2 uk4 bj256", reps, 256, &keepP);
+  run_variant<P2, false, false, 128, 4, 2, 4>(pb, "open ordered P2 t128 b4 np2 u4", reps, 1024, &keepO);
   run_sym<P2, false, false, 128, 3, 2, 4>(pb, "open sym t128 b3 np2 uk4 bj256", reps, 256, &keepO);
-  run_sym<P2, false, false, 128, 3, 3, 2>(pb, "open sym t128 b3 np3 uk2 bj384", reps, 384, &keepO);
+  run_variant<P2, false, true, 128, 3, 2, 4>(pb, "open+RDF ordered t128 b3 np2 u4", reps, 1024, &keepO);
+  run_sym<P2, false, true, 128, 3, 2, 4>(pb, "open+RDF sym t128 b3 np2 uk4 bj256", reps, 256, &keepO);
   return 0;
 }
