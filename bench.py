@@ -133,7 +133,8 @@ def describe(name, cfg, world):
             "rdf_every": cfg["rdf_every"], "dt": DT,
             "parallelism": f"i-shards x{world}" if world > 1 else "single GPU",
             "init": "reference start lattice (MDSystem.cpp:147-168) + 5% jitter, seeded Gaussian velocities",
-            "l2": "192 MiB scratch overwritten before every step (L2 flush); inputs themselves fit in L2 by design"}
+            "l2": "192 MiB scratch overwritten before every timed step (L2 flush, outside the per-step event pairs); "
+                  "inputs themselves fit in L2 by design"}
 
 
 # ------------------------------------------------------------------------------------- reference arm

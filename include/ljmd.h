@@ -169,8 +169,9 @@ int ljmd_velocity_histogram(ljmd_system* s, double step, int nbins, int* out);
 /* Kernel launches issued by this handle so far (for bench.py's gpu_launches). */
 long long ljmd_launch_count(ljmd_system* s);
 
-/* Milliseconds the last ljmd_step spent in its force kernels / in total, from
- * CUDA events on the handle's stream (0 when event timing is off). */
+/* Milliseconds the last ljmd_step spent in its force kernels / in its steps, from CUDA events on the
+ * handle's stream (0 when event timing is off).  With an L2 flush configured, total_ms is the sum of the
+ * per-step intervals, i.e. it excludes the flush writes issued between steps. */
 int ljmd_set_event_timing(ljmd_system* s, int on);
 int ljmd_last_step_timing(ljmd_system* s, double* force_ms, double* total_ms, int* force_launches);
 

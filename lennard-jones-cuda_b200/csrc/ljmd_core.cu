@@ -96,7 +96,8 @@ struct ljmd_system {
   int timing = 0;
   std::vector<cudaEvent_t> ev;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-  double last_force_ms = 0., last_total_ms = 0.;
+  double last_force_ms = 0., last_total_ms = 0., last_steps_ms = 0.;
+  std::vector<cudaEvent_t> step_ev;   // per-step (begin, end) pairs: step time without the L2-flush write
   int last_force_launches = 0;
 #ifdef LJMD_WITH_NCCL
   ncclComm_t comm = nullptr;
@@ -195,12 +196,8 @@ static cudaError_t launch_force_t(ljmd_system* s, const ForceParams& fp) {
   constexpr int MINB = RDF ? kMinBlocksRdf : kMinBlocks;
   auto kern = k_force<P2, PERIODIC, RDF, kForceThreads, MINB, kNPair, kUnroll>;
   const size_t smem = force_smem_bytes(RDF, kTileJ, kForceThreads);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
+  static_assert(2 * kTileJ * 16 + 16 + 64 + (kForceThreads / 32) * (kRdfBins * 4 + kRdfQueueCap * 8) <= 48 * 1024,
+                "dynamic shared memory must stay under the 48 KB default (no per-device opt-in needed)");
   dim3 grid(s->n_itiles, s->nsplit);
   kern<<<grid, kForceThreads, smem, s->stream>>>(fp);
   return cudaGetLastError();
@@ -211,12 +208,9 @@ static cudaError_t launch_force_sym_t(ljmd_system* s, const SymParams& sp) {
   constexpr int MINB = RDF ? kMinBlocksRdf : kSymMinBlocks;
   auto kern = k_force_sym<P2, PERIODIC, RDF, kForceThreads, MINB, kNPair>;
   const size_t smem = force_sym_smem_bytes(RDF, kSymBJ, kForceThreads);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
+  static_assert(2 * kSymBJ * 16 + (kForceThreads / 32) * (kSymBJ + 64) * 16 + 16 + 64 +
+                        (kForceThreads / 32) * (kRdfBins * 4 + kRdfQueueCap * 8) <= 48 * 1024,
+                "dynamic shared memory must stay under the 48 KB default (no per-device opt-in needed)");
   dim3 grid(s->n_itiles, s->nsplit);
   kern<<<grid, kForceThreads, smem, s->stream>>>(sp);
   return cudaGetLastError();
@@ -691,8 +685,19 @@ extern "C" int ljmd_step(ljmd_system* s, double dt, int nsteps, int rdf_every) {
   for (int k = 0; k < nsteps; ++k) {
     const bool rdf = rdf_every > 0 && ((k + 1) % rdf_every == 0);
     if (s->flush_bytes) CU(cudaMemsetAsync(s->flush_buf, k & 0xff, s->flush_bytes, s->stream));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (s->timing) {
+      CU(cudaEventCreate(&e0));
+      CU(cudaEventCreate(&e1));
+      CU(cudaEventRecord(e0, s->stream));
+    }
     int rc = one_step(s, p, rdf);
     if (rc) return rc;
+    if (s->timing) {
+      CU(cudaEventRecord(e1, s->stream));
+      s->step_ev.push_back(e0);
+      s->step_ev.push_back(e1);
+    }
   }
   if (s->timing) CU(cudaEventRecord(s->ev_end, s->stream));
   int rc = sync_scalars(s);
@@ -701,6 +706,13 @@ extern "C" int ljmd_step(ljmd_system* s, double dt, int nsteps, int rdf_every) {
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, s->ev_begin, s->ev_end));
     s->last_total_ms = ms;
+    s->last_steps_ms = 0.;
+    for (size_t k = 0; k + 1 < s->step_ev.size(); k += 2) {
+      if (cudaEventElapsedTime(&ms, s->step_ev[k], s->step_ev[k + 1]) == cudaSuccess) s->last_steps_ms += ms;
+      cudaEventDestroy(s->step_ev[k]);
+      cudaEventDestroy(s->step_ev[k + 1]);
+    }
+    s->step_ev.clear();
     collect_timing(s);
   }
   return LJMD_OK;
@@ -848,7 +860,8 @@ extern "C" int ljmd_set_event_timing(ljmd_system* s, int on) {
 extern "C" int ljmd_last_step_timing(ljmd_system* s, double* force_ms, double* total_ms, int* force_launches) {
   CHECK_S(s);
   if (force_ms) *force_ms = s->last_force_ms;
-  if (total_ms) *total_ms = s->last_total_ms;
+  // the steps themselves (sum of per-step intervals); the L2-flush writes between them are not step work
+  if (total_ms) *total_ms = s->flush_bytes ? s->last_steps_ms : s->last_total_ms;
   if (force_launches) *force_launches = s->last_force_launches;
   return LJMD_OK;
 }
