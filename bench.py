@@ -124,7 +124,7 @@ def workload(pkg, name):
     return cfg, pos, vel
 
 
-def describe(name, cfg, world):
+def describe(name, cfg, world, transport="none"):
     ens = "TVN" if cfg["canonical"] else "EVN"
     bc = {0: "periodic", 1: "hard-wall", 2: "open"}[cfg["bc"]]
     return {"workload": f"{name}: N={cfg['N']} T*={cfg['T']} rho*={cfg['rho']} {bc} {ens} dt*={DT}"
@@ -132,6 +132,7 @@ def describe(name, cfg, world):
             "N": cfg["N"], "rho": cfg["rho"], "T": cfg["T"], "boundary": bc, "ensemble": ens,
             "rdf_every": cfg["rdf_every"], "dt": DT,
             "parallelism": f"i-shards x{world}" if world > 1 else "single GPU",
+            "transport": transport,
             "init": "reference start lattice (MDSystem.cpp:147-168) + 5% jitter, seeded Gaussian velocities",
             "l2": "192 MiB scratch overwritten before every timed step (L2 flush, outside the per-step event pairs); "
                   "inputs themselves fit in L2 by design"}
@@ -237,6 +238,7 @@ def main_ours(args, pkg):
     N = cfg["N"]
     sysm = ljmd.LJSystem(N, T0=cfg["T"], rho=cfg["rho"], canonical=cfg["canonical"], bc=cfg["bc"], device=local_rank,
                          rank=rank, world=world, nccl_unique_id=uid)
+    fabric = D.connect_fabric(sysm) if world > 1 else False
     sysm.set_state(pos, vel)
     sysm.set_l2_flush(192 << 20)
     sysm.set_event_timing(True)
@@ -317,7 +319,9 @@ def main_ours(args, pkg):
             "metric": "pair_interactions_per_s", "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": describe(args.config, cfg, world),
+            "config": describe(args.config, cfg, world,
+                               ("NVLink peer windows (CUDA IPC), fused into drift/gather kernels" if fabric
+                                else "NCCL") if world > 1 else "none"),
             "md_steps_per_s": args.steps / (dev_ms * 1e-3),
             "wall_ms_per_step": 1e3 * wall_s / args.steps,
             "clocks": clocks,

@@ -85,6 +85,20 @@ int ljmd_create_distributed(ljmd_system** out, int N, double rho, double T0, int
                             const void* nccl_unique_id);
 int ljmd_nccl_unique_id(void* out128);
 
+/*
+ * Intra-node fabric (optional, after ljmd_create_distributed on every rank): each rank exports the 64-byte
+ * CUDA-IPC handle of its window (positions, fixed-point records, reaction sums, reduction slots, flags),
+ * the caller ships all handles to all ranks, and ljmd_fabric_connect maps the peers' windows.  From then on
+ * the per-step exchange runs over NVLink peer memory inside the library's own kernels: k_drift stores each
+ * new position straight into every rank's window (the all-gather is fused into the integrator),
+ * k_gather pulls the peers' reaction sums for its own particles, and the scalar all-reduces are a
+ * flag-and-slot barrier kernel with a fixed summation order.  NCCL stays in use for the rare read-out
+ * collectives (ljmd_get_state, histograms) and as the transport when connect is never called or fails.
+ * handles: world x 64 bytes in rank order.  All ranks must connect (or none).
+ */
+int ljmd_fabric_export(ljmd_system* s, void* out64);
+int ljmd_fabric_connect(ljmd_system* s, const void* handles);
+
 int ljmd_destroy(ljmd_system* s);
 
 /* MDSystem.cpp:93-95. */

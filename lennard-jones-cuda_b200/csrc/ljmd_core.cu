@@ -75,6 +75,13 @@ struct ljmd_system {
   float4* rpart = nullptr;   // [n_itiles][hmax*kITile] reaction rows
   float4* rsum = nullptr;    // [npad] rank-local column sums of the reaction rows (world > 1)
   float4* rshard = nullptr;  // [cnt]  reaction totals of this rank's particles after the reduce-scatter
+  // fabric (world > 1): one window allocation holding posA | upos | rsum | slots | flags, exported through
+  // CUDA IPC; once the peers' windows are mapped the per-step collectives run over peer memory, not NCCL
+  char* win = nullptr;
+  size_t win_bytes = 0;
+  Fabric fab;                 // fab.n == 0 until ljmd_fabric_connect succeeded
+  void* peer_map[kMaxPeers] = {nullptr};   // cudaIpcOpenMemHandle results (to close on destroy)
+  unsigned long long epoch = 0;
   float thr1 = 0.f, thr2 = 0.f;
   cudaStream_t stream = nullptr;
   float4 *pos = nullptr, *posA = nullptr, *vel = nullptr, *force = nullptr, *tforce = nullptr, *fpart = nullptr;
@@ -186,6 +193,7 @@ static StepParams make_step_params(ljmd_system* s, double dt) {
   p.fpart = s->fpart; p.blockW = s->blockW; p.part = s->part; p.counter = s->counter; p.sc = s->sc;
   p.use_sym = s->use_sym; p.nblk = s->nblk; p.blk0 = s->i_begin / kITile; p.n_itiles = s->n_itiles;
   p.rp_stride = s->hmax * kITile; p.rpart = s->rpart; p.rsum = s->rsum; p.rshard = s->rshard; p.npad = s->npad;
+  p.fab = s->fab;
   return p;
 }
 
@@ -261,23 +269,33 @@ static int launch_force(ljmd_system* s, bool rdf) {
 }
 
 // ---- collectives (no-ops for world == 1) -------------------------------------------------------
+// Two transports: the fabric (peer windows over NVLink, ljmd_fabric_connect) and NCCL (always available,
+// and still used for the rare read-out collectives).
+static int fabric_sync(ljmd_system* s, int first, int count) {
+  s->epoch += 1;
+  k_fabric_sync<<<1, 32, 0, s->stream>>>(s->fab, s->epoch, first, count, s->sc);
+  CU(cudaGetLastError());
+  s->launches += 1;
+  return LJMD_OK;
+}
+// after k_drift / k_prepare: every rank's evaluation positions must be in every window
 static int allgather_positions(ljmd_system* s) {
+  if (s->world == 1) return LJMD_OK;
+  if (s->fab.n > 0) return fabric_sync(s, 0, 0);   // the kernels pushed the records themselves: barrier only
 #ifdef LJMD_WITH_NCCL
-  if (s->world > 1) {
-    const size_t bytes = (size_t)s->cnt * 16;
-    NC(ncclAllGather((const char*)s->posA + (size_t)s->rank * bytes, s->posA, bytes, ncclChar, s->comm, s->stream));
-    if (s->bc == LJMD_BC_PERIODIC)
-      NC(ncclAllGather((const char*)s->upos + (size_t)s->rank * bytes, s->upos, bytes, ncclChar, s->comm, s->stream));
-  }
+  const size_t bytes = (size_t)s->cnt * 16;
+  NC(ncclAllGather((const char*)s->posA + (size_t)s->rank * bytes, s->posA, bytes, ncclChar, s->comm, s->stream));
+  if (s->bc == LJMD_BC_PERIODIC)
+    NC(ncclAllGather((const char*)s->upos + (size_t)s->rank * bytes, s->upos, bytes, ncclChar, s->comm, s->stream));
 #endif
   return LJMD_OK;
 }
 static int allreduce_sums(ljmd_system* s, int first, int count) {
+  if (s->world == 1) return LJMD_OK;
+  if (s->fab.n > 0) return fabric_sync(s, first, count);
 #ifdef LJMD_WITH_NCCL
-  if (s->world > 1) {
-    double* ptr = s->sc->sums + first;
-    NC(ncclAllReduce(ptr, ptr, count, ncclDouble, ncclSum, s->comm, s->stream));
-  }
+  double* ptr = s->sc->sums + first;
+  NC(ncclAllReduce(ptr, ptr, count, ncclDouble, ncclSum, s->comm, s->stream));
 #endif
   return LJMD_OK;
 }
@@ -288,15 +306,20 @@ static int evaluate(ljmd_system* s, const StepParams& p, int mode, bool rdf, int
   if (rc) return rc;
   const int g = step_grid(s);
   const int fin = (s->world == 1) ? 1 : 0;
-#ifdef LJMD_WITH_NCCL
   if (s->use_sym && s->world > 1) {
-    // reaction forces land on particles of every rank: column sums of the local rows, then a reduce-scatter
+    // reaction forces land on particles of every rank: column sums of the local rows, then either a barrier
+    // (fabric: k_gather pulls the peers' sums for its own particles) or a reduce-scatter (NCCL)
     k_reduce_reaction<<<(s->npad + kStepThreads - 1) / kStepThreads, kStepThreads, 0, s->stream>>>(p);
     CU(cudaGetLastError());
     s->launches += 1;
-    NC(ncclReduceScatter(s->rsum, s->rshard, (size_t)s->cnt * 4, ncclFloat, ncclSum, s->comm, s->stream));
-  }
+    if (s->fab.n > 0) {
+      if ((rc = fabric_sync(s, 0, 0))) return rc;
+    } else {
+#ifdef LJMD_WITH_NCCL
+      NC(ncclReduceScatter(s->rsum, s->rshard, (size_t)s->cnt * 4, ncclFloat, ncclSum, s->comm, s->stream));
 #endif
+    }
+  }
   if (mode == GATHER_EVAL) k_gather<GATHER_EVAL><<<g, kStepThreads, 0, s->stream>>>(p, fin, accumulate);
   else if (mode == GATHER_EVN) k_gather<GATHER_EVN><<<g, kStepThreads, 0, s->stream>>>(p, fin, accumulate);
   else k_gather<GATHER_TVN><<<g, kStepThreads, 0, s->stream>>>(p, fin, accumulate);
@@ -342,6 +365,9 @@ static int one_step(ljmd_system* s, const StepParams& p, bool rdf) {
 static int sync_scalars(ljmd_system* s) {
   CU(cudaMemcpyAsync(s->h_sc, s->sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
+  if (s->h_sc->fabric_timeout)
+    return set_err(LJMD_ERR_NCCL, "fabric barrier timed out: a peer rank never arrived (rank %d of %d)", s->rank,
+                   s->world);
   return LJMD_OK;
 }
 
@@ -404,11 +430,18 @@ static int destroy_impl(ljmd_system* s) {
 #ifdef LJMD_WITH_NCCL
   if (s->comm) ncclCommDestroy(s->comm);
 #endif
-  cudaFree(s->pos); cudaFree(s->posA); cudaFree(s->vel); cudaFree(s->force); cudaFree(s->tforce);
-  cudaFree(s->fpart); cudaFree(s->gath); cudaFree(s->upos); cudaFree(s->blockW); cudaFree(s->part);
+  for (int r = 0; r < kMaxPeers; ++r)
+    if (s->peer_map[r]) cudaIpcCloseMemHandle(s->peer_map[r]);
+  if (s->win) {
+    cudaFree(s->win);   // posA, upos and rsum live inside the window
+  } else {
+    cudaFree(s->posA); cudaFree(s->upos);
+  }
+  cudaFree(s->pos); cudaFree(s->vel); cudaFree(s->force); cudaFree(s->tforce);
+  cudaFree(s->fpart); cudaFree(s->gath); cudaFree(s->blockW); cudaFree(s->part);
   cudaFree(s->counter); cudaFree(s->velh); cudaFree(s->sc); cudaFree(s->rdf_cur); cudaFree(s->rdf_acc);
   cudaFree(s->flush_buf);
-  cudaFree(s->rpart); cudaFree(s->rsum); cudaFree(s->rshard);
+  cudaFree(s->rpart); cudaFree(s->rshard);
   cudaFreeHost(s->h_sc); cudaFreeHost(s->h_rdf);
   for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
   if (s->ev_begin) cudaEventDestroy(s->ev_begin);
@@ -473,8 +506,23 @@ static int create_impl(ljmd_system** out, int N, double rho_or_negL, double T0, 
   CUC(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   const size_t b16 = 16;
   CUC(cudaMalloc(&s->pos, (size_t)s->cnt * b16));
-  CUC(cudaMalloc(&s->posA, (size_t)s->npad * b16));
-  CUC(cudaMalloc(&s->upos, (size_t)s->npad * b16));
+  memset(&s->fab, 0, sizeof(s->fab));
+  if (world > 1) {
+    // one allocation so that a single IPC handle exposes everything the peers touch
+    const size_t arr = (size_t)s->npad * b16;
+    s->fab.off_posA = 0; s->fab.off_upos = arr; s->fab.off_rsum = 2 * arr;
+    s->fab.off_slots = 3 * arr;
+    s->fab.off_flags = s->fab.off_slots + (size_t)2 * kMaxPeers * kSlotDoubles * sizeof(double);
+    s->win_bytes = s->fab.off_flags + kMaxPeers * sizeof(unsigned long long) + 256;
+    CUC(cudaMalloc(&s->win, s->win_bytes));
+    CUC(cudaMemsetAsync(s->win, 0, s->win_bytes, s->stream));
+    s->posA = reinterpret_cast<float4*>(s->win + s->fab.off_posA);
+    s->upos = reinterpret_cast<uint4*>(s->win + s->fab.off_upos);
+    s->rsum = reinterpret_cast<float4*>(s->win + s->fab.off_rsum);
+  } else {
+    CUC(cudaMalloc(&s->posA, (size_t)s->npad * b16));
+    CUC(cudaMalloc(&s->upos, (size_t)s->npad * b16));
+  }
   CUC(cudaMalloc(&s->gath, (size_t)s->npad * b16));
   CUC(cudaMalloc(&s->vel, (size_t)s->cnt * b16));
   CUC(cudaMalloc(&s->force, (size_t)s->cnt * b16));
@@ -487,10 +535,7 @@ static int create_impl(ljmd_system** out, int N, double rho_or_negL, double T0, 
     const size_t rp = (size_t)s->n_itiles * s->hmax * kITile * b16;
     CUC(cudaMalloc(&s->rpart, rp));
     CUC(cudaMemsetAsync(s->rpart, 0, rp, s->stream));
-    if (world > 1) {
-      CUC(cudaMalloc(&s->rsum, (size_t)s->npad * b16));
-      CUC(cudaMalloc(&s->rshard, (size_t)s->cnt * b16));
-    }
+    if (world > 1) CUC(cudaMalloc(&s->rshard, (size_t)s->cnt * b16));
   }
   CUC(cudaMalloc(&s->part, (size_t)2 * (step_grid(s) + 1) * sizeof(double)));
   CUC(cudaMalloc(&s->counter, sizeof(unsigned int)));
@@ -500,8 +545,10 @@ static int create_impl(ljmd_system** out, int N, double rho_or_negL, double T0, 
   CUC(cudaMalloc(&s->rdf_acc, kRdfBins * sizeof(unsigned long long)));
   CUC(cudaMallocHost(&s->h_sc, sizeof(DevScalars)));
   CUC(cudaMallocHost(&s->h_rdf, kRdfBins * sizeof(unsigned long long)));
-  CUC(cudaMemsetAsync(s->posA, 0, (size_t)s->npad * b16, s->stream));
-  CUC(cudaMemsetAsync(s->upos, 0, (size_t)s->npad * b16, s->stream));
+  if (world == 1) {
+    CUC(cudaMemsetAsync(s->posA, 0, (size_t)s->npad * b16, s->stream));
+    CUC(cudaMemsetAsync(s->upos, 0, (size_t)s->npad * b16, s->stream));
+  }
   CUC(cudaMemsetAsync(s->pos, 0, (size_t)s->cnt * b16, s->stream));
   CUC(cudaMemsetAsync(s->vel, 0, (size_t)s->cnt * b16, s->stream));
   CUC(cudaMemsetAsync(s->force, 0, (size_t)s->cnt * b16, s->stream));
@@ -553,6 +600,44 @@ int ljmd_create_with_L(ljmd_system** out, int N, double L, int bc, float rdf_dr2
 }
 
 extern "C" int ljmd_destroy(ljmd_system* s) { return destroy_impl(s); }
+
+extern "C" int ljmd_fabric_export(ljmd_system* s, void* out64) {
+  if (!s || !out64) return set_err(LJMD_ERR_ARG, "NULL argument");
+  CU(cudaSetDevice(s->device));
+  if (s->world == 1 || !s->win) return set_err(LJMD_ERR_ARG, "fabric needs a distributed system (world > 1)");
+  cudaIpcMemHandle_t h;
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t size");
+  CU(cudaIpcGetMemHandle(&h, s->win));
+  memcpy(out64, &h, 64);
+  return LJMD_OK;
+}
+
+extern "C" int ljmd_fabric_connect(ljmd_system* s, const void* handles) {
+  if (!s || !handles) return set_err(LJMD_ERR_ARG, "NULL argument");
+  CU(cudaSetDevice(s->device));
+  if (s->world == 1 || !s->win) return set_err(LJMD_ERR_ARG, "fabric needs a distributed system (world > 1)");
+  if (s->world > kMaxPeers) return set_err(LJMD_ERR_ARG, "fabric supports up to %d ranks", kMaxPeers);
+  if (s->fab.n > 0) return LJMD_OK;
+  CU(cudaStreamSynchronize(s->stream));
+  for (int r = 0; r < s->world; ++r) {
+    if (r == s->rank) { s->fab.base[r] = s->win; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + (size_t)r * 64, 64);
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      for (int q = 0; q < r; ++q)
+        if (s->peer_map[q]) { cudaIpcCloseMemHandle(s->peer_map[q]); s->peer_map[q] = nullptr; }
+      return set_err(LJMD_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s (staying on NCCL)", r, cudaGetErrorString(e));
+    }
+    s->peer_map[r] = ptr;
+    s->fab.base[r] = (char*)ptr;
+  }
+  s->fab.me = s->rank;
+  s->fab.n = s->world;   // from now on the step collectives run over the peer windows
+  return LJMD_OK;
+}
 
 #define CHECK_S(s)                                              \
   do {                                                          \

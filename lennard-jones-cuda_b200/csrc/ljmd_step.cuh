@@ -24,7 +24,20 @@ struct DevScalars {
   long long av_iters;
   double chi, Tkin_trial;
   double sums[SUM_COUNT];  // raw sums of the current step (local, then all-reduced in place)
+  int fabric_timeout;      // set when a peer never arrived at a fabric barrier
+  int pad_;
 };
+
+// ---- intra-node fabric: peers' windows mapped through CUDA IPC (NVLink / NVSwitch peer memory) ----------
+// Each rank owns one window allocation [posA | upos | rsum | slots | flags]; base[r] is rank r's window as
+// seen from this device (base[me] is the local one).  n == 0: fabric off.
+constexpr int kMaxPeers = 8;
+struct Fabric {
+  char* base[kMaxPeers];
+  int n, me;
+  unsigned long long off_posA, off_upos, off_rsum, off_slots, off_flags;
+};
+constexpr int kSlotDoubles = 8;   // per (parity, source rank): up to 8 doubles
 
 struct StepParams {
   int N;            // all particles
@@ -60,7 +73,8 @@ struct StepParams {
   int npad;         // padded particle count (world * shard capacity)
   const float4* rpart;    // [n_itiles][rp_stride]
   float4* rsum;           // [npad] rank-local column sums (world > 1)
-  const float4* rshard;   // [nloc] reaction totals after the reduce-scatter (world > 1)
+  const float4* rshard;   // [nloc] reaction totals after the reduce-scatter (world > 1, NCCL path)
+  Fabric fab;             // peer windows (world > 1, fabric path)
 };
 
 constexpr int kBlockParticles = 512;   // = kITile of ljmd_core.cu / B of k_force_sym
@@ -98,6 +112,21 @@ __global__ void __launch_bounds__(256) k_reduce_reaction(const StepParams p) {
 __device__ __forceinline__ uint32_t to_fixed(float x, double fix_scale) {
   // box fraction in 32-bit fixed point; the cast to 32 bits is the periodic wrap
   return (uint32_t)(unsigned long long)__double2ll_rn(__dmul_rn((double)x, fix_scale));
+}
+
+// Publish one particle's evaluation position (and fixed-point record).  Fabric on: the store goes straight
+// into every rank's window over NVLink — the all-gather is fused into the producing kernel.
+__device__ __forceinline__ void publish_position(const StepParams& p, int ig, const float4& x) {
+  const uint4 u = make_uint4(to_fixed(x.x, p.fix_scale), to_fixed(x.y, p.fix_scale), to_fixed(x.z, p.fix_scale), 0u);
+  if (p.fab.n > 0) {
+    for (int r = 0; r < p.fab.n; ++r) {
+      reinterpret_cast<float4*>(p.fab.base[r] + p.fab.off_posA)[ig] = x;
+      if (p.bc == 0) reinterpret_cast<uint4*>(p.fab.base[r] + p.fab.off_upos)[ig] = u;
+    }
+  } else {
+    p.posA[ig] = x;
+    if (p.bc == 0) p.upos[ig] = u;
+  }
 }
 
 // pos += dt*v + dt*dt*f/2  in double, stored to float (MDSystem.cpp:447-449, :473-475)
@@ -165,10 +194,7 @@ __global__ void __launch_bounds__(kStepThreads) k_drift(const StepParams p) {
   x.x = drift1(x.x, v.x, f.x, p.dt, p.dt2);
   x.y = drift1(x.y, v.y, f.y, p.dt, p.dt2);
   x.z = drift1(x.z, v.z, f.z, p.dt, p.dt2);
-  const int ig = p.i_begin + il;
-  p.posA[ig] = x;
-  if (p.bc == 0) p.upos[ig] = make_uint4(to_fixed(x.x, p.fix_scale), to_fixed(x.y, p.fix_scale),
-                                        to_fixed(x.z, p.fix_scale), 0u);
+  publish_position(p, p.i_begin + il, x);
   if (!CANON) {
     v.x = kick1(v.x, f.x, p.dt);
     v.y = kick1(v.y, f.y, p.dt);
@@ -181,11 +207,7 @@ __global__ void __launch_bounds__(kStepThreads) k_drift(const StepParams p) {
 __global__ void __launch_bounds__(kStepThreads) k_prepare(const StepParams p) {
   const int il = blockIdx.x * kStepThreads + threadIdx.x;
   if (il >= p.nloc) return;
-  const float4 x = p.pos[il];
-  const int ig = p.i_begin + il;
-  p.posA[ig] = x;
-  if (p.bc == 0) p.upos[ig] = make_uint4(to_fixed(x.x, p.fix_scale), to_fixed(x.y, p.fix_scale),
-                                        to_fixed(x.z, p.fix_scale), 0u);
+  publish_position(p, p.i_begin + il, p.pos[il]);
 }
 
 // Deterministic two-value block reduction + last-block final sum over all blocks.
@@ -263,7 +285,19 @@ __global__ void __launch_bounds__(kStepThreads) k_gather(const StepParams p, int
       f.x += g.x; f.y += g.y; f.z += g.z; f.w += g.w;
     }
     if (p.use_sym) {   // Newton-3 kernel: add the reaction of every pair this particle was the j of
-      const float4 r = (p.world == 1) ? reaction_sum(p, p.i_begin + il) : p.rshard[il];
+      float4 r;
+      if (p.world == 1) {
+        r = reaction_sum(p, p.i_begin + il);
+      } else if (p.fab.n > 0) {
+        // pull every rank's column sum for my particle straight from its window, fixed rank order
+        r = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < p.fab.n; ++q) {
+          const float4 g = reinterpret_cast<const float4*>(p.fab.base[q] + p.fab.off_rsum)[p.i_begin + il];
+          r.x += g.x; r.y += g.y; r.z += g.z;
+        }
+      } else {
+        r = p.rshard[il];
+      }
       f.x += r.x; f.y += r.y; f.z += r.z;
     }
     pe = (double)f.w;
@@ -359,6 +393,44 @@ __global__ void __launch_bounds__(kStepThreads) k_velhist(const float4* __restri
   __syncthreads();
   for (int k = threadIdx.x; k < nbins; k += kStepThreads)
     if (h[k]) atomicAdd(&out[k], h[k]);
+}
+
+// Fabric barrier with an optional all-reduce of sc->sums[first .. first+count): every rank stores its partial
+// sums into its slot of every peer's window, raises its flag there to `epoch`, waits until all its own flags
+// reached `epoch`, and adds the slots up in rank order (bit-identical totals on every rank).  Slots are
+// double-buffered on the epoch parity: a fast rank can be one sync ahead of a slow one, never two.
+__global__ void k_fabric_sync(const Fabric f, unsigned long long epoch, int first, int count, DevScalars* sc) {
+  const int lane = threadIdx.x;
+  const int par = (int)(epoch & 1ull);
+  if (lane < f.n) {
+    if (count > 0) {
+      volatile double* dst = reinterpret_cast<volatile double*>(f.base[lane] + f.off_slots) +
+                             ((size_t)par * kMaxPeers + f.me) * kSlotDoubles;
+      for (int k = 0; k < count; ++k) dst[k] = sc->sums[first + k];
+    }
+    __threadfence_system();
+    reinterpret_cast<volatile unsigned long long*>(f.base[lane] + f.off_flags)[f.me] = epoch;
+    // wait for rank `lane` to arrive
+    volatile unsigned long long* mine = reinterpret_cast<volatile unsigned long long*>(f.base[f.me] + f.off_flags);
+    const long long t0 = clock64();
+    while (mine[lane] < epoch) {
+      if (clock64() - t0 > 20000000000ll) {   // ~10 s: a peer died; fail the step instead of hanging the GPU
+        sc->fabric_timeout = 1;
+        break;
+      }
+    }
+  }
+  __syncwarp();
+  __threadfence_system();
+  if (count > 0 && lane == 0) {
+    const volatile double* src = reinterpret_cast<const volatile double*>(f.base[f.me] + f.off_slots) +
+                                 (size_t)par * kMaxPeers * kSlotDoubles;
+    for (int k = 0; k < count; ++k) {
+      double t = 0.;
+      for (int r = 0; r < f.n; ++r) t += src[(size_t)r * kSlotDoubles + k];
+      sc->sums[first + k] = t;
+    }
+  }
 }
 
 __global__ void k_rdf_accum(const unsigned long long* cur, unsigned long long* acc) {

@@ -54,6 +54,39 @@ def share_unique_id(make_id):
     return uid
 
 
+def all_gather_bytes(b):
+    """Every rank contributes a bytes object; every rank gets the list in rank order."""
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return [bytes(b)]
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, bytes(b))
+    return [bytes(x) for x in out]
+
+
+def connect_fabric(system):
+    """Map every rank's window into every other rank (CUDA IPC) so the per-step exchange uses NVLink peer
+    memory.  Returns True when the fabric is on; False (NCCL stays the transport) when LJMD_COMM=nccl or the
+    mapping fails on any rank."""
+    import torch
+    import torch.distributed as dist
+
+    if system.world == 1 or os.environ.get("LJMD_COMM", "p2p") == "nccl":
+        return False
+    handles = all_gather_bytes(system.fabric_handle())
+    ok = 1
+    try:
+        system.fabric_connect(handles)
+    except Exception:
+        ok = 0
+    t = torch.tensor([ok], device="cuda" if dist.get_backend() == "nccl" else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if int(t.item()) == 0:
+        raise RuntimeError("fabric connect failed on some rank; set LJMD_COMM=nccl to run over NCCL only")
+    return True
+
+
 def barrier():
     import torch
     import torch.distributed as dist

@@ -21,7 +21,7 @@ S_COUNT = 16
 # every symbol include/ljmd.h declares (tests check the library exports all of them)
 API_SYMBOLS = [
     "ljmd_last_error", "ljmd_device_count", "ljmd_create", "ljmd_create_distributed", "ljmd_nccl_unique_id",
-    "ljmd_destroy", "ljmd_rdf_dr2", "ljmd_set_canonical", "ljmd_set_boundary", "ljmd_set_T0", "ljmd_set_state",
+    "ljmd_fabric_export", "ljmd_fabric_connect", "ljmd_destroy", "ljmd_rdf_dr2", "ljmd_set_canonical", "ljmd_set_boundary", "ljmd_set_T0", "ljmd_set_state",
     "ljmd_set_velocities", "ljmd_upload", "ljmd_get_state", "ljmd_step", "ljmd_integrate_host", "ljmd_compute_forces",
     "ljmd_get_scalars", "ljmd_reset_averaging", "ljmd_get_rdf", "ljmd_get_rdf_accum", "ljmd_velocity_histogram",
     "ljmd_launch_count", "ljmd_set_event_timing", "ljmd_last_step_timing", "ljmd_get_launch_info",
@@ -58,6 +58,8 @@ def load_library(path=None):
     lib.ljmd_create_distributed.argtypes = lib.ljmd_create.argtypes + [C.c_int, C.c_int, vp]
     lib.ljmd_nccl_unique_id.argtypes = [vp]
     lib.ljmd_destroy.argtypes = [vp]
+    lib.ljmd_fabric_export.argtypes = [vp, vp]
+    lib.ljmd_fabric_connect.argtypes = [vp, vp]
     lib.ljmd_set_canonical.argtypes = [vp, C.c_int]
     lib.ljmd_set_boundary.argtypes = [vp, C.c_int]
     lib.ljmd_set_T0.argtypes = [vp, C.c_double]
@@ -163,6 +165,19 @@ class LJSystem:
         if rc != 0:
             raise LJMDError(lib.ljmd_last_error().decode())
         return buf.raw
+
+    # -- intra-node fabric (peer windows over NVLink instead of NCCL for the per-step exchange)
+    def fabric_handle(self):
+        buf = C.create_string_buffer(64)
+        self._check(self._lib.ljmd_fabric_export(self._h, buf))
+        return buf.raw
+
+    def fabric_connect(self, handles):
+        """handles: list of `world` 64-byte handles in rank order (every rank's fabric_handle())."""
+        blob = b"".join(bytes(h) for h in handles)
+        if len(blob) != 64 * self.world:
+            raise ValueError("need one 64-byte handle per rank")
+        self._check(self._lib.ljmd_fabric_connect(self._h, C.create_string_buffer(blob, len(blob))))
 
     # -- state
     def set_state(self, pos, vel):

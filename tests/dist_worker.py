@@ -35,6 +35,7 @@ def main():
         vel = pkg.snapshots.velocities(cfg["N"], cfg["T"], seed=21)
         s = pkg.ljmd.LJSystem(cfg["N"], T0=cfg["T"], rho=cfg["rho"], canonical=canonical, bc=bc, device=local_rank,
                               rank=rank, world=world, nccl_unique_id=uid)
+        fabric = D.connect_fabric(s)
         s.set_state(pos, vel)
         _, _, f0 = s.get_state()
         sc0 = s.scalars()
@@ -46,7 +47,7 @@ def main():
         vh = s.velocity_histogram(0.12, 101)
         np.savez(os.path.join(outdir, f"{name}_rank{rank}.npz"), f0=f0, rdf0=rdf0, p1=p1, v1=v1, f1=f1, rdf1=rdf1,
                  vh=vh, sc0=np.array([sc0[k] for k in sorted(sc0)]), sc1=np.array([sc1[k] for k in sorted(sc1)]))
-        res = dict(rank=rank, world=world, nacc=nacc, info=s.launch_info())
+        res = dict(rank=rank, world=world, nacc=nacc, info=s.launch_info(), fabric=bool(fabric))
         s.close()
     with open(os.path.join(outdir, f"{mode}_rank{rank}.json"), "w") as fh:
         json.dump(res, fh)

@@ -13,16 +13,22 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name,canonical,bc,N,rho", [("tvn_periodic", 1, 0, 6000, 0.8), ("evn_hardwall", 0, 1, 5003, 0.05)])
-def test_two_gpu_step_matches_single_gpu(pkg, gpu_lib, tmp_path, name, canonical, bc, N, rho):
+@pytest.mark.parametrize("comm", ["p2p", "nccl"])
+@pytest.mark.parametrize("name,canonical,bc,N,rho", [("tvn_periodic", 1, 0, 6000, 0.8), ("evn_hardwall", 0, 1, 5003, 0.05),
+                                                     ("tvn_periodic_sym", 1, 0, 20000, 0.5)])
+def test_two_gpu_step_matches_single_gpu(pkg, gpu_lib, tmp_path, name, canonical, bc, N, rho, comm):
+    """comm = p2p: per-step exchange over the CUDA-IPC peer windows (fabric); nccl: the NCCL transport."""
     if gpu_lib.ljmd_device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", LJMD_COMM=comm)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", "29544", os.path.join(ROOT, "tests", "dist_worker.py"), "gpu", str(tmp_path),
            name, str(canonical), str(bc), str(N), str(rho)]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stderr[-3000:]
+    import json
+    meta = json.load(open(os.path.join(tmp_path, "gpu_rank0.json")))
+    assert meta["fabric"] == (comm == "p2p")
     r0 = np.load(os.path.join(tmp_path, f"{name}_rank0.npz"))
     r1 = np.load(os.path.join(tmp_path, f"{name}_rank1.npz"))
     for k in r0.files:                       # every rank reports the same global state
