@@ -26,8 +26,13 @@ import ljpkg  # noqa: E402
 DT = 0.004                      # GUI/task default (reference src/gui/mainwindow.cpp:150, input/*)
 FLOP_PER_PAIR = {0: 37, 1: 25, 2: 25}   # flops of one ORDERED pair evaluation, periodic / open
 REACTION_FLOP = 6                        # Newton-3 kernel: 3 more FMAs per unordered pair put -f_ij on particle j
-INSTR_PER_PAIR = {0: 29, 1: 20, 2: 20}  # SURVEY.md §8d minimal FP32-pipe instruction counts per ordered pair
+# FP32-pipe lane-instructions this library's kernels execute per pair evaluation (SASS count):
+# 7 packed FFMA2-class instructions = 14 lanes periodic, 8 = 16 open, + 3 scalar FFMA of reaction (Newton-3)
+FP32_LANE_INSTR = {0: 14, 1: 16, 2: 16}
 SM_COUNT, FP32_LANES = 148, 128
+# dram__bytes_read.sum + dram__bytes_write.sum of the force kernel per launch on one GPU, from the ncu captures
+# under profiles/ (r01_launches_benchC5_newton3.csv, r01_force_sym_kernel_ncu.md); null where not captured
+TRAFFIC_NOTE = {"C5": 1.79e10, "C3": 2.06e7}
 
 
 def measured_peaks():
@@ -312,7 +317,9 @@ def main_ours(args, pkg):
         "ordered_pair_equivalent": {"tflops": ordered_equiv, "frac": ordered_equiv / fp32_peak,
                                     "note": "same launch priced as the reference's ordered double loop (37/25 flop x N(N-1))"},
         "kernel_ms": force_ms, "kernel_share_of_step": force_ms * args.steps / dev_ms,
-        "traffic": None,
+        "fp32_pipe_util": (FP32_LANE_INSTR[cfg["bc"]] + (3 if newton3 else 0)) * evals_per_launch / (force_ms * 1e-3)
+                          / (SM_COUNT * FP32_LANES * clk * 1e6),
+        "traffic": TRAFFIC_NOTE.get(args.config),
     }
     if rank == 0:
         line = {
