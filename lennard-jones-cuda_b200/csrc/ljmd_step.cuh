@@ -84,17 +84,20 @@ __host__ __device__ inline int partner_count(int g, int n) {
   return n / 2 - 1 + (g < n / 2 ? 1 : 0);
 }
 
-// Sum of the reaction rows that hold contributions for global particle j: i-tile I (global block gI) wrote
-// its reaction on block J = j / 512 at window slot o - 1, o = (J - gI) mod n, when 1 <= o <= partner_count(gI).
-// Fixed ascending tile order: deterministic.
+// Sum of the reaction rows that hold contributions for global particle j (block J = j / 512): the i-tile of
+// global block gI = J - o (mod n) wrote its reaction on J at window slot o - 1 when o <= partner_count(gI).
+// Walks the partner offsets in ascending order (fixed order: deterministic), four loads in flight.
 __device__ __forceinline__ float4 reaction_sum(const StepParams& p, int j) {
   const int J = j / kBlockParticles, jj = j - J * kBlockParticles;
+  const int n = p.nblk;
+  const int omax = (n & 1) ? (n - 1) / 2 : n / 2;
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int t = 0; t < p.n_itiles; ++t) {
-    const int gI = p.blk0 + t;
-    int o = J - gI;
-    if (o < 0) o += p.nblk;
-    if (o >= 1 && o <= partner_count(gI, p.nblk)) {
+#pragma unroll 4
+  for (int o = 1; o <= omax; ++o) {
+    int gI = J - o;
+    if (gI < 0) gI += n;
+    const int t = gI - p.blk0;
+    if (t >= 0 && t < p.n_itiles && o <= partner_count(gI, n)) {
       const float4 g = p.rpart[(size_t)t * p.rp_stride + (size_t)(o - 1) * kBlockParticles + jj];
       a.x += g.x; a.y += g.y; a.z += g.z;
     }
