@@ -195,7 +195,7 @@ int ljmd_set_l2_flush(ljmd_system* s, long long bytes);
 
 /* Static facts for rooflines: out[0]=SM count, out[1]=i-tile size, out[2]=splits per i-tile,
  * out[3]=force CTAs per launch, out[4]=world size, out[5]=local particles, out[6]=1 if the Newton-3 kernel
- * (each unordered pair evaluated once) is in use, out[7]=reserved. */
+ * (each unordered pair evaluated once) is in use, out[7]=j-records per shared-memory tile / work unit. */
 int ljmd_get_launch_info(ljmd_system* s, int* out8);
 
 /* Host-only helpers (no device needed), exported so the launch plan and the exact-RDF constants can

@@ -56,7 +56,7 @@ constexpr int kTileJ = 1024;                  // j-records per smem stage
 constexpr int kMinBlocks = 4;                 // resident CTAs/SM the ordered non-RDF kernel is built for
 constexpr int kSymMinBlocks = 3;              // Newton-3 kernel: 139 registers, 3 CTAs/SM measured 4 % faster than 4 (128 regs)
 constexpr int kMinBlocksRdf = 3;
-constexpr int kSymBJ = 256;                   // j-records per work unit of the Newton-3 kernel
+constexpr int kSymBJ = 256;                   // largest j-chunk (work unit) of the Newton-3 kernel; 128 for small N
 constexpr int kSymMinBlocksN = 16;            // use the Newton-3 kernel from this many 512-particle blocks on
 
 struct ljmd_system {
@@ -72,6 +72,7 @@ struct ljmd_system {
   int nblk = 1;     // global number of kITile-blocks
   int use_sym = 0;  // Newton-3 kernel (k_force_sym) instead of the ordered one (k_force)
   int hmax = 0;     // partner offsets per i-tile (rows of the partner window)
+  int sym_bj = 256; // j-records per work unit of the Newton-3 kernel
   float4* rpart = nullptr;   // [n_itiles][hmax*kITile] reaction rows
   float4* rsum = nullptr;    // [npad] rank-local column sums of the reaction rows (world > 1)
   float4* rshard = nullptr;  // [cnt]  reaction totals of this rank's particles after the reduce-scatter
@@ -153,8 +154,29 @@ static int choose_split(int n_itiles, long long work, int smax, int num_sms, int
 }
 
 struct Plan {
-  int nblk, bpr, cnt, i_begin, i_end, nloc, n_itiles, use_sym, hmax, nsplit;
+  int nblk, bpr, cnt, i_begin, i_end, nloc, n_itiles, use_sym, hmax, nsplit, bj;
 };
+
+// Newton-3 kernel: an i-tile's work is `units` chunks of bj j-records that cannot be cut further, so a CTA of
+// a split into S parts does ceil(units/S) of them.  Same wave model as choose_split, with that quantisation
+// and a per-unit cost (two barriers + the slice reduction), over both unit sizes.
+static void choose_sym_split(int n_itiles, int nblk, int num_sms, int nloc, int* out_s, int* out_bj) {
+  const double ovh = 128., unit_ovh = 16.;
+  const long long slots = (long long)num_sms * kSymMinBlocks;
+  double best_cost = 1e300;
+  *out_s = 1;
+  *out_bj = kSymBJ;
+  for (int bj = kSymBJ; bj >= 128; bj >>= 1) {
+    const int units = (sym_max_partner_count(nblk) + 1) * (kITile / bj);
+    for (int sp = 1; sp <= std::min(units, 8 * num_sms); ++sp) {
+      if ((double)sp * nloc * 16. > 1.5e9) break;
+      const long long waves = ((long long)n_itiles * sp + slots - 1) / slots;
+      const int per_cta = (units + sp - 1) / sp;
+      const double cost = (double)waves * (per_cta * (bj + unit_ovh) + ovh);
+      if (cost < best_cost * 0.999) { best_cost = cost; *out_s = sp; *out_bj = bj; }
+    }
+  }
+}
 // Shards are whole kITile-blocks so that an i-tile never straddles two ranks (the Newton-3 block pairing
 // needs global block indices).  LJMD_KERNEL=ordered|sym overrides the kernel choice.
 static Plan make_plan(int N, int rank, int world, int num_sms) {
@@ -173,9 +195,9 @@ static Plan make_plan(int N, int rank, int world, int num_sms) {
   }
   pl.hmax = std::max(1, sym_max_partner_count(pl.nblk));
   if (pl.nloc <= 0) { pl.nsplit = 0; return pl; }
+  pl.bj = kSymBJ;
   if (pl.use_sym) {
-    const int units = (sym_max_partner_count(pl.nblk) + 1) * (kITile / kSymBJ);
-    pl.nsplit = choose_split(pl.n_itiles, (long long)units * kSymBJ, units, num_sms, kSymMinBlocks, pl.cnt);
+    choose_sym_split(pl.n_itiles, pl.nblk, num_sms, pl.cnt, &pl.nsplit, &pl.bj);
   } else {
     pl.nsplit = choose_split(pl.n_itiles, N, N / 64, num_sms, kMinBlocks, pl.cnt);
   }
@@ -215,7 +237,7 @@ template <bool PERIODIC, bool RDF>
 static cudaError_t launch_force_sym_t(ljmd_system* s, const SymParams& sp) {
   constexpr int MINB = RDF ? kMinBlocksRdf : kSymMinBlocks;
   auto kern = k_force_sym<P2, PERIODIC, RDF, kForceThreads, MINB, kNPair>;
-  const size_t smem = force_sym_smem_bytes(RDF, kSymBJ, kForceThreads);
+  const size_t smem = force_sym_smem_bytes(RDF, s->sym_bj, kForceThreads);
   static_assert(2 * kSymBJ * 16 + (kForceThreads / 32) * (kSymBJ + 64) * 16 + 16 + 64 +
                         (kForceThreads / 32) * (kRdfBins * 4 + kRdfQueueCap * 8) <= 48 * 1024,
                 "dynamic shared memory must stay under the 48 KB default (no per-device opt-in needed)");
@@ -251,8 +273,8 @@ static int launch_force(ljmd_system* s, bool rdf) {
   if (s->use_sym) {
     SymParams sp;
     sp.f = fp;
-    sp.f.tile_j = kSymBJ;
-    sp.rpart = s->rpart; sp.ncols = s->hmax * kITile; sp.nblk = s->nblk; sp.bj = kSymBJ;
+    sp.f.tile_j = s->sym_bj;
+    sp.rpart = s->rpart; sp.ncols = s->hmax * kITile; sp.nblk = s->nblk; sp.bj = s->sym_bj;
     if (periodic) e = rdf ? launch_force_sym_t<true, true>(s, sp) : launch_force_sym_t<true, false>(s, sp);
     else e = rdf ? launch_force_sym_t<false, true>(s, sp) : launch_force_sym_t<false, false>(s, sp);
   } else if (periodic) e = rdf ? launch_force_t<true, true>(s, fp) : launch_force_t<true, false>(s, fp);
@@ -478,7 +500,7 @@ static int create_impl(ljmd_system** out, int N, double rho_or_negL, double T0, 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     const Plan pl = make_plan(N, rank, world, sms);
     s->nblk = pl.nblk; s->cnt = pl.cnt; s->npad = pl.cnt * world; s->i_begin = pl.i_begin; s->i_end = pl.i_end;
-    s->nloc = pl.nloc; s->n_itiles = pl.n_itiles; s->use_sym = pl.use_sym; s->hmax = pl.hmax; s->nsplit = pl.nsplit;
+    s->nloc = pl.nloc; s->n_itiles = pl.n_itiles; s->use_sym = pl.use_sym; s->hmax = pl.hmax; s->nsplit = pl.nsplit; s->sym_bj = pl.bj;
     s->num_sms = sms;
   }
   if (s->nloc < 1) { delete s; return set_err(LJMD_ERR_ARG, "rank %d of %d has no particles for N=%d", rank, world, N); }
@@ -954,7 +976,7 @@ extern "C" int ljmd_get_launch_info(ljmd_system* s, int* out8) {
   CHECK_S(s);
   if (!out8) return set_err(LJMD_ERR_ARG, "out8 is NULL");
   out8[0] = s->num_sms; out8[1] = kITile; out8[2] = s->nsplit; out8[3] = s->n_itiles * s->nsplit;
-  out8[4] = s->world; out8[5] = s->nloc; out8[6] = s->use_sym; out8[7] = 0;
+  out8[4] = s->world; out8[5] = s->nloc; out8[6] = s->use_sym; out8[7] = s->use_sym ? s->sym_bj : kTileJ;
   return LJMD_OK;
 }
 

@@ -1,0 +1,73 @@
+"""GPU: long-run statistics next to the reference CPU path run on the same start snapshot.
+
+Error model = the reference's own (src/tasks/auxiliary/time-average-aux.h:27-67): naive standard error of the
+mean times sqrt(s), s = 2 / ln(Var / C1) the statistical inefficiency from the lag-1 autocorrelation
+(Allen & Tildesley pp. 194-195).  The two trajectories decorrelate through FP32 chaos, so the time averages
+must agree within a few of those sigmas; the EVN energy drift must be of the same order."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle.oracle import Reference, reference_available
+
+pytestmark = pytest.mark.gpu
+
+
+def time_average(x):
+    """(mean, error) as TimeAverage::GetMean / GetMeanError."""
+    x = np.asarray(x, dtype=np.float64)
+    n = len(x)
+    mean, var = x.mean(), x.var()
+    c1 = (x[:-1] * x[1:]).sum() / (n - 1) - mean * mean
+    s = 2.0 / math.log(var / c1) if (c1 > 0 and var > c1) else 1.0
+    if s < 0:
+        s = 1.0
+    return mean, math.sqrt(var / n) * math.sqrt(s)
+
+
+@pytest.mark.skipif(not reference_available(), reason="oracle/_ref/libljmd_ref.so not built")
+@pytest.mark.parametrize("name,canonical", [("liquid_evn_periodic", 1), ("liquid_evn_periodic", 0),
+                                            ("mixed_tvn_periodic", 1)])
+def test_time_averages_match_reference(pkg, gpu_lib, name, canonical):
+    g = load_golden(name)
+    N, dt, nsteps = g["N"], 0.004, 1500
+    ref = Reference(N, g["T0"], g["rho"], canonical, 0)
+    ref.set_state(g["pos0"], g["vel0"])
+    series_ref = {k: [] for k in ("U", "T", "P")}
+    for _ in range(nsteps):
+        ref.integrate(dt, 1)
+        sc = ref.scalars()
+        for k in series_ref:
+            series_ref[k].append(sc[k])
+    series_gpu = {k: [] for k in ("U", "T", "P")}
+    with pkg.ljmd.LJSystem(N, T0=g["T0"], rho=g["rho"], canonical=canonical, bc=0) as s:
+        s.set_state(g["pos0"], g["vel0"])
+        for _ in range(nsteps):
+            s.step(dt, 1)
+            sc = s.scalars()
+            for k in series_gpu:
+                series_gpu[k].append(sc[k])
+        tot = s.scalars()
+    # running sums kept on the device = sum of the per-step values (CalculateParameters, MDSystem.cpp:355-358)
+    assert tot["av_iters"] == nsteps
+    assert abs(tot["av_U_tot"] - sum(series_gpu["U"])) <= 1e-9 * abs(sum(series_gpu["U"])) + 1e-6
+    half = nsteps // 3          # discard the first third as equilibration of the thermostat switch
+    for k in ("U", "T", "P"):
+        if k == "U" and not canonical:
+            continue            # conserved in EVN: checked through the drift below
+        if k == "T" and canonical:
+            mr, mg = np.mean(series_ref[k][half:]), np.mean(series_gpu[k][half:])
+            assert abs(mr - g["T0"]) < 5e-3 and abs(mg - g["T0"]) < 5e-3      # the thermostat holds T*
+            continue
+        mr, er = time_average(series_ref[k][half:])
+        mg, eg = time_average(series_gpu[k][half:])
+        scale = N if k == "U" else 1.0
+        assert abs(mr - mg) / scale <= 4.0 * math.hypot(er, eg) / scale + 1e-4, (k, mr, mg, er, eg)
+    if not canonical:
+        u_r, u_g = np.array(series_ref["U"]) / N, np.array(series_gpu["U"]) / N
+        drift_r = abs(np.polyfit(np.arange(nsteps) * dt, u_r, 1)[0])
+        drift_g = abs(np.polyfit(np.arange(nsteps) * dt, u_g, 1)[0])
+        assert drift_g <= 3.0 * drift_r + 2e-4, (drift_r, drift_g)            # |dU/dt| per particle
+        assert np.std(u_g) <= 2.0 * np.std(u_r) + 1e-4                          # same energy fluctuation
