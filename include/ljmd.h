@@ -180,6 +180,18 @@ int ljmd_get_rdf_accum(ljmd_system* s, long long* out256, int* nsamples, int res
  */
 int ljmd_velocity_histogram(ljmd_system* s, double step, int nbins, int* out);
 
+/*
+ * Cumulative sub-volume occupancies, counted on the device: what the fluctuation tasks'
+ * GetNSubsystemBatch(syst, alpha_step, type) and GetNsubVzBatch(syst, vcut_max, alpha_step, type) compute from
+ * h_Pos / h_Vel (src/tasks/run-fluctuations/include/run-fluctuations-aux.h:188-278).  type: 0/1/2 slab along
+ * x/y/z, 3 cube about the centre; velocities 0/1/2 = |vx|,|vy|,|vz| < fraction * vcut_max.  out[k] = number of
+ * particles in the sub-volume of fraction (k+1)*alpha_step; *nout = number of fractions (the reference's own
+ * repeated-addition grid).  Bit-exact with those functions.
+ */
+int ljmd_subvolume_counts(ljmd_system* s, int type, double alpha_step, int* out, int cap, int* nout);
+int ljmd_velocity_subvolume_counts(ljmd_system* s, int type, double vcut_max, double alpha_step, int* out, int cap,
+                                   int* nout);
+
 /* Kernel launches issued by this handle so far (for bench.py's gpu_launches). */
 long long ljmd_launch_count(ljmd_system* s);
 

@@ -178,8 +178,8 @@ static void choose_sym_split(int n_itiles, int nblk, int num_sms, int nloc, int*
   }
 }
 // Shards are whole kITile-blocks so that an i-tile never straddles two ranks (the Newton-3 block pairing
-// needs global block indices).  LJMD_KERNEL=ordered|sym overrides the kernel choice.
-static Plan make_plan(int N, int rank, int world, int num_sms) {
+// needs global block indices).  LJMD_KERNEL=ordered|sym overrides the kernel choice (force_ordered: internal).
+static Plan make_plan(int N, int rank, int world, int num_sms, bool force_ordered = false) {
   Plan pl;
   pl.nblk = (N + kITile - 1) / kITile;
   pl.bpr = (pl.nblk + world - 1) / world;
@@ -193,6 +193,7 @@ static Plan make_plan(int N, int rank, int world, int num_sms) {
     if (!strcmp(e, "ordered")) pl.use_sym = 0;
     if (!strcmp(e, "sym")) pl.use_sym = 1;
   }
+  if (force_ordered) pl.use_sym = 0;
   pl.hmax = std::max(1, sym_max_partner_count(pl.nblk));
   if (pl.nloc <= 0) { pl.nsplit = 0; return pl; }
   pl.bj = kSymBJ;
@@ -434,6 +435,8 @@ extern "C" int ljmd_nccl_unique_id(void* out128) {
 #endif
 }
 
+static Plan make_plan_ordered(int N, int rank, int world, int num_sms) { return make_plan(N, rank, world, num_sms, true); }
+
 extern "C" float ljmd_image_threshold(double L, int k) { return image_threshold(L, k); }
 
 extern "C" int ljmd_plan(int N, int rank, int world, int num_sms, int* out8) {
@@ -549,6 +552,17 @@ static int create_impl(ljmd_system** out, int N, double rho_or_negL, double T0, 
   CUC(cudaMalloc(&s->vel, (size_t)s->cnt * b16));
   CUC(cudaMalloc(&s->force, (size_t)s->cnt * b16));
   CUC(cudaMalloc(&s->tforce, (size_t)s->cnt * b16));
+  if (s->use_sym) {
+    // the reaction rows grow as N^2 / (1024 G) * 16 B: fall back to the ordered kernel when they would not fit
+    size_t free_b = 0, total_b = 0;
+    CUC(cudaMemGetInfo(&free_b, &total_b));
+    const size_t need = (size_t)s->n_itiles * s->hmax * kITile * b16;
+    if (need > free_b / 2) {
+      s->use_sym = 0;
+      const Plan po = make_plan_ordered(N, rank, world, s->num_sms);
+      s->nsplit = po.nsplit;
+    }
+  }
   CUC(cudaMalloc(&s->fpart, (size_t)s->nsplit * s->cnt * b16));
   CUC(cudaMalloc(&s->blockW, (size_t)s->n_itiles * s->nsplit * sizeof(double)));
   if (s->use_sym) {
@@ -955,6 +969,60 @@ extern "C" int ljmd_set_l2_flush(ljmd_system* s, long long bytes) {
     }
   }
   return LJMD_OK;
+}
+
+// Sub-volume occupancy: the per-step consumers of run-fluctuations read h_Pos / h_Vel only
+// to count particles in nested sub-volumes; counting on the device returns ~20 integers instead of 32 B/particle.
+static int subvolume_impl(ljmd_system* s, int type, double alpha_step, double vcut_max, int* out, int cap, int* nout) {
+  CHECK_S(s);
+  if (!out || !nout || !(alpha_step > 0.) || type < 0 || type > 6) return set_err(LJMD_ERR_ARG, "bad sub-volume arguments");
+  SubvolParams q;
+  memset(&q, 0, sizeof(q));
+  q.type = type; q.L = s->L; q.alpha_step = alpha_step; q.vcut_max = vcut_max;
+  q.arr = (type <= 3) ? s->pos : s->vel;
+  q.n = s->nloc;
+  // the reference builds its fraction grid by repeated addition in double: restate the loops literally
+  int nb = 0;
+  if (type <= 3) {
+    for (double alpha = alpha_step; alpha < 1. - 1.e-9; alpha += alpha_step) {   // run-fluctuations-aux.h:198-203
+      if (nb >= kMaxSubBins) return set_err(LJMD_ERR_ARG, "alpha_step too small (more than %d fractions)", kMaxSubBins);
+      q.tLs[nb++] = s->L * pow(alpha, 1. / 3.);
+    }
+  } else {
+    if (!(vcut_max > 0.)) return set_err(LJMD_ERR_ARG, "vcut_max must be positive");
+    for (double alpha = alpha_step; alpha < 1. + 1.e-9; alpha += alpha_step) {   // :251-253
+      if (nb >= kMaxSubBins) return set_err(LJMD_ERR_ARG, "alpha_step too small (more than %d fractions)", kMaxSubBins);
+      ++nb;
+    }
+  }
+  q.nbins = nb;
+  *nout = nb;
+  if (nb == 0) return LJMD_OK;
+  if (nb > cap) return set_err(LJMD_ERR_ARG, "output holds %d counts, %d needed", cap, nb);
+  CU(cudaMemsetAsync(s->velh, 0, (size_t)nb * 4, s->stream));
+  const int g = std::max(1, std::min(step_grid(s), 4 * s->num_sms));
+  k_subvolume<<<g, kStepThreads, 0, s->stream>>>(q, s->velh);
+  CU(cudaGetLastError());
+  s->launches += 1;
+#ifdef LJMD_WITH_NCCL
+  if (s->world > 1) NC(ncclAllReduce(s->velh, s->velh, nb, ncclUint32, ncclSum, s->comm, s->stream));
+#endif
+  unsigned int h[kMaxSubBins];
+  CU(cudaMemcpyAsync(h, s->velh, (size_t)nb * 4, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  long long run = 0;
+  for (int k = 0; k < nb; ++k) { run += h[k]; out[k] = (int)run; }   // cumulative, as :236-237 / :273-274
+  return LJMD_OK;
+}
+
+extern "C" int ljmd_subvolume_counts(ljmd_system* s, int type, double alpha_step, int* out, int cap, int* nout) {
+  if (type < 0 || type > 3) return set_err(LJMD_ERR_ARG, "type must be 0 (x slab), 1 (y), 2 (z) or 3 (cube)");
+  return subvolume_impl(s, type, alpha_step, 1., out, cap, nout);
+}
+extern "C" int ljmd_velocity_subvolume_counts(ljmd_system* s, int type, double vcut_max, double alpha_step, int* out,
+                                              int cap, int* nout) {
+  if (type < 0 || type > 2) return set_err(LJMD_ERR_ARG, "type must be 0 (vx), 1 (vy) or 2 (vz)");
+  return subvolume_impl(s, 4 + type, alpha_step, vcut_max, out, cap, nout);
 }
 
 extern "C" long long ljmd_launch_count(ljmd_system* s) { return s ? s->launches : 0; }

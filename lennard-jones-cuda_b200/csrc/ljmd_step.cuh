@@ -436,6 +436,59 @@ __global__ void k_fabric_sync(const Fabric f, unsigned long long epoch, int firs
   }
 }
 
+// Sub-volume occupancy histograms for the fluctuation tasks
+// (src/tasks/run-fluctuations/include/run-fluctuations-aux.h:188-278 GetNSubsystemBatch / GetNsubVzBatch):
+//  type 0..2  slab along x/y/z: bin = (int)(((double)coord / L) / alpha_step)
+//  type 3     cube about the centre: bin = max over axes of upper_bound(tLs, |coord - L/2| / 0.5)
+//  type 4..6  |v_x|,|v_y|,|v_z|:   bin = (int)((|(double)v| / vcut_max) / alpha_step)
+// Particles whose bin is >= nbins are dropped; the host turns the histogram into cumulative counts.
+// IEEE double divisions on the device are correctly rounded, so the bins equal the CPU's bit for bit.
+constexpr int kMaxSubBins = 128;
+struct SubvolParams {
+  const float4* arr;   // pos (types 0-3) or vel (types 4-6), local shard
+  int n, type, nbins;
+  double L, alpha_step, vcut_max;
+  double tLs[kMaxSubBins];   // type 3: L * alpha_k^(1/3), ascending
+};
+__global__ void __launch_bounds__(kStepThreads) k_subvolume(const SubvolParams q, unsigned int* __restrict__ out) {
+  __shared__ unsigned int h[kMaxSubBins];
+  for (int k = threadIdx.x; k < q.nbins; k += kStepThreads) h[k] = 0u;
+  __syncthreads();
+  for (int i = blockIdx.x * kStepThreads + threadIdx.x; i < q.n; i += gridDim.x * kStepThreads) {
+    const float4 a = q.arr[i];
+    int bin;
+    if (q.type <= 2) {
+      double c = (q.type == 0) ? (double)a.x : (q.type == 1) ? (double)a.y : (double)a.z;
+      c = __ddiv_rn(c, q.L);
+      const double b = __ddiv_rn(c, q.alpha_step);
+      bin = (b < (double)q.nbins) ? (int)b : q.nbins;   // (int) truncates toward zero like the CPU cast
+    } else if (q.type == 3) {
+      bin = 0;
+      const double half = __dmul_rn(0.5, q.L);
+#pragma unroll
+      for (int ax = 0; ax < 3; ++ax) {
+        const double c = (ax == 0) ? (double)a.x : (ax == 1) ? (double)a.y : (double)a.z;
+        const double v = __ddiv_rn(fabs(__dadd_rn(c, -half)), 0.5);
+        int lo = 0, hi = q.nbins;                        // upper_bound: first tLs[k] > v
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (q.tLs[mid] > v) hi = mid; else lo = mid + 1;
+        }
+        bin = max(bin, lo);
+      }
+    } else {
+      double v = (q.type == 4) ? (double)a.x : (q.type == 5) ? (double)a.y : (double)a.z;
+      v = __ddiv_rn(v, q.vcut_max);
+      const double b = __ddiv_rn(fabs(v), q.alpha_step);
+      bin = (b < (double)q.nbins) ? (int)b : q.nbins;
+    }
+    if (bin >= 0 && bin < q.nbins) atomicAdd(&h[bin], 1u);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < q.nbins; k += kStepThreads)
+    if (h[k]) atomicAdd(&out[k], h[k]);
+}
+
 __global__ void k_rdf_accum(const unsigned long long* cur, unsigned long long* acc) {
   acc[threadIdx.x] += cur[threadIdx.x];
 }

@@ -23,7 +23,7 @@ API_SYMBOLS = [
     "ljmd_last_error", "ljmd_device_count", "ljmd_create", "ljmd_create_distributed", "ljmd_nccl_unique_id",
     "ljmd_fabric_export", "ljmd_fabric_connect", "ljmd_destroy", "ljmd_rdf_dr2", "ljmd_set_canonical", "ljmd_set_boundary", "ljmd_set_T0", "ljmd_set_state",
     "ljmd_set_velocities", "ljmd_upload", "ljmd_get_state", "ljmd_step", "ljmd_integrate_host", "ljmd_compute_forces",
-    "ljmd_get_scalars", "ljmd_reset_averaging", "ljmd_get_rdf", "ljmd_get_rdf_accum", "ljmd_velocity_histogram",
+    "ljmd_get_scalars", "ljmd_reset_averaging", "ljmd_get_rdf", "ljmd_get_rdf_accum", "ljmd_velocity_histogram", "ljmd_subvolume_counts", "ljmd_velocity_subvolume_counts",
     "ljmd_launch_count", "ljmd_set_event_timing", "ljmd_last_step_timing", "ljmd_get_launch_info",
     "ljmd_image_threshold", "ljmd_plan", "ljmd_set_l2_flush",
     # legacy seam (MDSystem.cpp:9-25)
@@ -75,6 +75,8 @@ def load_library(path=None):
     lib.ljmd_get_rdf.argtypes = [vp, ip]
     lib.ljmd_get_rdf_accum.argtypes = [vp, C.POINTER(C.c_longlong), ip, C.c_int]
     lib.ljmd_velocity_histogram.argtypes = [vp, C.c_double, C.c_int, ip]
+    lib.ljmd_subvolume_counts.argtypes = [vp, C.c_int, C.c_double, ip, C.c_int, ip]
+    lib.ljmd_velocity_subvolume_counts.argtypes = [vp, C.c_int, C.c_double, C.c_double, ip, C.c_int, ip]
     lib.ljmd_set_event_timing.argtypes = [vp, C.c_int]
     lib.ljmd_last_step_timing.argtypes = [vp, dp, dp, ip]
     lib.ljmd_get_launch_info.argtypes = [vp, ip]
@@ -255,6 +257,22 @@ class LJSystem:
         self._check(self._lib.ljmd_velocity_histogram(self._h, float(step), int(nbins),
                                                       out.ctypes.data_as(C.POINTER(C.c_int))))
         return out
+
+    def subvolume_counts(self, type=3, alpha_step=0.05):
+        """Cumulative counts of GetNSubsystemBatch (type 0/1/2 slab, 3 cube)."""
+        out = np.zeros(128, dtype=np.int32)
+        n = C.c_int(0)
+        self._check(self._lib.ljmd_subvolume_counts(self._h, int(type), float(alpha_step),
+                                                    out.ctypes.data_as(C.POINTER(C.c_int)), 128, C.byref(n)))
+        return out[:n.value].copy()
+
+    def velocity_subvolume_counts(self, type=2, vcut_max=3.0, alpha_step=0.05):
+        """Cumulative counts of GetNsubVzBatch."""
+        out = np.zeros(128, dtype=np.int32)
+        n = C.c_int(0)
+        self._check(self._lib.ljmd_velocity_subvolume_counts(self._h, int(type), float(vcut_max), float(alpha_step),
+                                                             out.ctypes.data_as(C.POINTER(C.c_int)), 128, C.byref(n)))
+        return out[:n.value].copy()
 
     # -- instrumentation
     def launch_count(self):

@@ -164,6 +164,11 @@ class Reference:
             lib.ljref_renormalize_velocities.argtypes = [vp, C.c_int]
             lib.ljref_kinetic_temperature.restype = C.c_double
             lib.ljref_kinetic_temperature.argtypes = [vp]
+            if hasattr(lib, "ljref_subsystem_batch"):
+                lib.ljref_subsystem_batch.argtypes = [vp, C.c_double, C.c_int, vp, C.c_int]
+                lib.ljref_velocity_batch.argtypes = [vp, C.c_double, C.c_double, C.c_int, vp, C.c_int]
+                lib.ljref_subsystem.argtypes = [vp, C.c_double, C.c_int]
+                lib.ljref_velocity_subsystem.argtypes = [vp, C.c_double, C.c_int]
             cls._libs[legacy] = lib
         return cls._libs[legacy]
 
@@ -233,6 +238,18 @@ class Reference:
 
     def updatevelo(self):
         self._l.ljref_updatevelo(self._h)
+
+    def subsystem_batch(self, alpha_step=0.05, type=3):
+        """The reference task helper GetNSubsystemBatch on this system's h_Pos."""
+        out = np.zeros(256, dtype=np.int32)
+        n = self._l.ljref_subsystem_batch(self._h, alpha_step, type, _p(out), 256)
+        return out[:n].copy()
+
+    def velocity_batch(self, vcut_max=3.0, alpha_step=0.05, type=2):
+        """The reference task helper GetNsubVzBatch on this system's h_Vel."""
+        out = np.zeros(256, dtype=np.int32)
+        n = self._l.ljref_velocity_batch(self._h, vcut_max, alpha_step, type, _p(out), 256)
+        return out[:n].copy()
 
     def renormalize_to_energy(self, ust):
         self._l.ljref_renormalize_to_energy(self._h, ust)

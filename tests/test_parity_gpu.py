@@ -322,6 +322,26 @@ def test_legacy_seam(pkg, oracle, gpu_lib):
 
 
 @pytest.mark.skipif(not reference_available(), reason="oracle/_ref/libljmd_ref.so not built")
+@pytest.mark.parametrize("name", ["liquid_evn_periodic", "c1_gas_tvn_periodic", "ragged_tvn_hardwall"])
+def test_subvolume_counters_match_reference_task_helpers(pkg, gpu_lib, name):
+    """the fluctuation tasks' sub-volume counters computed on the device equal the reference's own
+    GetNSubsystemBatch / GetNsubVzBatch (run-fluctuations-aux.h, compiled unmodified) bit for bit."""
+    g = load_golden(name)
+    ref = Reference(g["N"], g["T0"], g["rho"], g["canonical"], g["bc"])
+    ref.set_state(g["pos1"], g["vel1"])
+    with make_system(pkg, g) as s:
+        s.set_state(g["pos1"], g["vel1"])
+        for alpha_step in (0.05, 0.1, 0.03):
+            for t in (0, 1, 2, 3):
+                assert np.array_equal(s.subvolume_counts(t, alpha_step), ref.subsystem_batch(alpha_step, t)), (t, alpha_step)
+            for t in (0, 1, 2):
+                assert np.array_equal(s.velocity_subvolume_counts(t, 3.0, alpha_step),
+                                      ref.velocity_batch(3.0, alpha_step, t)), (t, alpha_step)
+        counts = s.subvolume_counts(3, 0.05)
+        assert (np.diff(counts) >= 0).all() and counts[-1] <= g["N"]
+
+
+@pytest.mark.skipif(not reference_available(), reason="oracle/_ref/libljmd_ref.so not built")
 def test_long_run_statistics_match_reference(pkg, gpu_lib):
     """EVN energy drift and TVN <T>, <P> over a few hundred steps next to the reference CPU path run on
     the same snapshot (N = 500 liquid): same order of drift, averages within the run-to-run spread."""
