@@ -263,6 +263,7 @@ def main_ours(args, pkg):
     wall_s = time.perf_counter() - t0
     launches = sysm.launch_count() - l0
     tim = sysm.last_step_timing()
+    gat = sysm.last_gather_timing()
     clocks = sampler.stop() if sampler else None
     dev_ms = max_over_ranks(tim["total_ms"])
     force_ms = max_over_ranks(tim["force_ms"] / max(1, tim["force_launches"]))
@@ -321,6 +322,20 @@ def main_ours(args, pkg):
                           / (SM_COUNT * FP32_LANES * clk * 1e6),
         "traffic": TRAFFIC_NOTE.get(args.config),
     }
+    # second roofline: the HBM-bound part of the step (k_gather: partial-force + reaction rows -> force,
+    # velocity update) against the measured copy bandwidth of MEASURED_PEAKS.json
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    gather_ms = max_over_ranks(gat["gather_ms"] / max(1, gat["launches"]))
+    roofline_hbm = {
+        "bound": "hbm", "kernel": "k_gather (sum partial-force and reaction rows, finish velocities)",
+        "achieved": gat["bytes_per_launch"] / (gather_ms * 1e-3) / 1e9 if gather_ms > 0 else None,
+        "peak": hbm_peak, "unit": "GB/s",
+        "frac": (gat["bytes_per_launch"] / (gather_ms * 1e-3) / 1e9 / hbm_peak) if gather_ms > 0 else None,
+        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+        "bytes_per_launch": gat["bytes_per_launch"], "kernel_ms": gather_ms,
+        "kernel_share_of_step": gather_ms * args.steps / dev_ms,
+        "note": "rows written by the force kernel a moment earlier are partly served from the 126 MB L2",
+    }
     if rank == 0:
         line = {
             "metric": "pair_interactions_per_s", "value": value, "unit": "pairs/s", "n_gpus": world,
@@ -337,6 +352,7 @@ def main_ours(args, pkg):
                     "call": "ljmd_integrate_host (upload pos+vel, Integrate, download pos+vel+scalars)"},
             "gpu_launches": int(launches),
             "roofline": roofline,
+            "roofline_hbm": roofline_hbm,
             "launch": info,
             "state": {"U_per_N": sc["U"] / N, "T": sc["T"], "P": sc["P"]},
         }

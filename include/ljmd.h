@@ -205,6 +205,11 @@ int ljmd_last_step_timing(ljmd_system* s, double* force_ms, double* total_ms, in
  * stream before every step, evicting the previous step's lines from the 126 MB L2. */
 int ljmd_set_l2_flush(ljmd_system* s, long long bytes);
 
+/* The same for k_gather, the dominant HBM-bound kernel of the step (sums the partial-force and reaction rows,
+ * finishes the velocity update): total milliseconds and launches of the last call, and the algorithmic bytes
+ * one launch moves. */
+int ljmd_last_gather_timing(ljmd_system* s, double* gather_ms, int* launches, double* bytes_per_launch);
+
 /* Static facts for rooflines: out[0]=SM count, out[1]=i-tile size, out[2]=splits per i-tile,
  * out[3]=force CTAs per launch, out[4]=world size, out[5]=local particles, out[6]=1 if the Newton-3 kernel
  * (each unordered pair evaluated once) is in use, out[7]=j-records per shared-memory tile / work unit. */

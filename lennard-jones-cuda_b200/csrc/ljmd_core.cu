@@ -106,6 +106,9 @@ struct ljmd_system {
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
   double last_force_ms = 0., last_total_ms = 0., last_steps_ms = 0.;
   std::vector<cudaEvent_t> step_ev;   // per-step (begin, end) pairs: step time without the L2-flush write
+  std::vector<cudaEvent_t> gath_ev;   // (begin, end) pairs around k_gather: the dominant HBM-bound kernel
+  double last_gather_ms = 0.;
+  int last_gather_launches = 0;
   int last_force_launches = 0;
 #ifdef LJMD_WITH_NCCL
   ncclComm_t comm = nullptr;
@@ -343,11 +346,22 @@ static int evaluate(ljmd_system* s, const StepParams& p, int mode, bool rdf, int
 #endif
     }
   }
+  cudaEvent_t g0 = nullptr, g1 = nullptr;
+  if (s->timing) {
+    CU(cudaEventCreate(&g0));
+    CU(cudaEventCreate(&g1));
+    CU(cudaEventRecord(g0, s->stream));
+  }
   if (mode == GATHER_EVAL) k_gather<GATHER_EVAL><<<g, kStepThreads, 0, s->stream>>>(p, fin, accumulate);
   else if (mode == GATHER_EVN) k_gather<GATHER_EVN><<<g, kStepThreads, 0, s->stream>>>(p, fin, accumulate);
   else k_gather<GATHER_TVN><<<g, kStepThreads, 0, s->stream>>>(p, fin, accumulate);
   CU(cudaGetLastError());
   s->launches += 1;
+  if (s->timing) {
+    CU(cudaEventRecord(g1, s->stream));
+    s->gath_ev.push_back(g0);
+    s->gath_ev.push_back(g1);
+  }
   if (mode == GATHER_TVN) {
     if ((rc = allreduce_sums(s, SUM_PE, 3))) return rc;  // PE, W, TV2
     k_finish_tvn<<<g, kStepThreads, 0, s->stream>>>(p, fin);
@@ -407,6 +421,18 @@ static void collect_timing(ljmd_system* s) {
     cudaEventDestroy(s->ev[k + 1]);
   }
   s->ev.clear();
+  s->last_gather_ms = 0.;
+  s->last_gather_launches = 0;
+  for (size_t k = 0; k + 1 < s->gath_ev.size(); k += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s->gath_ev[k], s->gath_ev[k + 1]) == cudaSuccess) {
+      s->last_gather_ms += ms;
+      s->last_gather_launches += 1;
+    }
+    cudaEventDestroy(s->gath_ev[k]);
+    cudaEventDestroy(s->gath_ev[k + 1]);
+  }
+  s->gath_ev.clear();
 }
 
 // ------------------------------------------------------------------------------------ C ABI: A
@@ -1040,6 +1066,21 @@ extern "C" int ljmd_last_step_timing(ljmd_system* s, double* force_ms, double* t
   if (force_launches) *force_launches = s->last_force_launches;
   return LJMD_OK;
 }
+extern "C" int ljmd_last_gather_timing(ljmd_system* s, double* gather_ms, int* launches, double* bytes_per_launch) {
+  CHECK_S(s);
+  if (gather_ms) *gather_ms = s->last_gather_ms;
+  if (launches) *launches = s->last_gather_launches;
+  if (bytes_per_launch) {
+    // algorithmic bytes of one k_gather launch: per local particle it reads the S direct
+    // partial rows, the reaction rows that target it (one per partner block, or one pre-reduced record per
+    // rank when sharded), velocity and old force, and writes force plus t_Force (TVN) or velocity and position
+    const double per_particle_reads =
+        16. * s->nsplit + (s->use_sym ? 16. * (s->world == 1 ? sym_max_partner_count(s->nblk) : s->world) : 0.) + 32.;
+    *bytes_per_launch = (per_particle_reads + 48.) * (double)s->nloc;
+  }
+  return LJMD_OK;
+}
+
 extern "C" int ljmd_get_launch_info(ljmd_system* s, int* out8) {
   CHECK_S(s);
   if (!out8) return set_err(LJMD_ERR_ARG, "out8 is NULL");

@@ -24,7 +24,7 @@ API_SYMBOLS = [
     "ljmd_fabric_export", "ljmd_fabric_connect", "ljmd_destroy", "ljmd_rdf_dr2", "ljmd_set_canonical", "ljmd_set_boundary", "ljmd_set_T0", "ljmd_set_state",
     "ljmd_set_velocities", "ljmd_upload", "ljmd_get_state", "ljmd_step", "ljmd_integrate_host", "ljmd_compute_forces",
     "ljmd_get_scalars", "ljmd_reset_averaging", "ljmd_get_rdf", "ljmd_get_rdf_accum", "ljmd_velocity_histogram", "ljmd_subvolume_counts", "ljmd_velocity_subvolume_counts",
-    "ljmd_launch_count", "ljmd_set_event_timing", "ljmd_last_step_timing", "ljmd_get_launch_info",
+    "ljmd_launch_count", "ljmd_set_event_timing", "ljmd_last_step_timing", "ljmd_last_gather_timing", "ljmd_get_launch_info",
     "ljmd_image_threshold", "ljmd_plan", "ljmd_set_l2_flush",
     # legacy seam (MDSystem.cpp:9-25)
     "allocateArray", "deleteArray", "copyArrayToDevice", "copyArrayFromDevice", "calculateNForces", "threadExit",
@@ -80,6 +80,7 @@ def load_library(path=None):
     lib.ljmd_set_event_timing.argtypes = [vp, C.c_int]
     lib.ljmd_last_step_timing.argtypes = [vp, dp, dp, ip]
     lib.ljmd_get_launch_info.argtypes = [vp, ip]
+    lib.ljmd_last_gather_timing.argtypes = [vp, dp, ip, dp]
     lib.ljmd_set_l2_flush.argtypes = [vp, C.c_longlong]
     lib.ljmd_image_threshold.restype = C.c_float
     lib.ljmd_image_threshold.argtypes = [C.c_double, C.c_int]
@@ -288,6 +289,11 @@ class LJSystem:
         f, t, n = C.c_double(0), C.c_double(0), C.c_int(0)
         self._check(self._lib.ljmd_last_step_timing(self._h, C.byref(f), C.byref(t), C.byref(n)))
         return dict(force_ms=f.value, total_ms=t.value, force_launches=n.value)
+
+    def last_gather_timing(self):
+        ms, n, b = C.c_double(0), C.c_int(0), C.c_double(0)
+        self._check(self._lib.ljmd_last_gather_timing(self._h, C.byref(ms), C.byref(n), C.byref(b)))
+        return dict(gather_ms=ms.value, launches=n.value, bytes_per_launch=b.value)
 
     def launch_info(self):
         buf = (C.c_int * 8)()
