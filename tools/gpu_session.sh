@@ -17,7 +17,7 @@ if [[ $STAGE == all || $STAGE == bench ]]; then
   timeout 600 python bench.py --config C3 --steps 20 --warmup 3 > gpurun_out/bench_C3.json 2> gpurun_out/bench_C3.err
   timeout 600 python bench.py --config C2 --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/bench_C2.json 2> gpurun_out/bench_C2.err
   timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_C5.json 2> gpurun_out/bench_C5.err
-  cat gpurun_out/bench_C3.json gpurun_out/bench_C2.json gpurun_out/bench_C5.json; tail -3 gpurun_out/bench_*.err
+  cat gpurun_out/bench_C3.json gpurun_out/bench_C2.json gpurun_out/bench_C5.json; for f in gpurun_out/bench_*.err; do tail -n 3 $f; done
 fi
 if [[ $STAGE == all || $STAGE == prof ]]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_C3.csv \
