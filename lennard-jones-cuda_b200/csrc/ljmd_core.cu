@@ -327,7 +327,8 @@ static int allreduce_sums(ljmd_system* s, int first, int count) {
 }
 
 // force evaluation at posA/upos + gather in the given mode
-static int evaluate(ljmd_system* s, const StepParams& p, int mode, bool rdf, int accumulate) {
+// fuse_next: another Integrate follows immediately, so the finishing kernel also does its drift
+static int evaluate(ljmd_system* s, const StepParams& p, int mode, bool rdf, int accumulate, bool fuse_next = false) {
   int rc = launch_force(s, rdf);
   if (rc) return rc;
   const int g = step_grid(s);
@@ -353,6 +354,7 @@ static int evaluate(ljmd_system* s, const StepParams& p, int mode, bool rdf, int
     CU(cudaEventRecord(g0, s->stream));
   }
   if (mode == GATHER_EVAL) k_gather<GATHER_EVAL><<<g, kStepThreads, 0, s->stream>>>(p, fin, accumulate);
+  else if (mode == GATHER_EVN && fuse_next) k_gather<GATHER_EVN, true><<<g, kStepThreads, 0, s->stream>>>(p, fin, accumulate);
   else if (mode == GATHER_EVN) k_gather<GATHER_EVN><<<g, kStepThreads, 0, s->stream>>>(p, fin, accumulate);
   else k_gather<GATHER_TVN><<<g, kStepThreads, 0, s->stream>>>(p, fin, accumulate);
   CU(cudaGetLastError());
@@ -364,7 +366,8 @@ static int evaluate(ljmd_system* s, const StepParams& p, int mode, bool rdf, int
   }
   if (mode == GATHER_TVN) {
     if ((rc = allreduce_sums(s, SUM_PE, 3))) return rc;  // PE, W, TV2
-    k_finish_tvn<<<g, kStepThreads, 0, s->stream>>>(p, fin);
+    if (fuse_next) k_finish_tvn<true><<<g, kStepThreads, 0, s->stream>>>(p, fin);
+    else k_finish_tvn<false><<<g, kStepThreads, 0, s->stream>>>(p, fin);
     CU(cudaGetLastError());
     s->launches += 1;
     if (s->world > 1) {
@@ -385,18 +388,24 @@ static int evaluate(ljmd_system* s, const StepParams& p, int mode, bool rdf, int
     s->launches += 1;
     s->rdf_nacc += 1;
   }
+  // the fused kernel published the next step's evaluation positions: make them visible on every rank
+  if (fuse_next && (rc = allgather_positions(s))) return rc;
   return LJMD_OK;
 }
 
-static int one_step(ljmd_system* s, const StepParams& p, bool rdf) {
+// One Integrate.  drifted: the previous step's finishing kernel already did this step's drift (fusion);
+// fuse_next: do the next step's drift in this step's finishing kernel.
+static int one_step(ljmd_system* s, const StepParams& p, bool rdf, bool drifted = false, bool fuse_next = false) {
   const int g = step_grid(s);
-  if (s->canonical) k_drift<true><<<g, kStepThreads, 0, s->stream>>>(p);
-  else k_drift<false><<<g, kStepThreads, 0, s->stream>>>(p);
-  CU(cudaGetLastError());
-  s->launches += 1;
-  int rc = allgather_positions(s);
-  if (rc) return rc;
-  return evaluate(s, p, s->canonical ? GATHER_TVN : GATHER_EVN, rdf, 1);
+  int rc;
+  if (!drifted) {
+    if (s->canonical) k_drift<true><<<g, kStepThreads, 0, s->stream>>>(p);
+    else k_drift<false><<<g, kStepThreads, 0, s->stream>>>(p);
+    CU(cudaGetLastError());
+    s->launches += 1;
+    if ((rc = allgather_positions(s))) return rc;
+  }
+  return evaluate(s, p, s->canonical ? GATHER_TVN : GATHER_EVN, rdf, 1, fuse_next);
 }
 
 static int sync_scalars(ljmd_system* s) {
@@ -829,6 +838,7 @@ extern "C" int ljmd_step(ljmd_system* s, double dt, int nsteps, int rdf_every) {
   if (nsteps < 0) return set_err(LJMD_ERR_ARG, "nsteps must be >= 0");
   StepParams p = make_step_params(s, dt);
   if (s->timing) CU(cudaEventRecord(s->ev_begin, s->stream));
+  bool drifted = false;
   for (int k = 0; k < nsteps; ++k) {
     const bool rdf = rdf_every > 0 && ((k + 1) % rdf_every == 0);
     if (s->flush_bytes) CU(cudaMemsetAsync(s->flush_buf, k & 0xff, s->flush_bytes, s->stream));
@@ -838,8 +848,13 @@ extern "C" int ljmd_step(ljmd_system* s, double dt, int nsteps, int rdf_every) {
       CU(cudaEventCreate(&e1));
       CU(cudaEventRecord(e0, s->stream));
     }
-    int rc = one_step(s, p, rdf);
+    // Kick-drift-wrap fusion inside a batch.  With the fabric an EVN step of the ordered kernel has no barrier
+    // between a peer's force kernel and this rank's finishing kernel, so its position pushes must not be fused.
+    const bool can_fuse = (s->world == 1) || s->fab.n == 0 || s->use_sym || s->canonical;
+    const bool fuse_next = can_fuse && (k + 1 < nsteps);
+    int rc = one_step(s, p, rdf, drifted, fuse_next);
     if (rc) return rc;
+    drifted = fuse_next;
     if (s->timing) {
       CU(cudaEventRecord(e1, s->stream));
       s->step_ev.push_back(e0);

@@ -273,11 +273,29 @@ __device__ __forceinline__ bool reduce_two(double a, double b, const StepParams&
 
 enum { GATHER_EVAL = 0, GATHER_EVN = 1, GATHER_TVN = 2 };
 
+// Kick-drift-wrap fusion: when another step follows, the kernel that finishes step n (final velocities,
+// boundary wrap, kinetic energy) goes straight on with the drift of step n+1 for its particle — the same
+// arithmetic k_drift would do on the values it just produced — so a batched ljmd_step runs one O(N) kernel
+// per step beside the force kernel instead of two.  `canon`: step n+1 is TVN (no first half-kick).
+__device__ __forceinline__ void fused_next_drift(const StepParams& p, int il, float4 x, float4& v, const float4& f,
+                                                 bool canon) {
+  x.x = drift1(x.x, v.x, f.x, p.dt, p.dt2);
+  x.y = drift1(x.y, v.y, f.y, p.dt, p.dt2);
+  x.z = drift1(x.z, v.z, f.z, p.dt, p.dt2);
+  publish_position(p, p.i_begin + il, x);
+  if (!canon) {
+    v.x = kick1(v.x, f.x, p.dt);
+    v.y = kick1(v.y, f.y, p.dt);
+    v.z = kick1(v.z, f.z, p.dt);
+  }
+}
+
 // Sum the j-split partial forces; then, per mode,
 //  EVAL: K from the current velocities (a bare CalculateForces + CalculateParameters)
 //  EVN : second half-kick, boundary conditions, K            (MDSystem.cpp:458-463,578-579)
 //  TVN : t_Force, t_Vel and sum t_Vel^2                       (MDSystem.cpp:484-498)
-template <int MODE>
+// FUSE (EVN only here; TVN fuses in k_finish_tvn): also perform the drift of the next step.
+template <int MODE, bool FUSE = false>
 __global__ void __launch_bounds__(kStepThreads) k_gather(const StepParams p, int finalize, int accumulate) {
   const int il = blockIdx.x * kStepThreads + threadIdx.x;
   double pe = 0., q = 0.;
@@ -316,8 +334,9 @@ __global__ void __launch_bounds__(kStepThreads) k_gather(const StepParams p, int
       float4 x = p.posA[p.i_begin + il];
       apply_bc(x, v, p.L, p.bc);
       p.pos[il] = x;
-      p.vel[il] = v;
       q = (double)sq3(v.x, v.y, v.z) * 0.5;
+      if (FUSE) fused_next_drift(p, il, x, v, f, false);
+      p.vel[il] = v;
     } else {
       const float4 fo = p.force[il];
       p.force[il] = f;
@@ -338,6 +357,7 @@ __global__ void __launch_bounds__(kStepThreads) k_gather(const StepParams p, int
 }
 
 // TVN velocity update with chi = sqrt(T0 / Tkin(t_Vel)), boundaries, K  (MDSystem.cpp:498-506,578-579)
+template <bool FUSE = false>
 __global__ void __launch_bounds__(kStepThreads) k_finish_tvn(const StepParams p, int finalize) {
   const int il = blockIdx.x * kStepThreads + threadIdx.x;
   double Tkin = p.sc->sums[SUM_TV2];
@@ -355,8 +375,9 @@ __global__ void __launch_bounds__(kStepThreads) k_finish_tvn(const StepParams p,
     float4 x = p.posA[p.i_begin + il];
     apply_bc(x, v, p.L, p.bc);
     p.pos[il] = x;
-    p.vel[il] = v;
     q = (double)sq3(v.x, v.y, v.z) * 0.5;
+    if (FUSE) fused_next_drift(p, il, x, v, p.force[il], true);
+    p.vel[il] = v;
   }
   if (il == 0) { p.sc->chi = chi; p.sc->Tkin_trial = Tkin; }
   const bool last = reduce_two(q, 0., p, SUM_K, SUM_TV2, false);
