@@ -129,8 +129,12 @@ int ljmd_upload(ljmd_system* s, const float* pos4, const float* vel4);
 int ljmd_set_velocities(ljmd_system* s, const float* vel4);
 
 /* Download the current state into host AoS float[4N] arrays (any may be NULL).
- * pos4.w keeps the uploaded w (L/150, MDSystem.cpp:168); force4.w = per-particle
- * sum_j (r^-12 - r^-6) as on the reference GPU path (MDSystem.cu:52,135).
+ * pos4.w keeps the uploaded w (L/150, MDSystem.cpp:168); force4.w carries the
+ * potential column of the reference GPU path (MDSystem.cu:52,135): sum over
+ * particles of force4.w * 2 = V, which is all MDSystem.cpp:340-346 uses.  With the
+ * ordered kernel the entry is the particle's own sum_j (r^-12 - r^-6); the
+ * Newton-3 kernel books each unordered pair (twice) on the particle that held
+ * it as "i", so only the sum is comparable.
  * Replaces copyArrayFromDevice (MDSystem.cu:199-210). */
 int ljmd_get_state(ljmd_system* s, float* pos4, float* vel4, float* force4);
 
@@ -138,7 +142,9 @@ int ljmd_get_state(ljmd_system* s, float* pos4, float* vel4, float* force4);
  * nsteps x MDSystem::Integrate(dt) (MDSystem.cpp:438-583): drift, force
  * evaluation, EVN half-kick or TVN chi-rescale, boundary conditions,
  * CalculateParameters, t += dt.  Everything stays on the device; returns after
- * the last step completed.  rdf_every > 0: the RDF histogram is rebuilt on
+ * the last step completed.  Inside the batch the kernel finishing step k also
+ * performs the drift of step k+1 (kick-drift-wrap fusion); results are bit-identical
+ * to nsteps single calls.  rdf_every > 0: the RDF histogram is rebuilt on
  * every rdf_every-th step of this call (and accumulated, see ljmd_get_rdf_accum);
  * 0: no RDF work (ljmd_get_rdf evaluates it lazily when asked).
  */

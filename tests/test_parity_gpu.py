@@ -192,6 +192,32 @@ def test_ragged_sizes(pkg, oracle, gpu_lib, kernel, N, bc):
         check_forces(oracle, pos, s.L, bc, s.rdf_dr2, frc, s.scalars(), s.rdf_counts())
 
 
+@pytest.mark.parametrize("seed", range(10))
+def test_random_configurations(pkg, oracle, gpu_lib, kernel, seed):
+    """Seeded fuzz: random size, density, boundary and ensemble; evaluation and one step against the oracle."""
+    rng = np.random.Generator(np.random.PCG64(1000 + seed))
+    N = int(rng.integers(2, 2600))
+    rho = float(10 ** rng.uniform(-2.3, 0.0))
+    bc = int(rng.integers(0, 3))
+    canonical = int(rng.integers(0, 2))
+    T = float(rng.uniform(0.5, 2.5))
+    pos = (pkg.snapshots.random_gas(N, rho, min_sep=0.85, seed=seed, periodic=bc == 0) if rho < 0.6
+           else pkg.snapshots.lattice(N, rho, 0.08, seed=seed))
+    vel = pkg.snapshots.velocities(N, T, seed=seed) if N > 2 else np.zeros((N, 4), np.float32)
+    with pkg.ljmd.LJSystem(N, T0=T, rho=rho, canonical=canonical, bc=bc) as s:
+        s.set_state(pos, vel)
+        p0, v0, f0 = s.get_state()
+        check_forces(oracle, pos, s.L, bc, s.rdf_dr2, f0, s.scalars(), s.rdf_counts())
+        if N > 2:
+            s.step(0.004, 1, rdf_every=1)
+            g = dict(N=N, rho=rho, T0=T, dr2=s.rdf_dr2)
+            opos, ovel, ofrc, osc, ordf = oracle_step_from(oracle, g, p0, v0, f0, 0.004, canonical, bc)
+            p1, v1, f1 = s.get_state()
+            assert np.array_equal(p1[:, :3], opos[:, :3])
+            assert np.array_equal(s.rdf_counts(), ordf)
+            assert np.abs(v1[:, :3] - ovel[:, :3]).max() <= 1e-5 * max(1.0, np.abs(ovel[:, :3]).max())
+
+
 def test_positions_outside_the_box(pkg, oracle, gpu_lib, kernel):
     """Unwrapped coordinates (up to several box lengths out): forces still follow the minimum image and the
     RDF still reproduces fast_round() for |n| >= 2."""
