@@ -105,7 +105,9 @@ void ljo_forces(int N, const float* pos, double L, int bc, float rdf_dr2,
  * and every accumulator in double, minimum image by rint().  Not a restatement
  * of reference arithmetic — used to judge which of two FP32 answers is closer
  * and to build the per-particle normalisation sum_j |f_ij| for the tolerance.
- * out: frc[3N] doubles (x,y,z, x4 applied), fabs_sum[N] = 4*sum_j |f_ij|,
+ * out: frc[3N] doubles (x,y,z, x4 applied), fabs_sum[2N]: [0..N) = 4*sum_j |f_ij| (net pair forces),
+ * [N..2N) = 4*sum_j (12 r^-13 + 6 r^-7) (repulsive + attractive magnitudes: the terms any evaluation has to
+ * cancel; near the potential minimum r = 2^(1/6) the net pair force vanishes while its two terms do not),
  * scal[0]=V, scal[1]=P(virial part) with the reference's prefactors;
  * scal[2]=sum of |pair potential| terms, scal[3]=sum of |pair virial| terms (same prefactors): the
  * scales against which "relative" errors of V and P are judged when V or P nearly cancels.
@@ -116,7 +118,7 @@ void ljo_forces_f64(int N, const float* pos, double L, int bc,
   double V = 0., P = 0., Vabs = 0., Pabs = 0.;
   int i, j;
   for (i = 0; i < N; ++i) {
-    double fx = 0., fy = 0., fz = 0., fa = 0.;
+    double fx = 0., fy = 0., fz = 0., fa = 0., ft = 0.;
     const double xi = pos[4 * i], yi = pos[4 * i + 1], zi = pos[4 * i + 2];
     for (j = 0; j < N; ++j) {
       double rx, ry, rz, r2, ir2, r6, s;
@@ -130,6 +132,7 @@ void ljo_forces_f64(int N, const float* pos, double L, int bc,
       s = ir2 * (12. * r6 * r6 - 6. * r6);
       fx += s * rx; fy += s * ry; fz += s * rz;
       fa += fabs(s) * sqrt(r2);
+      ft += ir2 * (12. * r6 * r6 + 6. * r6) * sqrt(r2);
       V += r6 * r6 - r6;
       P += s * r2;
       Vabs += r6 * r6 + r6;
@@ -137,6 +140,7 @@ void ljo_forces_f64(int N, const float* pos, double L, int bc,
     }
     frc[3 * i] = 4. * fx; frc[3 * i + 1] = 4. * fy; frc[3 * i + 2] = 4. * fz;
     fabs_sum[i] = 4. * fa;
+    fabs_sum[N + i] = 4. * ft;
   }
   scal[0] = V * 4. / 2.;
   scal[1] = P * 4. / 3. / 2.;

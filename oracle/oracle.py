@@ -75,14 +75,15 @@ class Oracle:
         return frc, dict(V=scal[0], Pvirial=scal[1], Pshear_conf=scal[2]), rdf
 
     def forces_f64(self, pos, L, bc):
-        """FP64 arbiter -> frc[N,3] float64, fabs_sum[N] float64, dict(V, Pvirial, Vabs, Pabs)"""
+        """FP64 arbiter -> frc[N,3] float64, fabs_sum[N] float64 (sum_j |f_ij|), dict(V, Pvirial, Vabs, Pabs,
+        fterm_sum[N] = sum_j (|repulsive| + |attractive| pair force))"""
         pos = _f4(pos)
         N = pos.size // 4
         frc = np.zeros((N, 3), dtype=np.float64)
-        fa = np.zeros(N, dtype=np.float64)
+        fa = np.zeros(2 * N, dtype=np.float64)
         scal = np.zeros(4, dtype=np.float64)
         self.lib.ljo_forces_f64(N, _p(pos), L, bc, _p(frc), _p(fa), _p(scal))
-        return frc, fa, dict(V=scal[0], Pvirial=scal[1], Vabs=scal[2], Pabs=scal[3])
+        return frc, fa[:N].copy(), dict(V=scal[0], Pvirial=scal[1], Vabs=scal[2], Pabs=scal[3], fterm_sum=fa[N:].copy())
 
     def parameters(self, N, rho, vel, V, Pvirial, Pshear_conf=0.0):
         vel = _f4(vel)
