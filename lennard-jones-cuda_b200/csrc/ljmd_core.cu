@@ -76,6 +76,7 @@ struct ljmd_system {
   float4* rpart = nullptr;   // [n_itiles][hmax*kITile] reaction rows
   float4* rsum = nullptr;    // [npad] rank-local column sums of the reaction rows (world > 1)
   float4* rshard = nullptr;  // [cnt]  reaction totals of this rank's particles after the reduce-scatter
+  uint4* bbox = nullptr;     // [nblk][2] block bounding boxes (RDF pruning in the Newton-3 kernel)
   // fabric (world > 1): one window allocation holding posA | upos | rsum | slots | flags, exported through
   // CUDA IPC; once the peers' windows are mapped the per-step collectives run over peer memory, not NCCL
   char* win = nullptr;
@@ -266,6 +267,16 @@ static int launch_force(ljmd_system* s, bool rdf) {
   const double cut = (double)kRdfBins * (double)s->dr2 * 1.001;
   fp.cut_fast = (float)(periodic ? cut * k2 * k2 : cut);
   fp.L = s->L; fp.thr1 = s->thr1; fp.thr2 = s->thr2; fp.dr2 = s->dr2; fp.inv_dr2 = 1.0f / s->dr2;
+  fp.bbox = nullptr;
+  fp.bbox_cut2 = (float)(cut * 1.002 + 1e-3);
+  if (rdf && s->use_sym) {
+    // block bounding boxes: units whose two boxes are out of histogram range skip the RDF test altogether
+    if (periodic) k_bbox<true, kITile><<<s->nblk, 128, 0, s->stream>>>(fp.jrec, s->N, s->bbox);
+    else k_bbox<false, kITile><<<s->nblk, 128, 0, s->stream>>>(fp.jrec, s->N, s->bbox);
+    CU(cudaGetLastError());
+    s->launches += 1;
+    fp.bbox = s->bbox;
+  }
   if (rdf) CU(cudaMemsetAsync(s->rdf_cur, 0, kRdfBins * sizeof(unsigned long long), s->stream));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (s->timing) {
@@ -501,7 +512,7 @@ static int destroy_impl(ljmd_system* s) {
   cudaFree(s->fpart); cudaFree(s->gath); cudaFree(s->blockW); cudaFree(s->part);
   cudaFree(s->counter); cudaFree(s->velh); cudaFree(s->sc); cudaFree(s->rdf_cur); cudaFree(s->rdf_acc);
   cudaFree(s->flush_buf);
-  cudaFree(s->rpart); cudaFree(s->rshard);
+  cudaFree(s->rpart); cudaFree(s->rshard); cudaFree(s->bbox);
   cudaFreeHost(s->h_sc); cudaFreeHost(s->h_rdf);
   for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
   if (s->ev_begin) cudaEventDestroy(s->ev_begin);
@@ -607,6 +618,7 @@ static int create_impl(ljmd_system** out, int N, double rho_or_negL, double T0, 
     CUC(cudaMalloc(&s->rpart, rp));
     CUC(cudaMemsetAsync(s->rpart, 0, rp, s->stream));
     if (world > 1) CUC(cudaMalloc(&s->rshard, (size_t)s->cnt * b16));
+    CUC(cudaMalloc(&s->bbox, (size_t)s->nblk * 2 * sizeof(uint4)));
   }
   CUC(cudaMalloc(&s->part, (size_t)2 * (step_grid(s) + 1) * sizeof(double)));
   CUC(cudaMalloc(&s->counter, sizeof(unsigned int)));

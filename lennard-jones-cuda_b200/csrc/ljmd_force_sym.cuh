@@ -20,6 +20,8 @@
 // rotating positions and accumulators by shuffle (6 SHFL per step) 1.92 ms; broadcast j + 5-level butterfly
 // sum of the reaction (15 SHFL + 15 FADD per j) 2.37 ms.
 #pragma once
+#include <type_traits>
+
 #include "ljmd_force.cuh"
 
 namespace ljmd {
@@ -39,6 +41,89 @@ __host__ __device__ inline int sym_partner_count(int g, int n) {
   return n / 2 - 1 + (g < n / 2 ? 1 : 0);
 }
 inline int sym_max_partner_count(int n) { return (n & 1) ? (n - 1) / 2 : n / 2; }
+
+// ---- RDF pruning by block bounding boxes ----------------------------------------------------------------------
+// One CTA per block of B particles: component-wise min / max of the j-records (fixed-point for periodic boxes,
+// floats otherwise).  A block that straddles the periodic wrap simply gets a box spanning the axis.
+template <bool PERIODIC, int B>
+__global__ void __launch_bounds__(128) k_bbox(const uint4* __restrict__ jrec, int N, uint4* __restrict__ bbox) {
+  __shared__ unsigned int slo[4][3], shi[4][3];
+  const int base = blockIdx.x * B;
+  unsigned int lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
+  float flo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, fhi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+  for (int k = threadIdx.x; k < B; k += 128) {
+    const int i = base + k;
+    if (i < N) {
+      const uint4 r = jrec[i];
+      const unsigned int c[3] = {r.x, r.y, r.z};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        if (PERIODIC) { lo[a] = min(lo[a], c[a]); hi[a] = max(hi[a], c[a]); }
+        else { flo[a] = fminf(flo[a], __uint_as_float(c[a])); fhi[a] = fmaxf(fhi[a], __uint_as_float(c[a])); }
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      if (PERIODIC) {
+        lo[a] = min(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+        hi[a] = max(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+      } else {
+        flo[a] = fminf(flo[a], __shfl_xor_sync(0xffffffffu, flo[a], o));
+        fhi[a] = fmaxf(fhi[a], __shfl_xor_sync(0xffffffffu, fhi[a], o));
+      }
+    }
+    if ((threadIdx.x & 31) == 0) {
+      slo[threadIdx.x >> 5][a] = PERIODIC ? lo[a] : __float_as_uint(flo[a]);
+      shi[threadIdx.x >> 5][a] = PERIODIC ? hi[a] : __float_as_uint(fhi[a]);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int L3[3], H3[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      if (PERIODIC) {
+        L3[a] = min(min(slo[0][a], slo[1][a]), min(slo[2][a], slo[3][a]));
+        H3[a] = max(max(shi[0][a], shi[1][a]), max(shi[2][a], shi[3][a]));
+      } else {
+        L3[a] = __float_as_uint(fminf(fminf(__uint_as_float(slo[0][a]), __uint_as_float(slo[1][a])),
+                                      fminf(__uint_as_float(slo[2][a]), __uint_as_float(slo[3][a]))));
+        H3[a] = __float_as_uint(fmaxf(fmaxf(__uint_as_float(shi[0][a]), __uint_as_float(shi[1][a])),
+                                      fmaxf(__uint_as_float(shi[2][a]), __uint_as_float(shi[3][a]))));
+      }
+    }
+    bbox[2 * blockIdx.x] = make_uint4(L3[0], L3[1], L3[2], 0u);
+    bbox[2 * blockIdx.x + 1] = make_uint4(H3[0], H3[1], H3[2], 0u);
+  }
+}
+
+// Can any particle of box a be within the histogram range of any particle of box b?  Per axis the gap between
+// the two intervals (on the ring of 2^32 fixed-point units for periodic boxes), summed in quadrature.
+template <bool PERIODIC>
+__device__ __forceinline__ bool boxes_in_range(const uint4& alo, const uint4& ahi, const uint4& blo, const uint4& bhi,
+                                               const ForceParams& p) {
+  const unsigned int al[3] = {alo.x, alo.y, alo.z}, ah[3] = {ahi.x, ahi.y, ahi.z};
+  const unsigned int bl[3] = {blo.x, blo.y, blo.z}, bh[3] = {bhi.x, bhi.y, bhi.z};
+  float g2 = 0.f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float gap;
+    if (PERIODIC) {
+      const bool overlap = (bl[a] <= ah[a]) && (al[a] <= bh[a]);
+      const unsigned int d1 = bl[a] - ah[a], d2 = al[a] - bh[a];   // modulo 2^32: the two ways round the ring
+      gap = overlap ? 0.f : (float)min(d1, d2) * (float)(p.L * (1.0 / 4294967296.0));
+    } else {
+      const float d1 = __uint_as_float(bl[a]) - __uint_as_float(ah[a]);
+      const float d2 = __uint_as_float(al[a]) - __uint_as_float(bh[a]);
+      gap = fmaxf(0.f, fmaxf(d1, d2));
+    }
+    g2 = fmaf(gap, gap, g2);
+  }
+  return g2 <= p.bbox_cut2;
+}
 
 // One pair of i-particles (two lanes of V) against the broadcast j-record; also accumulates this lane's
 // reaction on j.  KILL: per-lane flags zero the interaction (clamped duplicate i's of a ragged last tile).
@@ -180,6 +265,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
   R.n = 0;
   float4* myslice = slices + (size_t)warp * BJ;
   uint4* mystage = stage + warp * 64;
+  uint4 my_lo = make_uint4(0u, 0u, 0u, 0u), my_hi = my_lo;   // bounding box of my own block (RDF pruning)
+  if (RDF && p.bbox != nullptr) { my_lo = p.bbox[2 * gI]; my_hi = p.bbox[2 * gI + 1]; }
 
   while (cur < ue) {
     const int nxt = next_nonempty(cur + 1);
@@ -211,47 +298,63 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
     } else {
       // ---- partner block: each unordered pair once, reaction accumulators travel with the rotating j ----
       wgt = 2.f;
-      const int nchunk = (nj + 31) >> 5;
-      for (int c = 0; c < nchunk; ++c) {
-        const int jl = (c << 5) + lane;
-        // stage the chunk twice back to back: step k reads entry lane + k, no wrap arithmetic
-        const uint4 rec = tu[min(jl, nj - 1)];
-        __syncwarp();
-        mystage[lane] = rec;
-        mystage[lane + 32] = rec;
-        __syncwarp();
-        const uint4* sp_l = mystage + lane;
-        float rjx = 0.f, rjy = 0.f, rjz = 0.f;
-        const bool full = warp_all_valid && ((c << 5) + 32 <= nj);
-        const unsigned nxt_lane = (lane + 1) & 31;
-        if (full) {
+      auto partner_unit = [&](auto rdf_tag) {
+        constexpr bool RU = decltype(rdf_tag)::value;   // build the RDF for this unit?
+        const int nchunk = (nj + 31) >> 5;
+        for (int c = 0; c < nchunk; ++c) {
+          const int jl = (c << 5) + lane;
+          // stage the chunk twice back to back: step k reads entry lane + k, no wrap arithmetic
+          const uint4 rec = tu[min(jl, nj - 1)];
+          __syncwarp();
+          mystage[lane] = rec;
+          mystage[lane + 32] = rec;
+          __syncwarp();
+          const uint4* sp_l = mystage + lane;
+          float rjx = 0.f, rjy = 0.f, rjz = 0.f;
+          const bool full = warp_all_valid && ((c << 5) + 32 <= nj);
+          const unsigned nxt_lane = (lane + 1) & 31;
+          if (full) {
 #pragma unroll UNROLLK
-          for (int k = 0; k < 32; ++k) {
-            const uint4 uj = sp_l[k];
-            const unsigned jg = (unsigned)(j0 + (c << 5) + ((lane + k) & 31));   // only live in RDF variants
+            for (int k = 0; k < 32; ++k) {
+              const uint4 uj = sp_l[k];
+              const unsigned jg = (unsigned)(j0 + (c << 5) + ((lane + k) & 31));   // only live when RU
 #pragma unroll
-            for (int q = 0; q < NPAIR; ++q)
-              pair_sym<V, PERIODIC, false, RDF>(uj, pi[q], acc[q], false, false, rjx, rjy, rjz, p, jg, R);
-            rjx = __shfl_sync(0xffffffffu, rjx, nxt_lane);
-            rjy = __shfl_sync(0xffffffffu, rjy, nxt_lane);
-            rjz = __shfl_sync(0xffffffffu, rjz, nxt_lane);
-          }
-        } else {
-          for (int k = 0; k < 32; ++k) {
-            const uint4 uj = sp_l[k];
-            const int hl = (lane + k) & 31;               // home lane of the j I work on now
-            const bool jdead = ((c << 5) + hl) >= nj;
-            const unsigned jg = (unsigned)(j0 + min((c << 5) + hl, nj - 1));
+              for (int q = 0; q < NPAIR; ++q)
+                pair_sym<V, PERIODIC, false, RU>(uj, pi[q], acc[q], false, false, rjx, rjy, rjz, p, jg, R);
+              rjx = __shfl_sync(0xffffffffu, rjx, nxt_lane);
+              rjy = __shfl_sync(0xffffffffu, rjy, nxt_lane);
+              rjz = __shfl_sync(0xffffffffu, rjz, nxt_lane);
+            }
+          } else {
+            for (int k = 0; k < 32; ++k) {
+              const uint4 uj = sp_l[k];
+              const int hl = (lane + k) & 31;               // home lane of the j I work on now
+              const bool jdead = ((c << 5) + hl) >= nj;
+              const unsigned jg = (unsigned)(j0 + min((c << 5) + hl, nj - 1));
 #pragma unroll
-            for (int q = 0; q < NPAIR; ++q)
-              pair_sym<V, PERIODIC, true, RDF>(uj, pi[q], acc[q], jdead || !pi[q].v_lo, jdead || !pi[q].v_hi, rjx,
-                                               rjy, rjz, p, jg, R);
-            rjx = __shfl_sync(0xffffffffu, rjx, nxt_lane);
-            rjy = __shfl_sync(0xffffffffu, rjy, nxt_lane);
-            rjz = __shfl_sync(0xffffffffu, rjz, nxt_lane);
+              for (int q = 0; q < NPAIR; ++q)
+                pair_sym<V, PERIODIC, true, RU>(uj, pi[q], acc[q], jdead || !pi[q].v_lo, jdead || !pi[q].v_hi, rjx,
+                                                rjy, rjz, p, jg, R);
+              rjx = __shfl_sync(0xffffffffu, rjx, nxt_lane);
+              rjy = __shfl_sync(0xffffffffu, rjy, nxt_lane);
+              rjz = __shfl_sync(0xffffffffu, rjz, nxt_lane);
+            }
           }
+          myslice[jl] = make_float4(rjx, rjy, rjz, 0.f);  // the accumulators are home again; jl < BJ always
         }
-        myslice[jl] = make_float4(rjx, rjy, rjz, 0.f);  // the accumulators are home again; jl < BJ always
+      };
+      if (RDF) {
+        // bounding boxes of the two blocks farther apart than the histogram range: no pair of this unit can
+        // count, run the plain loop (warp-uniform: every thread of the CTA sees the same two boxes)
+        bool near = true;
+        if (p.bbox != nullptr) {
+          const int J = j0 / B;
+          near = boxes_in_range<PERIODIC>(my_lo, my_hi, p.bbox[2 * J], p.bbox[2 * J + 1], p);
+        }
+        if (near) partner_unit(std::true_type());
+        else partner_unit(std::false_type());
+      } else {
+        partner_unit(std::false_type());
       }
     }
     // fold the unit's tile-level accumulators into the run-level ones (two-level float summation);

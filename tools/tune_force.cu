@@ -110,6 +110,7 @@ struct Problem {
   double* blockW;
   unsigned long long* rdf;
   float4* rpart;   // [n][hmax*B] reaction rows for the symmetric kernel (B = 512)
+  uint4* bbox;     // [n][2] block bounding boxes
   int hmax;
   int sms;
 };
@@ -149,6 +150,7 @@ static void run_variant(const Problem& pb, const char* tag, int reps, int tile_j
   fp.fscale = PERIODIC ? (float)(4.0 * pb.L / 4294967296.0) : 4.f;
   fp.cut_fast = (float)(PERIODIC ? 25.6 * 1.001 * k2 * k2 : 25.6 * 1.001);
   fp.L = pb.L; fp.thr1 = (float)(0.5 * pb.L); fp.thr2 = (float)(1.5 * pb.L); fp.dr2 = 0.1f; fp.inv_dr2 = 10.f;
+  fp.bbox = nullptr; fp.bbox_cut2 = 25.7f;
   dim3 grid(n_it, S);
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
@@ -192,7 +194,8 @@ static void run_variant(const Problem& pb, const char* tag, int reps, int tile_j
 }
 
 template <typename V, bool PERIODIC, bool RDF, int THREADS, int MINB, int NPAIR, int UNROLLK = 4>
-static void run_sym(const Problem& pb, const char* tag, int reps, int bj, std::vector<float4>* keep) {
+static void run_sym(const Problem& pb, const char* tag, int reps, int bj, std::vector<float4>* keep,
+                    bool prune = true) {
   auto kern = k_force_sym<V, PERIODIC, RDF, THREADS, MINB, NPAIR, UNROLLK>;
   const size_t smem = force_sym_smem_bytes(RDF, bj, THREADS);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -223,6 +226,13 @@ static void run_sym(const Problem& pb, const char* tag, int reps, int bj, std::v
   fp.fscale = PERIODIC ? (float)(4.0 * pb.L / 4294967296.0) : 4.f;
   fp.cut_fast = (float)(PERIODIC ? 25.6 * 1.001 * k2 * k2 : 25.6 * 1.001);
   fp.L = pb.L; fp.thr1 = (float)(0.5 * pb.L); fp.thr2 = (float)(1.5 * pb.L); fp.dr2 = 0.1f; fp.inv_dr2 = 10.f;
+  fp.bbox = nullptr; fp.bbox_cut2 = 25.7f;
+  if (RDF && prune) {   // block bounding boxes for the RDF pruning test
+    if (PERIODIC) k_bbox<true, THREADS * 2 * NPAIR><<<n, 128>>>(fp.jrec, pb.N, pb.bbox);
+    else k_bbox<false, THREADS * 2 * NPAIR><<<n, 128>>>(fp.jrec, pb.N, pb.bbox);
+    CK(cudaGetLastError());
+    fp.bbox = pb.bbox;
+  }
   const int hmax = std::max(1, sym_max_partner_count(n));
   sp.rpart = pb.rpart; sp.ncols = hmax * B; sp.nblk = n; sp.bj = bj;
   dim3 grid(n, S);
@@ -231,9 +241,13 @@ static void run_sym(const Problem& pb, const char* tag, int reps, int bj, std::v
   CK(cudaEventCreate(&e1));
   const size_t rp_elems = (size_t)n * std::max(1, sym_max_partner_count(n)) * B;
   CK(cudaMemset(pb.rpart, 0, rp_elems * 16));
+  CK(cudaMemset(pb.rdf, 0, 256 * 8));
   kern<<<grid, THREADS, smem>>>(sp);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
+  unsigned long long hist[256], hsum = 0, hmix = 0;   // the histogram of the first launch: total and a hash
+  CK(cudaMemcpy(hist, pb.rdf, sizeof(hist), cudaMemcpyDeviceToHost));
+  for (int b = 0; b < 256; ++b) { hsum += hist[b]; hmix = hmix * 1000003ull + hist[b]; }
   float best = 1e30f, sum = 0.f;
   for (int r = 0; r < reps; ++r) {
     CK(cudaEventRecord(e0));
@@ -276,9 +290,11 @@ static void run_sym(const Problem& pb, const char* tag, int reps, int bj, std::v
   double wref = 0.;
   for (int i = 0; i < pb.N && !keep->empty(); ++i) wref += (*keep)[i].w;
   printf("sym   %-44s regs %3d occ %d grid %4dx%-3d smem %6zu | best %8.4f ms avg %8.4f ms | %7.3f Gpairs/s %6.2f TFLOP/s(alg) "
-         "| maxdiff %.2e/%.2e sum_pe %.6e vs %.6e\n",
+         "| maxdiff %.2e/%.2e sum_pe %.6e vs %.6e",
          tag, fa.numRegs, occ, n, S, smem, best, sum / reps, pairs / (best * 1e-3) / 1e9,
          pairs * flop / (best * 1e-3) / 1e12, maxdiff, scale, maxw, wref);
+  if (RDF) printf(" | rdf total %llu hash %016llx", hsum, hmix);
+  printf("\n");
   fflush(stdout);
 }
 
@@ -318,7 +334,8 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&pb.rdf, 256 * 8));
   pb.hmax = sym_max_partner_count((N + 511) / 512);
   if (pb.hmax < 1) pb.hmax = 1;
-  CK(cudaMalloc(&pb.rpart, ((size_t)N * N / 256 + 4096) * 16));   // enough for blocks of 256 and up
+  CK(cudaMalloc(&pb.rpart, ((size_t)N * N / 256 + 4096) * 16));
+  CK(cudaMalloc(&pb.bbox, (size_t)(N / 256 + 2) * 2 * sizeof(uint4)));   // enough for blocks of 256 and up
   CK(cudaMemset(pb.rdf, 0, 256 * 8));
   CK(cudaMemcpy(pb.upos, hu.data(), (size_t)N * 16, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(pb.posf, hp.data(), (size_t)N * 16, cudaMemcpyHostToDevice));
@@ -331,9 +348,11 @@ int main(int argc, char** argv) {
   run_sym<P2, true, false, 128, 4, 2, 4>(pb, "periodic sym t128 b4 np2 uk4 bj256", reps, 256, &keepP);
   run_variant<P2, true, true, 128, 3, 2, 4>(pb, "periodic+RDF ordered t128 b3 np2 u4", reps, 1024, &keepP);
   run_sym<P2, true, true, 128, 3, 2, 4>(pb, "periodic+RDF sym t128 b3 np2 uk4 bj256", reps, 256, &keepP);
+  run_sym<P2, true, true, 128, 3, 2, 4>(pb, "periodic+RDF sym, no box pruning", reps, 256, &keepP, false);
   run_variant<P2, false, false, 128, 4, 2, 4>(pb, "open ordered P2 t128 b4 np2 u4", reps, 1024, &keepO);
   run_sym<P2, false, false, 128, 3, 2, 4>(pb, "open sym t128 b3 np2 uk4 bj256", reps, 256, &keepO);
   run_variant<P2, false, true, 128, 3, 2, 4>(pb, "open+RDF ordered t128 b3 np2 u4", reps, 1024, &keepO);
   run_sym<P2, false, true, 128, 3, 2, 4>(pb, "open+RDF sym t128 b3 np2 uk4 bj256", reps, 256, &keepO);
+  run_sym<P2, false, true, 128, 3, 2, 4>(pb, "open+RDF sym, no box pruning", reps, 256, &keepO, false);
   return 0;
 }
