@@ -231,6 +231,41 @@ int ljmd_get_launch_info(ljmd_system* s, int* out8);
 float ljmd_image_threshold(double L, int k);
 int ljmd_plan(int N, int rank, int world, int num_sms, int* out8);
 
+/*
+ * Observation trace: everything the fluctuation tasks read after EVERY step,
+ * recorded on the device while ljmd_step runs and fetched in one copy.
+ * Replaces the per-step host passes over h_Pos / h_Vel in
+ * run-fluctuations.cpp:124-135 (CoordFlucsAverage / MomentumFlucsAverage ::
+ * AddTimeStep -> GetNSubsystemBatch / GetNsubVzBatch,
+ * run-fluctuations-aux.h:188-278), GetAvVel (:283-293) and the per-step reads
+ * of U and P in run-isotherm.cpp:104-106 — which force a D2H of the whole state
+ * per step — by one small kernel per step and one D2H per batch.
+ *
+ * kinds[c]: 0,1,2 slab in x,y,z; 3 centred cube (ljmd_subvolume_counts types);
+ * 4,5,6 |vx|,|vy|,|vz| < vcut (ljmd_velocity_subvolume_counts types 0,1,2, which
+ * need vcut_max[c]; the entry is ignored for kinds 0-3, vcut_max may be NULL
+ * when there is no velocity counter).  At most 8 counters.  While a trace is
+ * active ljmd_step appends one row per step and refuses to run past
+ * capacity_steps unread rows; the kick-drift fusion inside a batch is off
+ * (a row needs the end-of-step velocities).
+ */
+int ljmd_trace_begin(ljmd_system* s, int ncounters, const int* kinds, const double* alpha_steps,
+                     const double* vcut_max, int capacity_steps);
+/* Number of counts per step: the bins of all counters, concatenated in order. */
+int ljmd_trace_row_length(ljmd_system* s, int* counts_per_step);
+/*
+ * Fetch and clear the recorded rows (oldest first).  Any output may be NULL.
+ *   scalars       [nsteps][LJMD_TRACE_SCALARS]: t, U, T, P, K, V, Pvirial, 0
+ *   counts        [nsteps][row_length]: per counter the cumulative occupancies,
+ *                 exactly what ljmd_subvolume_counts returns for that step
+ *   mean_velocity [nsteps][3]: GetAvVel; summed in 2^-32 fixed point, so the
+ *                 value does not depend on the launch shape or the GPU count
+ */
+#define LJMD_TRACE_SCALARS 8
+int ljmd_trace_read(ljmd_system* s, int max_steps, int* nsteps, double* scalars, long long* counts,
+                    double* mean_velocity);
+int ljmd_trace_end(ljmd_system* s);
+
 /* ------------------------------------------------- B. legacy seam ---------
  * The six symbols MDSystem.cpp calls (MDSystem.cpp:9-25; definitions replaced:
  * MDSystem.cu:167-173,181-184,199-216,230-291,294-297).  Same signatures, same

@@ -77,6 +77,12 @@ struct ljmd_system {
   float4* rsum = nullptr;    // [npad] rank-local column sums of the reaction rows (world > 1)
   float4* rshard = nullptr;  // [cnt]  reaction totals of this rank's particles after the reduce-scatter
   uint4* bbox = nullptr;     // [nblk][2] block bounding boxes (RDF pruning in the Newton-3 kernel)
+  // observation trace (ljmd_trace_*)
+  int trace_on = 0, trace_cap = 0, trace_n = 0, trace_row = 0, trace_ncounters = 0;
+  int trace_nbins[kMaxTraceCounters] = {0};
+  SubvolSpec* trace_specs = nullptr;            // device copy of the counter specifications
+  unsigned long long* trace_counts = nullptr;   // [trace_cap][trace_row]
+  double* trace_scal = nullptr;                 // [trace_cap][kTraceScalars]
   // fabric (world > 1): one window allocation holding posA | upos | rsum | slots | flags, exported through
   // CUDA IPC; once the peers' windows are mapped the per-step collectives run over peer memory, not NCCL
   char* win = nullptr;
@@ -225,6 +231,9 @@ static StepParams make_step_params(ljmd_system* s, double dt) {
 }
 
 static int step_grid(const ljmd_system* s) { return (s->nloc + kStepThreads - 1) / kStepThreads; }
+
+static void trace_free(ljmd_system* s);
+static int trace_record(ljmd_system* s);
 
 template <bool PERIODIC, bool RDF>
 static cudaError_t launch_force_t(ljmd_system* s, const ForceParams& fp) {
@@ -513,6 +522,7 @@ static int destroy_impl(ljmd_system* s) {
   cudaFree(s->counter); cudaFree(s->velh); cudaFree(s->sc); cudaFree(s->rdf_cur); cudaFree(s->rdf_acc);
   cudaFree(s->flush_buf);
   cudaFree(s->rpart); cudaFree(s->rshard); cudaFree(s->bbox);
+  trace_free(s);
   cudaFreeHost(s->h_sc); cudaFreeHost(s->h_rdf);
   for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
   if (s->ev_begin) cudaEventDestroy(s->ev_begin);
@@ -848,6 +858,8 @@ extern "C" int ljmd_get_state(ljmd_system* s, float* pos4, float* vel4, float* f
 extern "C" int ljmd_step(ljmd_system* s, double dt, int nsteps, int rdf_every) {
   CHECK_S(s);
   if (nsteps < 0) return set_err(LJMD_ERR_ARG, "nsteps must be >= 0");
+  if (s->trace_on && s->trace_n + nsteps > s->trace_cap)
+    return set_err(LJMD_ERR_ARG, "trace holds %d of %d steps: read it before %d more", s->trace_n, s->trace_cap, nsteps);
   StepParams p = make_step_params(s, dt);
   if (s->timing) CU(cudaEventRecord(s->ev_begin, s->stream));
   bool drifted = false;
@@ -863,9 +875,11 @@ extern "C" int ljmd_step(ljmd_system* s, double dt, int nsteps, int rdf_every) {
     // Kick-drift-wrap fusion inside a batch.  With the fabric an EVN step of the ordered kernel has no barrier
     // between a peer's force kernel and this rank's finishing kernel, so its position pushes must not be fused.
     const bool can_fuse = (s->world == 1) || s->fab.n == 0 || s->use_sym || s->canonical;
-    const bool fuse_next = can_fuse && (k + 1 < nsteps);
+    // a trace row needs the end-of-step velocities: no fused half-kick of the next step behind them
+    const bool fuse_next = can_fuse && (k + 1 < nsteps) && !s->trace_on;
     int rc = one_step(s, p, rdf, drifted, fuse_next);
     if (rc) return rc;
+    if (s->trace_on && (rc = trace_record(s))) return rc;
     drifted = fuse_next;
     if (s->timing) {
       CU(cudaEventRecord(e1, s->stream));
@@ -1026,29 +1040,38 @@ extern "C" int ljmd_set_l2_flush(ljmd_system* s, long long bytes) {
 
 // Sub-volume occupancy: the per-step consumers of run-fluctuations read h_Pos / h_Vel only
 // to count particles in nested sub-volumes; counting on the device returns ~20 integers instead of 32 B/particle.
-static int subvolume_impl(ljmd_system* s, int type, double alpha_step, double vcut_max, int* out, int cap, int* nout) {
-  CHECK_S(s);
-  if (!out || !nout || !(alpha_step > 0.) || type < 0 || type > 6) return set_err(LJMD_ERR_ARG, "bad sub-volume arguments");
-  SubvolParams q;
-  memset(&q, 0, sizeof(q));
-  q.type = type; q.L = s->L; q.alpha_step = alpha_step; q.vcut_max = vcut_max;
-  q.arr = (type <= 3) ? s->pos : s->vel;
-  q.n = s->nloc;
-  // the reference builds its fraction grid by repeated addition in double: restate the loops literally
+// The fraction grid of one counter.  The reference builds it by repeated addition in double: restate the loops
+// literally (run-fluctuations-aux.h:198-203 for coordinates, :251-253 for velocities).
+static int build_subvol_spec(ljmd_system* s, int type, double alpha_step, double vcut_max, SubvolSpec* q) {
+  if (!(alpha_step > 0.) || type < 0 || type > 6) return set_err(LJMD_ERR_ARG, "bad sub-volume arguments");
+  memset(q, 0, sizeof(*q));
+  q->type = type; q->L = s->L; q->alpha_step = alpha_step; q->vcut_max = vcut_max;
   int nb = 0;
   if (type <= 3) {
-    for (double alpha = alpha_step; alpha < 1. - 1.e-9; alpha += alpha_step) {   // run-fluctuations-aux.h:198-203
+    for (double alpha = alpha_step; alpha < 1. - 1.e-9; alpha += alpha_step) {
       if (nb >= kMaxSubBins) return set_err(LJMD_ERR_ARG, "alpha_step too small (more than %d fractions)", kMaxSubBins);
-      q.tLs[nb++] = s->L * pow(alpha, 1. / 3.);
+      q->tLs[nb++] = s->L * pow(alpha, 1. / 3.);
     }
   } else {
     if (!(vcut_max > 0.)) return set_err(LJMD_ERR_ARG, "vcut_max must be positive");
-    for (double alpha = alpha_step; alpha < 1. + 1.e-9; alpha += alpha_step) {   // :251-253
+    for (double alpha = alpha_step; alpha < 1. + 1.e-9; alpha += alpha_step) {
       if (nb >= kMaxSubBins) return set_err(LJMD_ERR_ARG, "alpha_step too small (more than %d fractions)", kMaxSubBins);
       ++nb;
     }
   }
-  q.nbins = nb;
+  q->nbins = nb;
+  return LJMD_OK;
+}
+
+static int subvolume_impl(ljmd_system* s, int type, double alpha_step, double vcut_max, int* out, int cap, int* nout) {
+  CHECK_S(s);
+  if (!out || !nout) return set_err(LJMD_ERR_ARG, "bad sub-volume arguments");
+  SubvolParams q;
+  int rc = build_subvol_spec(s, type, alpha_step, vcut_max, &q.s);
+  if (rc) return rc;
+  q.arr = (type <= 3) ? s->pos : s->vel;
+  q.n = s->nloc;
+  const int nb = q.s.nbins;
   *nout = nb;
   if (nb == 0) return LJMD_OK;
   if (nb > cap) return set_err(LJMD_ERR_ARG, "output holds %d counts, %d needed", cap, nb);
@@ -1065,6 +1088,105 @@ static int subvolume_impl(ljmd_system* s, int type, double alpha_step, double vc
   CU(cudaStreamSynchronize(s->stream));
   long long run = 0;
   for (int k = 0; k < nb; ++k) { run += h[k]; out[k] = (int)run; }   // cumulative, as :236-237 / :273-274
+  return LJMD_OK;
+}
+
+// ---- observation trace ---------------------------------------------------------------------------
+static void trace_free(ljmd_system* s) {
+  cudaFree(s->trace_specs); cudaFree(s->trace_counts); cudaFree(s->trace_scal);
+  s->trace_specs = nullptr; s->trace_counts = nullptr; s->trace_scal = nullptr;
+  s->trace_on = 0; s->trace_cap = s->trace_n = s->trace_row = s->trace_ncounters = 0;
+}
+
+extern "C" int ljmd_trace_begin(ljmd_system* s, int ncounters, const int* kinds, const double* alpha_steps,
+                                const double* vcut_max, int capacity_steps) {
+  CHECK_S(s);
+  if (ncounters < 0 || ncounters > kMaxTraceCounters) return set_err(LJMD_ERR_ARG, "0..%d counters", kMaxTraceCounters);
+  if (capacity_steps < 1) return set_err(LJMD_ERR_ARG, "capacity_steps must be >= 1");
+  if (ncounters > 0 && (!kinds || !alpha_steps)) return set_err(LJMD_ERR_ARG, "kinds/alpha_steps must not be NULL");
+  trace_free(s);
+  std::vector<SubvolSpec> specs((size_t)std::max(1, ncounters));
+  int row = 3;
+  for (int c = 0; c < ncounters; ++c) {
+    const double vc = (kinds[c] >= 4) ? (vcut_max ? vcut_max[c] : 0.) : 1.;
+    int rc = build_subvol_spec(s, kinds[c], alpha_steps[c], vc, &specs[c]);
+    if (rc) return rc;
+    s->trace_nbins[c] = specs[c].nbins;
+    row += specs[c].nbins;
+  }
+  CU(cudaMalloc(&s->trace_specs, specs.size() * sizeof(SubvolSpec)));
+  CU(cudaMemcpyAsync(s->trace_specs, specs.data(), specs.size() * sizeof(SubvolSpec), cudaMemcpyHostToDevice, s->stream));
+  CU(cudaStreamSynchronize(s->stream));   // `specs` is a local
+  CU(cudaMalloc(&s->trace_counts, (size_t)capacity_steps * row * sizeof(unsigned long long)));
+  CU(cudaMalloc(&s->trace_scal, (size_t)capacity_steps * kTraceScalars * sizeof(double)));
+  CU(cudaMemsetAsync(s->trace_counts, 0, (size_t)capacity_steps * row * sizeof(unsigned long long), s->stream));
+  s->trace_on = 1; s->trace_cap = capacity_steps; s->trace_n = 0; s->trace_row = row; s->trace_ncounters = ncounters;
+  return LJMD_OK;
+}
+
+extern "C" int ljmd_trace_row_length(ljmd_system* s, int* counts_per_step) {
+  CHECK_S(s);
+  if (!counts_per_step) return set_err(LJMD_ERR_ARG, "counts_per_step must not be NULL");
+  if (!s->trace_on) return set_err(LJMD_ERR_ARG, "no trace is active");
+  *counts_per_step = s->trace_row - 3;
+  return LJMD_OK;
+}
+
+// one row: called in stream order right after a step finished
+static int trace_record(ljmd_system* s) {
+  TraceParams q;
+  q.pos = s->pos; q.vel = s->vel; q.n = s->nloc;
+  q.ncounters = s->trace_ncounters; q.row = s->trace_row; q.specs = s->trace_specs; q.sc = s->sc;
+  q.counts = s->trace_counts + (size_t)s->trace_n * s->trace_row;
+  q.scal = s->trace_scal + (size_t)s->trace_n * kTraceScalars;
+  const int g = std::max(1, std::min(step_grid(s), 4 * s->num_sms));
+  k_trace<<<g, kStepThreads, (size_t)(s->trace_row - 3 + 1) * sizeof(unsigned int), s->stream>>>(q);
+  CU(cudaGetLastError());
+  s->launches += 1;
+  s->trace_n += 1;
+  return LJMD_OK;
+}
+
+extern "C" int ljmd_trace_read(ljmd_system* s, int max_steps, int* nsteps, double* scalars, long long* counts,
+                               double* mean_velocity) {
+  CHECK_S(s);
+  if (!nsteps) return set_err(LJMD_ERR_ARG, "nsteps must not be NULL");
+  if (!s->trace_on) return set_err(LJMD_ERR_ARG, "no trace is active");
+  const int n = s->trace_n, row = s->trace_row, nb = row - 3;
+  if (n > max_steps) return set_err(LJMD_ERR_ARG, "trace holds %d steps, output has room for %d", n, max_steps);
+  *nsteps = n;
+  if (n == 0) return LJMD_OK;
+#ifdef LJMD_WITH_NCCL
+  if (s->world > 1)
+    NC(ncclAllReduce(s->trace_counts, s->trace_counts, (size_t)n * row, ncclUint64, ncclSum, s->comm, s->stream));
+#endif
+  std::vector<unsigned long long> h((size_t)n * row);
+  CU(cudaMemcpyAsync(h.data(), s->trace_counts, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+  if (scalars)
+    CU(cudaMemcpyAsync(scalars, s->trace_scal, (size_t)n * kTraceScalars * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaMemsetAsync(s->trace_counts, 0, (size_t)n * row * sizeof(unsigned long long), s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  for (int k = 0; k < n; ++k) {
+    const unsigned long long* r = h.data() + (size_t)k * row;
+    if (counts) {
+      int off = 0;
+      for (int c = 0; c < s->trace_ncounters; ++c) {   // cumulative per counter, as :236-237 / :273-274
+        long long run = 0;
+        for (int b = 0; b < s->trace_nbins[c]; ++b) { run += (long long)r[off + b]; counts[(size_t)k * nb + off + b] = run; }
+        off += s->trace_nbins[c];
+      }
+    }
+    if (mean_velocity)
+      for (int a = 0; a < 3; ++a)
+        mean_velocity[3 * k + a] = (double)(long long)r[nb + a] / 4294967296.0 / (double)s->N;
+  }
+  s->trace_n = 0;
+  return LJMD_OK;
+}
+
+extern "C" int ljmd_trace_end(ljmd_system* s) {
+  CHECK_S(s);
+  trace_free(s);
   return LJMD_OK;
 }
 

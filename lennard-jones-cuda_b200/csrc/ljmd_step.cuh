@@ -465,49 +465,114 @@ __global__ void k_fabric_sync(const Fabric f, unsigned long long epoch, int firs
 // Particles whose bin is >= nbins are dropped; the host turns the histogram into cumulative counts.
 // IEEE double divisions on the device are correctly rounded, so the bins equal the CPU's bit for bit.
 constexpr int kMaxSubBins = 128;
-struct SubvolParams {
-  const float4* arr;   // pos (types 0-3) or vel (types 4-6), local shard
-  int n, type, nbins;
+struct SubvolSpec {
+  int type, nbins;     // 0-2 slab in x/y/z, 3 centred cube, 4-6 |vx|,|vy|,|vz|
   double L, alpha_step, vcut_max;
   double tLs[kMaxSubBins];   // type 3: L * alpha_k^(1/3), ascending
 };
+struct SubvolParams {
+  const float4* arr;   // pos (types 0-3) or vel (types 4-6), local shard
+  int n;
+  SubvolSpec s;
+};
+// Bin of one particle: the literal arithmetic of GetNSubsystemBatch / GetNsubVzBatch
+// (run-fluctuations-aux.h:188-278); q.nbins = "counted nowhere".
+__device__ __forceinline__ int subvol_bin(const SubvolSpec& q, const float4 a) {
+  int bin;
+  if (q.type <= 2) {
+    double c = (q.type == 0) ? (double)a.x : (q.type == 1) ? (double)a.y : (double)a.z;
+    c = __ddiv_rn(c, q.L);
+    const double b = __ddiv_rn(c, q.alpha_step);
+    bin = (b < (double)q.nbins) ? (int)b : q.nbins;   // (int) truncates toward zero like the CPU cast
+  } else if (q.type == 3) {
+    bin = 0;
+    const double half = __dmul_rn(0.5, q.L);
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+      const double c = (ax == 0) ? (double)a.x : (ax == 1) ? (double)a.y : (double)a.z;
+      const double v = __ddiv_rn(fabs(__dadd_rn(c, -half)), 0.5);
+      int lo = 0, hi = q.nbins;                        // upper_bound: first tLs[k] > v
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (q.tLs[mid] > v) hi = mid; else lo = mid + 1;
+      }
+      bin = max(bin, lo);
+    }
+  } else {
+    double v = (q.type == 4) ? (double)a.x : (q.type == 5) ? (double)a.y : (double)a.z;
+    v = __ddiv_rn(v, q.vcut_max);
+    const double b = __ddiv_rn(fabs(v), q.alpha_step);
+    bin = (b < (double)q.nbins) ? (int)b : q.nbins;
+  }
+  return bin;
+}
 __global__ void __launch_bounds__(kStepThreads) k_subvolume(const SubvolParams q, unsigned int* __restrict__ out) {
   __shared__ unsigned int h[kMaxSubBins];
-  for (int k = threadIdx.x; k < q.nbins; k += kStepThreads) h[k] = 0u;
+  for (int k = threadIdx.x; k < q.s.nbins; k += kStepThreads) h[k] = 0u;
   __syncthreads();
   for (int i = blockIdx.x * kStepThreads + threadIdx.x; i < q.n; i += gridDim.x * kStepThreads) {
-    const float4 a = q.arr[i];
-    int bin;
-    if (q.type <= 2) {
-      double c = (q.type == 0) ? (double)a.x : (q.type == 1) ? (double)a.y : (double)a.z;
-      c = __ddiv_rn(c, q.L);
-      const double b = __ddiv_rn(c, q.alpha_step);
-      bin = (b < (double)q.nbins) ? (int)b : q.nbins;   // (int) truncates toward zero like the CPU cast
-    } else if (q.type == 3) {
-      bin = 0;
-      const double half = __dmul_rn(0.5, q.L);
-#pragma unroll
-      for (int ax = 0; ax < 3; ++ax) {
-        const double c = (ax == 0) ? (double)a.x : (ax == 1) ? (double)a.y : (double)a.z;
-        const double v = __ddiv_rn(fabs(__dadd_rn(c, -half)), 0.5);
-        int lo = 0, hi = q.nbins;                        // upper_bound: first tLs[k] > v
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (q.tLs[mid] > v) hi = mid; else lo = mid + 1;
-        }
-        bin = max(bin, lo);
-      }
-    } else {
-      double v = (q.type == 4) ? (double)a.x : (q.type == 5) ? (double)a.y : (double)a.z;
-      v = __ddiv_rn(v, q.vcut_max);
-      const double b = __ddiv_rn(fabs(v), q.alpha_step);
-      bin = (b < (double)q.nbins) ? (int)b : q.nbins;
-    }
-    if (bin >= 0 && bin < q.nbins) atomicAdd(&h[bin], 1u);
+    const int bin = subvol_bin(q.s, q.arr[i]);
+    if (bin >= 0 && bin < q.s.nbins) atomicAdd(&h[bin], 1u);
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < q.nbins; k += kStepThreads)
+  for (int k = threadIdx.x; k < q.s.nbins; k += kStepThreads)
     if (h[k]) atomicAdd(&out[k], h[k]);
+}
+
+// ---- observation trace: what the fluctuation tasks read after every step, recorded on the device ----------
+// One row per step: the bins of every configured counter (per-bin, not yet cumulative), then the three velocity
+// sums in 2^-32 fixed point (integers: order-free, identical for any grid and any number of ranks), and the
+// step's scalars {t, U, T, P, K, V, Pvirial}.  Replaces the per-step D2H of h_Pos / h_Vel in
+// run-fluctuations.cpp:124-135,177-180 and the per-step reads of U, P in run-isotherm.cpp:104-106.
+constexpr int kMaxTraceCounters = 8;
+constexpr int kTraceScalars = 8;
+struct TraceParams {
+  const float4* pos;
+  const float4* vel;
+  int n;                       // particles of this rank
+  int ncounters, row;          // row = sum of nbins + 3
+  const SubvolSpec* specs;     // [ncounters], device memory
+  const DevScalars* sc;
+  unsigned long long* counts;  // row of this step
+  double* scal;                // kTraceScalars doubles of this step
+};
+__global__ void __launch_bounds__(kStepThreads) k_trace(const TraceParams q) {
+  extern __shared__ unsigned int th[];   // row - 3 bins
+  const int nb = q.row - 3;
+  for (int k = threadIdx.x; k < nb; k += kStepThreads) th[k] = 0u;
+  __syncthreads();
+  long long sx = 0, sy = 0, sz = 0;
+  for (int i = blockIdx.x * kStepThreads + threadIdx.x; i < q.n; i += gridDim.x * kStepThreads) {
+    const float4 x = q.pos[i], v = q.vel[i];
+    int off = 0;
+    for (int c = 0; c < q.ncounters; ++c) {
+      const SubvolSpec& sp = q.specs[c];
+      const int bin = subvol_bin(sp, sp.type <= 3 ? x : v);
+      if (bin >= 0 && bin < sp.nbins) atomicAdd(&th[off + bin], 1u);
+      off += sp.nbins;
+    }
+    sx += __double2ll_rn((double)v.x * 4294967296.0);
+    sy += __double2ll_rn((double)v.y * 4294967296.0);
+    sz += __double2ll_rn((double)v.z * 4294967296.0);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sx += __shfl_xor_sync(0xffffffffu, sx, o);
+    sy += __shfl_xor_sync(0xffffffffu, sy, o);
+    sz += __shfl_xor_sync(0xffffffffu, sz, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&q.counts[nb + 0], (unsigned long long)sx);
+    atomicAdd(&q.counts[nb + 1], (unsigned long long)sy);
+    atomicAdd(&q.counts[nb + 2], (unsigned long long)sz);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < nb; k += kStepThreads)
+    if (th[k]) atomicAdd(&q.counts[k], (unsigned long long)th[k]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    q.scal[0] = q.sc->t; q.scal[1] = q.sc->U; q.scal[2] = q.sc->T; q.scal[3] = q.sc->P;
+    q.scal[4] = q.sc->K; q.scal[5] = q.sc->V; q.scal[6] = q.sc->Pvirial; q.scal[7] = 0.;
+  }
 }
 
 __global__ void k_rdf_accum(const unsigned long long* cur, unsigned long long* acc) {

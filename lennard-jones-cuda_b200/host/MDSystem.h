@@ -90,6 +90,9 @@ class MDSystem {
 
   // Extension: n steps without refreshing the host mirrors in between (they are refreshed once at the end).
   void IntegrateMany(double dt, int nsteps);
+  // Extension: the library handle behind this instance, for callers that go on with the C ABI of include/ljmd.h
+  // (device-resident batches, observation trace).  The host mirrors are NOT refreshed by calls made on it.
+  ljmd_system* handle() const { return m_sys; }
 
   float* getArray(int type);
   void setArray(int type, const float* data);

@@ -24,6 +24,7 @@ API_SYMBOLS = [
     "ljmd_fabric_export", "ljmd_fabric_connect", "ljmd_destroy", "ljmd_rdf_dr2", "ljmd_set_canonical", "ljmd_set_boundary", "ljmd_set_T0", "ljmd_set_state",
     "ljmd_set_velocities", "ljmd_upload", "ljmd_get_state", "ljmd_step", "ljmd_integrate_host", "ljmd_compute_forces",
     "ljmd_get_scalars", "ljmd_reset_averaging", "ljmd_get_rdf", "ljmd_get_rdf_accum", "ljmd_velocity_histogram", "ljmd_subvolume_counts", "ljmd_velocity_subvolume_counts",
+    "ljmd_trace_begin", "ljmd_trace_row_length", "ljmd_trace_read", "ljmd_trace_end",
     "ljmd_launch_count", "ljmd_set_event_timing", "ljmd_last_step_timing", "ljmd_last_gather_timing", "ljmd_get_launch_info",
     "ljmd_image_threshold", "ljmd_plan", "ljmd_set_l2_flush",
     # legacy seam (MDSystem.cpp:9-25)
@@ -77,6 +78,10 @@ def load_library(path=None):
     lib.ljmd_velocity_histogram.argtypes = [vp, C.c_double, C.c_int, ip]
     lib.ljmd_subvolume_counts.argtypes = [vp, C.c_int, C.c_double, ip, C.c_int, ip]
     lib.ljmd_velocity_subvolume_counts.argtypes = [vp, C.c_int, C.c_double, C.c_double, ip, C.c_int, ip]
+    lib.ljmd_trace_begin.argtypes = [vp, C.c_int, ip, dp, dp, C.c_int]
+    lib.ljmd_trace_row_length.argtypes = [vp, ip]
+    lib.ljmd_trace_read.argtypes = [vp, C.c_int, ip, dp, C.POINTER(C.c_longlong), dp]
+    lib.ljmd_trace_end.argtypes = [vp]
     lib.ljmd_set_event_timing.argtypes = [vp, C.c_int]
     lib.ljmd_last_step_timing.argtypes = [vp, dp, dp, ip]
     lib.ljmd_get_launch_info.argtypes = [vp, ip]
@@ -274,6 +279,34 @@ class LJSystem:
         self._check(self._lib.ljmd_velocity_subvolume_counts(self._h, int(type), float(vcut_max), float(alpha_step),
                                                              out.ctypes.data_as(C.POINTER(C.c_int)), 128, C.byref(n)))
         return out[:n.value].copy()
+
+    # -- observation trace (per-step counters and scalars recorded on the device)
+    def trace_begin(self, counters, capacity_steps):
+        """counters: list of (kind, alpha_step[, vcut_max]); kind 0-2 slab x/y/z, 3 cube, 4-6 |vx|,|vy|,|vz|."""
+        n = len(counters)
+        kinds = (C.c_int * max(1, n))(*[int(c[0]) for c in counters])
+        steps = (C.c_double * max(1, n))(*[float(c[1]) for c in counters])
+        vcut = (C.c_double * max(1, n))(*[float(c[2]) if len(c) > 2 else 0.0 for c in counters])
+        self._check(self._lib.ljmd_trace_begin(self._h, n, kinds, steps, vcut, int(capacity_steps)))
+        self._trace_cap = int(capacity_steps)
+
+    def trace_read(self):
+        """-> dict(scalars [n,8] = t,U,T,P,K,V,Pvirial,0; counts [n,row] cumulative per counter; mean_velocity [n,3])."""
+        row = C.c_int(0)
+        self._check(self._lib.ljmd_trace_row_length(self._h, C.byref(row)))
+        cap = self._trace_cap
+        scal = np.zeros((cap, 8), dtype=np.float64)
+        counts = np.zeros((cap, max(1, row.value)), dtype=np.int64)
+        mv = np.zeros((cap, 3), dtype=np.float64)
+        n = C.c_int(0)
+        self._check(self._lib.ljmd_trace_read(self._h, cap, C.byref(n), scal.ctypes.data_as(C.POINTER(C.c_double)),
+                                              counts.ctypes.data_as(C.POINTER(C.c_longlong)),
+                                              mv.ctypes.data_as(C.POINTER(C.c_double))))
+        k = n.value
+        return dict(scalars=scal[:k].copy(), counts=counts[:k, :row.value].copy(), mean_velocity=mv[:k].copy())
+
+    def trace_end(self):
+        self._check(self._lib.ljmd_trace_end(self._h))
 
     # -- instrumentation
     def launch_count(self):

@@ -32,4 +32,20 @@ int ljref_velocity_subsystem(void* h, double vcut, int type)
   return RunFluctuationsFunctions::GetNsubVz(*static_cast<MDSystem*>(h), vcut, type);
 }
 
+// The reference's statistics of one series: NumberStatistics (src/extra/sample-moments/NumberStatistics.h) and
+// TimeAverage (src/tasks/auxiliary/time-average-aux.h:27-67), as the task drivers use them.
+// out[12]: mean, mean error, variance, variance error, scaled variance, its error, skewness, its error,
+//          kurtosis, its error, statistical inefficiency s, correlated mean error
+void ljref_series_statistics(const double* x, int n, double* out)
+{
+  TimeAverage a;
+  for (int i = 0; i < n; ++i) a.AddObservation(x[i]);
+  out[0] = a.stats.GetMean();            out[1] = a.stats.GetMeanError();
+  out[2] = a.stats.GetVariance();        out[3] = a.stats.GetVarianceError();
+  out[4] = a.stats.GetScaledVariance();  out[5] = a.stats.GetScaledVarianceError();
+  out[6] = a.stats.GetSkewness();        out[7] = a.stats.GetSkewnessError();
+  out[8] = a.stats.GetKurtosis();        out[9] = a.stats.GetKurtosisError();
+  out[10] = a.GetS();                    out[11] = a.GetMeanError();
+}
+
 }  // extern "C"

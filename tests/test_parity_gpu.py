@@ -396,6 +396,47 @@ def test_subvolume_counters_match_reference_task_helpers(pkg, gpu_lib, name):
         assert (np.diff(counts) >= 0).all() and counts[-1] <= g["N"]
 
 
+@pytest.mark.parametrize("name", ["liquid_evn_periodic", "c1_gas_tvn_periodic", "ragged_tvn_hardwall"])
+def test_observation_trace_equals_per_step_reads(pkg, gpu_lib, name):
+    """ljmd_trace_*: the rows recorded on the device during one batched ljmd_step equal, bit for bit, what a caller
+    gets by stepping one step at a time and reading scalars, sub-volume counters and velocities after each."""
+    g = load_golden(name)
+    N, dt, nsteps = g["N"], g["dt"], 12
+    counters = [(0, 0.05), (1, 0.05), (2, 0.05), (3, 0.05), (6, 0.05, 3.0 * np.sqrt(g["T0"])), (2, 0.5)]
+    with make_system(pkg, g) as a, make_system(pkg, g) as b:
+        a.set_state(g["pos0"], g["vel0"])
+        b.set_state(g["pos0"], g["vel0"])
+        a.trace_begin(counters, capacity_steps=nsteps)
+        a.step(dt, nsteps)
+        tr = a.trace_read()
+        assert tr["scalars"].shape == (nsteps, 8)
+        for k in range(nsteps):
+            b.step(dt, 1)
+            sc = b.scalars()
+            for j, key in enumerate(("t", "U", "T", "P", "K", "V", "Pvirial")):
+                assert tr["scalars"][k, j] == sc[key], (k, key)
+            row = np.concatenate([b.subvolume_counts(0, 0.05), b.subvolume_counts(1, 0.05), b.subvolume_counts(2, 0.05),
+                                  b.subvolume_counts(3, 0.05),
+                                  b.velocity_subvolume_counts(2, 3.0 * np.sqrt(g["T0"]), 0.05),
+                                  b.subvolume_counts(2, 0.5)])
+            assert np.array_equal(tr["counts"][k], row), k
+            _, v, _ = b.get_state()
+            mv = v[:, :3].astype(np.float64).sum(axis=0) / N
+            assert np.allclose(tr["mean_velocity"][k], mv, rtol=0, atol=1e-9), k
+        # the state after a traced batch is the state after the same single steps
+        pa, va, _ = a.get_state()
+        pb, vb, _ = b.get_state()
+        assert np.array_equal(pa, pb) and np.array_equal(va, vb)
+        # read clears; a full trace refuses more steps until it is read
+        assert a.trace_read()["scalars"].shape[0] == 0
+        a.step(dt, nsteps)
+        with pytest.raises(pkg.ljmd.LJMDError):
+            a.step(dt, 1)
+        assert a.trace_read()["counts"].shape[0] == nsteps
+        a.trace_end()
+        a.step(dt, 3)
+
+
 @pytest.mark.skipif(not reference_available(), reason="oracle/_ref/libljmd_ref.so not built")
 def test_long_run_statistics_match_reference(pkg, gpu_lib):
     """EVN energy drift and TVN <T>, <P> over a few hundred steps next to the reference CPU path run on
