@@ -57,7 +57,7 @@ constexpr int kMinBlocks = 4;                 // resident CTAs/SM the ordered no
 constexpr int kSymMinBlocks = 3;              // Newton-3 kernel: 139 registers, 3 CTAs/SM measured 4 % faster than 4 (128 regs)
 constexpr int kMinBlocksRdf = 3;
 constexpr int kSymBJ = 256;                   // largest j-chunk (work unit) of the Newton-3 kernel; 128 for small N
-constexpr int kSymMinBlocksN = 16;            // use the Newton-3 kernel from this many 512-particle blocks on
+constexpr int kSymMinBlocksN = 8;            // use the Newton-3 kernel from this many 512-particle blocks on
 
 struct ljmd_system {
   int N = 0, bc = 0, canonical = 0;
@@ -167,25 +167,32 @@ struct Plan {
   int nblk, bpr, cnt, i_begin, i_end, nloc, n_itiles, use_sym, hmax, nsplit, bj;
 };
 
-// Newton-3 kernel: an i-tile's work is `units` chunks of bj j-records that cannot be cut further, so a CTA of
-// a split into S parts does ceil(units/S) of them.  Same wave model as choose_split, with that quantisation
-// and a per-unit cost (two barriers + the slice reduction), over both unit sizes.
+// Newton-3 kernel: an i-tile's work is `units` chunks of bj j-records that cannot be cut further; a CTA of a
+// split into S parts does ceil(units/S) of them.  Measured on the B200 (tools/tune_force N reps scan,
+// profiles/r01_tune_force_sym_split_scan.log): at every size from 8 192 to 131 072 particles the kernel gets
+// faster the MORE and SMALLER its CTAs are — down to one or two units per CTA — because the hardware block
+// scheduler then balances the SMs and the tail in which an SM runs a single CTA (one warp per scheduler, well
+// under half the issue rate) shrinks to one unit.  Few large CTAs sized to "whole waves" lost 5 % (65 536),
+// 16 % (32 768) and 15 % (16 384) against that.  So: aim for ~19 CTAs per slot, never fewer than ~4.5 per slot
+// (finer units instead: bj 128 or 64), and stop there — every split adds one row of partial forces that
+// k_gather has to read back.
 static void choose_sym_split(int n_itiles, int nblk, int num_sms, int nloc, int* out_s, int* out_bj) {
-  const double ovh = 128., unit_ovh = 16.;
   const long long slots = (long long)num_sms * kSymMinBlocks;
-  double best_cost = 1e300;
-  *out_s = 1;
-  *out_bj = kSymBJ;
-  for (int bj = kSymBJ; bj >= 128; bj >>= 1) {
-    const int units = (sym_max_partner_count(nblk) + 1) * (kITile / bj);
-    for (int sp = 1; sp <= std::min(units, 8 * num_sms); ++sp) {
-      if ((double)sp * nloc * 16. > 1.5e9) break;
-      const long long waves = ((long long)n_itiles * sp + slots - 1) / slots;
-      const int per_cta = (units + sp - 1) / sp;
-      const double cost = (double)waves * (per_cta * (bj + unit_ovh) + ovh);
-      if (cost < best_cost * 0.999) { best_cost = cost; *out_s = sp; *out_bj = bj; }
-    }
-  }
+  const long long want_lo = (9 * slots) / 2, want_hi = 19 * slots;
+  const int partners = sym_max_partner_count(nblk) + 1;
+  int bj = kSymBJ;
+  while (bj > 64 && (long long)n_itiles * partners * (kITile / bj) < want_lo) bj >>= 1;
+  const int units = partners * (kITile / bj);
+  const long long total = (long long)n_itiles * units;
+  int per_cta = (int)std::max<long long>(1, (total + want_hi - 1) / want_hi);
+  // CTAs of 8+ units amortise their prologue and partial-force row: go on to ~60 CTAs per slot, which keeps the
+  // tail (about half a CTA duration at low residency) under 1 % of the launch
+  if (per_cta >= 8) per_cta = (int)std::max<long long>(8, (total + 60 * slots - 1) / (60 * slots));
+  int sp = (units + per_cta - 1) / per_cta;
+  sp = std::min(sp, 8 * num_sms);
+  while (sp > 1 && (double)sp * nloc * 16. > 1.5e9) --sp;   // partial-force buffer cap
+  *out_s = std::max(1, sp);
+  *out_bj = bj;
 }
 // Shards are whole kITile-blocks so that an i-tile never straddles two ranks (the Newton-3 block pairing
 // needs global block indices).  LJMD_KERNEL=ordered|sym overrides the kernel choice (force_ordered: internal).
@@ -276,15 +283,14 @@ static int launch_force(ljmd_system* s, bool rdf) {
   const double cut = (double)kRdfBins * (double)s->dr2 * 1.001;
   fp.cut_fast = (float)(periodic ? cut * k2 * k2 : cut);
   fp.L = s->L; fp.thr1 = s->thr1; fp.thr2 = s->thr2; fp.dr2 = s->dr2; fp.inv_dr2 = 1.0f / s->dr2;
-  fp.bbox = nullptr;
-  fp.bbox_cut2 = (float)(cut * 1.002 + 1e-3);
+  const uint4* bbox = nullptr;
   if (rdf && s->use_sym) {
     // block bounding boxes: units whose two boxes are out of histogram range skip the RDF test altogether
     if (periodic) k_bbox<true, kITile><<<s->nblk, 128, 0, s->stream>>>(fp.jrec, s->N, s->bbox);
     else k_bbox<false, kITile><<<s->nblk, 128, 0, s->stream>>>(fp.jrec, s->N, s->bbox);
     CU(cudaGetLastError());
     s->launches += 1;
-    fp.bbox = s->bbox;
+    bbox = s->bbox;
   }
   if (rdf) CU(cudaMemsetAsync(s->rdf_cur, 0, kRdfBins * sizeof(unsigned long long), s->stream));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -299,6 +305,7 @@ static int launch_force(ljmd_system* s, bool rdf) {
     sp.f = fp;
     sp.f.tile_j = s->sym_bj;
     sp.rpart = s->rpart; sp.ncols = s->hmax * kITile; sp.nblk = s->nblk; sp.bj = s->sym_bj;
+    sp.bbox = bbox; sp.bbox_cut2 = (float)(cut * 1.002 + 1e-3);
     if (periodic) e = rdf ? launch_force_sym_t<true, true>(s, sp) : launch_force_sym_t<true, false>(s, sp);
     else e = rdf ? launch_force_sym_t<false, true>(s, sp) : launch_force_sym_t<false, false>(s, sp);
   } else if (periodic) e = rdf ? launch_force_t<true, true>(s, fp) : launch_force_t<true, false>(s, fp);

@@ -126,9 +126,6 @@ struct ForceParams {
   float4* fpart;         // [nsplit][ilocal_cap] partial forces (fx,fy,fz, sum_j(r^-12 - r^-6))
   double* blockW;        // [gridDim.y * gridDim.x] per-CTA sum of u = r.f_ij/4 (virial, un-prefactored)
   unsigned long long* rdf;  // [256] global RDF counters (RDF variants only)
-  const uint4* bbox;     // [nblk][2] per-block bounding boxes (lo.xyz, hi.xyz) or nullptr; periodic: fixed-point
-                         // coordinates, open: float bits.  Lets RDF variants skip whole units that are out of range
-  float bbox_cut2;       // squared histogram range (real units, with margin) for the box-gap test
   int N;                 // total particles (j range is always 0..N)
   int i_begin, i_end;    // this rank's i-shard [i_begin, i_end)
   int ilocal_cap;        // row stride of fpart

@@ -27,12 +27,20 @@
 namespace ljmd {
 
 struct SymParams {
+#ifdef LJMD_PERTURB   // tools/ only: shifts every parameter offset to sample ptxas' schedules
+  char perturb_[LJMD_PERTURB];
+#endif
   ForceParams f;   // jrec, posf, fpart, blockW, rdf, N, i_begin (multiple of B), i_end, ilocal_cap, constants
   float4* rpart;   // [local i-tiles][ncols] reaction rows (fx,fy,fz,0): row = i-tile of this rank, column =
                    // (partner offset - 1) * B + index inside the partner block (the tile's partner window)
   int ncols;       // row stride = hmax * B
   int nblk;        // global number of blocks = ceil(N / B)
   int bj;          // j-records per unit (multiple of 32, divides B)
+  // RDF pruning.  Appended here (not to ForceParams) so that every parameter offset the plain kernels read is
+  // what it was before: ptxas' schedule of the hot loop shifts with them, worth 1-2 % of the kernel either way.
+  float bbox_cut2;    // squared histogram range (real units, with margin) for the box-gap test
+  const uint4* bbox;  // [nblk][2] per-block bounding boxes (lo.xyz, hi.xyz) or nullptr; periodic: fixed-point
+                      // coordinates, open: float bits
 };
 
 // number of partner offsets of global block g among n blocks
@@ -104,7 +112,7 @@ __global__ void __launch_bounds__(128) k_bbox(const uint4* __restrict__ jrec, in
 // the two intervals (on the ring of 2^32 fixed-point units for periodic boxes), summed in quadrature.
 template <bool PERIODIC>
 __device__ __forceinline__ bool boxes_in_range(const uint4& alo, const uint4& ahi, const uint4& blo, const uint4& bhi,
-                                               const ForceParams& p) {
+                                               double L, float cut2) {
   const unsigned int al[3] = {alo.x, alo.y, alo.z}, ah[3] = {ahi.x, ahi.y, ahi.z};
   const unsigned int bl[3] = {blo.x, blo.y, blo.z}, bh[3] = {bhi.x, bhi.y, bhi.z};
   float g2 = 0.f;
@@ -114,7 +122,7 @@ __device__ __forceinline__ bool boxes_in_range(const uint4& alo, const uint4& ah
     if (PERIODIC) {
       const bool overlap = (bl[a] <= ah[a]) && (al[a] <= bh[a]);
       const unsigned int d1 = bl[a] - ah[a], d2 = al[a] - bh[a];   // modulo 2^32: the two ways round the ring
-      gap = overlap ? 0.f : (float)min(d1, d2) * (float)(p.L * (1.0 / 4294967296.0));
+      gap = overlap ? 0.f : (float)min(d1, d2) * (float)(L * (1.0 / 4294967296.0));
     } else {
       const float d1 = __uint_as_float(bl[a]) - __uint_as_float(ah[a]);
       const float d2 = __uint_as_float(al[a]) - __uint_as_float(bh[a]);
@@ -122,7 +130,7 @@ __device__ __forceinline__ bool boxes_in_range(const uint4& alo, const uint4& ah
     }
     g2 = fmaf(gap, gap, g2);
   }
-  return g2 <= p.bbox_cut2;
+  return g2 <= cut2;
 }
 
 // One pair of i-particles (two lanes of V) against the broadcast j-record; also accumulates this lane's
@@ -174,6 +182,55 @@ __device__ __forceinline__ void pair_sym(const uint4& uj, const PairI<V>& pi, Pa
 }
 
 // grid: (i-tiles of this rank, splits).  block: THREADS.  dyn smem: force_sym_smem_bytes().
+// The chunk loop of one partner unit, RU = build the RDF for it.  A macro, not a lambda or a helper template:
+// the plain kernel must compile to exactly the loop it had before the pruned path existed (wrapping it in a
+// generic lambda cost 2.3 % of the kernel through a different instruction schedule, same instruction mix).
+#define LJMD_SYM_PARTNER_CHUNKS(RU)                                                                              \
+  {                                                                                                              \
+    const int nchunk = (nj + 31) >> 5;                                                                           \
+    for (int c = 0; c < nchunk; ++c) {                                                                           \
+      const int jl = (c << 5) + lane;                                                                            \
+      /* stage the chunk twice back to back: step k reads entry lane + k, no wrap arithmetic */                  \
+      const uint4 rec = tu[min(jl, nj - 1)];                                                                     \
+      __syncwarp();                                                                                              \
+      mystage[lane] = rec;                                                                                       \
+      mystage[lane + 32] = rec;                                                                                  \
+      __syncwarp();                                                                                              \
+      const uint4* sp_l = mystage + lane;                                                                        \
+      float rjx = 0.f, rjy = 0.f, rjz = 0.f;                                                                     \
+      const bool full = warp_all_valid && ((c << 5) + 32 <= nj);                                                 \
+      const unsigned nxt_lane = (lane + 1) & 31;                                                                 \
+      if (full) {                                                                                                \
+        _Pragma("unroll UNROLLK")                                                                                \
+        for (int k = 0; k < 32; ++k) {                                                                           \
+          const uint4 uj = sp_l[k];                                                                              \
+          const unsigned jg = (unsigned)(j0 + (c << 5) + ((lane + k) & 31)); /* only live when RU */             \
+          _Pragma("unroll")                                                                                      \
+          for (int q = 0; q < NPAIR; ++q)                                                                        \
+            pair_sym<V, PERIODIC, false, RU>(uj, pi[q], acc[q], false, false, rjx, rjy, rjz, p, jg, R);          \
+          rjx = __shfl_sync(0xffffffffu, rjx, nxt_lane);                                                         \
+          rjy = __shfl_sync(0xffffffffu, rjy, nxt_lane);                                                         \
+          rjz = __shfl_sync(0xffffffffu, rjz, nxt_lane);                                                         \
+        }                                                                                                        \
+      } else {                                                                                                   \
+        for (int k = 0; k < 32; ++k) {                                                                           \
+          const uint4 uj = sp_l[k];                                                                              \
+          const int hl = (lane + k) & 31; /* home lane of the j I work on now */                                 \
+          const bool jdead = ((c << 5) + hl) >= nj;                                                              \
+          const unsigned jg = (unsigned)(j0 + min((c << 5) + hl, nj - 1));                                       \
+          _Pragma("unroll")                                                                                      \
+          for (int q = 0; q < NPAIR; ++q)                                                                        \
+            pair_sym<V, PERIODIC, true, RU>(uj, pi[q], acc[q], jdead || !pi[q].v_lo, jdead || !pi[q].v_hi, rjx,  \
+                                            rjy, rjz, p, jg, R);                                                 \
+          rjx = __shfl_sync(0xffffffffu, rjx, nxt_lane);                                                         \
+          rjy = __shfl_sync(0xffffffffu, rjy, nxt_lane);                                                         \
+          rjz = __shfl_sync(0xffffffffu, rjz, nxt_lane);                                                         \
+        }                                                                                                        \
+      }                                                                                                          \
+      myslice[jl] = make_float4(rjx, rjy, rjz, 0.f); /* the accumulators are home again; jl < BJ always */       \
+    }                                                                                                            \
+  }
+
 template <typename V, bool PERIODIC, bool RDF, int THREADS, int MINB, int NPAIR, int UNROLLK = 4>
 __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp) {
   constexpr int IPT = 2 * NPAIR;
@@ -266,7 +323,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
   float4* myslice = slices + (size_t)warp * BJ;
   uint4* mystage = stage + warp * 64;
   uint4 my_lo = make_uint4(0u, 0u, 0u, 0u), my_hi = my_lo;   // bounding box of my own block (RDF pruning)
-  if (RDF && p.bbox != nullptr) { my_lo = p.bbox[2 * gI]; my_hi = p.bbox[2 * gI + 1]; }
+  if (RDF && sp.bbox != nullptr) { my_lo = sp.bbox[2 * gI]; my_hi = sp.bbox[2 * gI + 1]; }
 
   while (cur < ue) {
     const int nxt = next_nonempty(cur + 1);
@@ -298,63 +355,17 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
     } else {
       // ---- partner block: each unordered pair once, reaction accumulators travel with the rotating j ----
       wgt = 2.f;
-      auto partner_unit = [&](auto rdf_tag) {
-        constexpr bool RU = decltype(rdf_tag)::value;   // build the RDF for this unit?
-        const int nchunk = (nj + 31) >> 5;
-        for (int c = 0; c < nchunk; ++c) {
-          const int jl = (c << 5) + lane;
-          // stage the chunk twice back to back: step k reads entry lane + k, no wrap arithmetic
-          const uint4 rec = tu[min(jl, nj - 1)];
-          __syncwarp();
-          mystage[lane] = rec;
-          mystage[lane + 32] = rec;
-          __syncwarp();
-          const uint4* sp_l = mystage + lane;
-          float rjx = 0.f, rjy = 0.f, rjz = 0.f;
-          const bool full = warp_all_valid && ((c << 5) + 32 <= nj);
-          const unsigned nxt_lane = (lane + 1) & 31;
-          if (full) {
-#pragma unroll UNROLLK
-            for (int k = 0; k < 32; ++k) {
-              const uint4 uj = sp_l[k];
-              const unsigned jg = (unsigned)(j0 + (c << 5) + ((lane + k) & 31));   // only live when RU
-#pragma unroll
-              for (int q = 0; q < NPAIR; ++q)
-                pair_sym<V, PERIODIC, false, RU>(uj, pi[q], acc[q], false, false, rjx, rjy, rjz, p, jg, R);
-              rjx = __shfl_sync(0xffffffffu, rjx, nxt_lane);
-              rjy = __shfl_sync(0xffffffffu, rjy, nxt_lane);
-              rjz = __shfl_sync(0xffffffffu, rjz, nxt_lane);
-            }
-          } else {
-            for (int k = 0; k < 32; ++k) {
-              const uint4 uj = sp_l[k];
-              const int hl = (lane + k) & 31;               // home lane of the j I work on now
-              const bool jdead = ((c << 5) + hl) >= nj;
-              const unsigned jg = (unsigned)(j0 + min((c << 5) + hl, nj - 1));
-#pragma unroll
-              for (int q = 0; q < NPAIR; ++q)
-                pair_sym<V, PERIODIC, true, RU>(uj, pi[q], acc[q], jdead || !pi[q].v_lo, jdead || !pi[q].v_hi, rjx,
-                                                rjy, rjz, p, jg, R);
-              rjx = __shfl_sync(0xffffffffu, rjx, nxt_lane);
-              rjy = __shfl_sync(0xffffffffu, rjy, nxt_lane);
-              rjz = __shfl_sync(0xffffffffu, rjz, nxt_lane);
-            }
-          }
-          myslice[jl] = make_float4(rjx, rjy, rjz, 0.f);  // the accumulators are home again; jl < BJ always
-        }
-      };
       if (RDF) {
         // bounding boxes of the two blocks farther apart than the histogram range: no pair of this unit can
-        // count, run the plain loop (warp-uniform: every thread of the CTA sees the same two boxes)
+        // count, run the plain loop (uniform: every thread of the CTA sees the same two boxes)
         bool near = true;
-        if (p.bbox != nullptr) {
+        if (sp.bbox != nullptr) {
           const int J = j0 / B;
-          near = boxes_in_range<PERIODIC>(my_lo, my_hi, p.bbox[2 * J], p.bbox[2 * J + 1], p);
+          near = boxes_in_range<PERIODIC>(my_lo, my_hi, sp.bbox[2 * J], sp.bbox[2 * J + 1], p.L, sp.bbox_cut2);
         }
-        if (near) partner_unit(std::true_type());
-        else partner_unit(std::false_type());
+        if (near) { LJMD_SYM_PARTNER_CHUNKS(true) } else { LJMD_SYM_PARTNER_CHUNKS(false) }
       } else {
-        partner_unit(std::false_type());
+        LJMD_SYM_PARTNER_CHUNKS(false)
       }
     }
     // fold the unit's tile-level accumulators into the run-level ones (two-level float summation);
@@ -390,6 +401,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
 
   force_epilogue<V, PERIODIC, RDF, THREADS, NPAIR>(p, ibase, pi, fxrun, fyrun, fzrun, s6run, wrun, red, hist, R);
 }
+#undef LJMD_SYM_PARTNER_CHUNKS
 
 inline size_t force_sym_smem_bytes(bool rdf, int bj, int threads) {
   return (size_t)2 * bj * 16 + (size_t)(threads / 32) * (bj + 64) * 16 + 16 + 8 * (threads / 32) +

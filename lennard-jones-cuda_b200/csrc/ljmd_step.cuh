@@ -301,6 +301,7 @@ __global__ void __launch_bounds__(kStepThreads) k_gather(const StepParams p, int
   double pe = 0., q = 0.;
   if (il < p.nloc) {
     float4 f = p.fpart[il];
+#pragma unroll 8   // rows are independent loads: keep several in flight (up to ~130 rows with fine splits)
     for (int s = 1; s < p.nsplit; ++s) {
       const float4 g = p.fpart[(size_t)s * p.ilocal_cap + il];
       f.x += g.x; f.y += g.y; f.z += g.z; f.w += g.w;

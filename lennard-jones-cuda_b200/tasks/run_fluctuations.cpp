@@ -6,6 +6,7 @@
 // device-resident: 1000 steps per ljmd_step call with the RDF histogram accumulated on the device and the
 // per-step observables (five occupancy families, the alpha = 1/2 slab count, U, T, P, mean velocity) recorded
 // by the observation trace — no h_Pos / h_Vel download per step (the reference's loop :120-135 reads both).
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -28,6 +29,13 @@ static void must(int rc, const char* what) {
   }
 }
 
+// LJMD_TASK_TIMING=1: wall-clock stamps of the phases on stderr
+static void stamp(const char* what) {
+  static const bool on = std::getenv("LJMD_TASK_TIMING") != NULL;
+  static const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  if (on) std::fprintf(stderr, "[%8.3f s] %s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), what);
+}
+
 // how many `t += dt` it takes until the loop condition of the reference stops holding
 static long steps_until(double& t, double tend, double dt, long limit) {
   long n = 0;
@@ -47,6 +55,7 @@ int main(int argc, char* argv[]) {
     return 1;
   }
   par.print();
+  stamp("start");
 
   const int N = (int)par.integer("N");
   const double dt = par["dt*"], teq = par["teq"], tfin = par["tfin"], dalpha = par["subvolume_spacing"];
@@ -61,6 +70,7 @@ int main(int argc, char* argv[]) {
   MDSystem syst(config);
   syst.Reinitialize(config);
   if (!config.canonical) syst.RenormalizeVelocitiesToEnergy(par["u*"]);
+  stamp("system constructed");
 
   // from here on everything runs on the library handle; the class instance only provided the initial state
   ljmd_system* h = syst.handle();
@@ -71,6 +81,7 @@ int main(int argc, char* argv[]) {
     const long neq = steps_until(t, teq, dt, 2000000000L);   // :84-87
     must(ljmd_step(h, dt, (int)neq, 0), "ljmd_step (equilibration)");
   }
+  stamp("equilibrated");
 
   const double vfactor = 3.0;   // MomentumFlucsAverage::Vfactor (:436)
   const double vcut_max = std::sqrt(config.T0) * vfactor;
@@ -117,6 +128,7 @@ int main(int argc, char* argv[]) {
     must(ljmd_step(h, dt, (int)chunk, 1), "ljmd_step");
     int got = 0;
     must(ljmd_trace_read(h, report_every, &got, scal.data(), counts.data(), mvel.data()), "ljmd_trace_read");
+    stamp("batch stepped and trace read");
     for (int k = 0; k < got; ++k) {
       const long long* r = counts.data() + (std::size_t)k * row;
       occX.add_step(r);
@@ -161,6 +173,7 @@ int main(int argc, char* argv[]) {
     occZ.write_coordinate_file(par.output_prefix + ".flucsZ.dat");
     occCube.write_coordinate_file(par.output_prefix + ".flucsCube.dat");
     occVz.write_momentum_file(par.output_prefix + ".flucsVz.dat", N);
+    stamp("report written");
   }
   must(ljmd_trace_end(h), "ljmd_trace_end");
   return 0;

@@ -83,12 +83,15 @@ def test_launch_plan_tiles_the_problem(pkg, N, world):
         assert p["i_begin"] % p["i_tile"] == 0          # shards are whole blocks
         assert p["i_tiles"] * p["i_tile"] >= n_loc > (p["i_tiles"] - 1) * p["i_tile"]
         assert 1 <= p["j_splits"] <= max(1, N // 64)
-        assert p["newton3"] == (N >= 16 * 512 - 511)
+        assert p["newton3"] == (N >= 8 * 512 - 511)
         assert p["force_ctas"] == p["i_tiles"] * p["j_splits"]
-        if N >= 16384:   # big enough to fill the machine: the last wave must be reasonably full
-            slots = 148 * (3 if p["newton3"] else 4)     # resident CTAs/SM of the kernel in use
-            waves = math.ceil(p["force_ctas"] / slots)
-            assert p["force_ctas"] / (waves * slots) > (0.93 if N >= 262144 else 0.8)
+        if p["newton3"]:
+            # many small CTAs (measured optimum, profiles/r01_tune_force_sym_split_scan.log): at least ~4.5 per
+            # resident slot so the hardware scheduler can balance the SMs, at most ~60 so the partial-force rows
+            # k_gather reads back stay a small fraction of the step
+            slots = 148 * 3
+            assert 4.4 * slots <= p["force_ctas"] <= 61 * slots
+            assert p["j_splits"] * n_loc * 16 <= 1.5e9
     assert covered == N
 
 

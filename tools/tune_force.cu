@@ -150,7 +150,6 @@ static void run_variant(const Problem& pb, const char* tag, int reps, int tile_j
   fp.fscale = PERIODIC ? (float)(4.0 * pb.L / 4294967296.0) : 4.f;
   fp.cut_fast = (float)(PERIODIC ? 25.6 * 1.001 * k2 * k2 : 25.6 * 1.001);
   fp.L = pb.L; fp.thr1 = (float)(0.5 * pb.L); fp.thr2 = (float)(1.5 * pb.L); fp.dr2 = 0.1f; fp.inv_dr2 = 10.f;
-  fp.bbox = nullptr; fp.bbox_cut2 = 25.7f;
   dim3 grid(n_it, S);
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
@@ -195,7 +194,7 @@ static void run_variant(const Problem& pb, const char* tag, int reps, int tile_j
 
 template <typename V, bool PERIODIC, bool RDF, int THREADS, int MINB, int NPAIR, int UNROLLK = 4>
 static void run_sym(const Problem& pb, const char* tag, int reps, int bj, std::vector<float4>* keep,
-                    bool prune = true) {
+                    bool prune = true, int force_S = 0) {
   auto kern = k_force_sym<V, PERIODIC, RDF, THREADS, MINB, NPAIR, UNROLLK>;
   const size_t smem = force_sym_smem_bytes(RDF, bj, THREADS);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -215,6 +214,7 @@ static void run_sym(const Problem& pb, const char* tag, int reps, int bj, std::v
     const double cost = (double)waves * (ceil((double)units / s) + 0.5);
     if (cost < bc * 0.999) { bc = cost; S = s; }
   }
+  if (force_S > 0) S = force_S;
   SymParams sp;
   memset(&sp, 0, sizeof(sp));
   ForceParams& fp = sp.f;
@@ -226,12 +226,12 @@ static void run_sym(const Problem& pb, const char* tag, int reps, int bj, std::v
   fp.fscale = PERIODIC ? (float)(4.0 * pb.L / 4294967296.0) : 4.f;
   fp.cut_fast = (float)(PERIODIC ? 25.6 * 1.001 * k2 * k2 : 25.6 * 1.001);
   fp.L = pb.L; fp.thr1 = (float)(0.5 * pb.L); fp.thr2 = (float)(1.5 * pb.L); fp.dr2 = 0.1f; fp.inv_dr2 = 10.f;
-  fp.bbox = nullptr; fp.bbox_cut2 = 25.7f;
+  sp.bbox = nullptr; sp.bbox_cut2 = 25.7f;
   if (RDF && prune) {   // block bounding boxes for the RDF pruning test
     if (PERIODIC) k_bbox<true, THREADS * 2 * NPAIR><<<n, 128>>>(fp.jrec, pb.N, pb.bbox);
     else k_bbox<false, THREADS * 2 * NPAIR><<<n, 128>>>(fp.jrec, pb.N, pb.bbox);
     CK(cudaGetLastError());
-    fp.bbox = pb.bbox;
+    sp.bbox = pb.bbox;
   }
   const int hmax = std::max(1, sym_max_partner_count(n));
   sp.rpart = pb.rpart; sp.ncols = hmax * B; sp.nblk = n; sp.bj = bj;
@@ -341,11 +341,38 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(pb.posf, hp.data(), (size_t)N * 16, cudaMemcpyHostToDevice));
 
   std::vector<float4> keepP, keepO;
+  if (argc > 3 && !strcmp(argv[3], "shipped")) {   // only the shipped Newton-3 variants (A/B of builds)
+    run_sym<P2, true, false, 128, 3, 2, 4>(pb, "periodic sym t128 b3 np2 uk4 bj256", reps, 256, &keepP);
+    run_sym<P2, false, false, 128, 3, 2, 4>(pb, "open sym t128 b3 np2 uk4 bj256", reps, 256, &keepO);
+    return 0;
+  }
+  if (argc > 3 && !strcmp(argv[3], "scan")) {
+    // every distinct "units per CTA" for three unit sizes: the data the launch planner is calibrated on
+    run_variant<P2, true, false, 128, 4, 2, 4>(pb, "periodic ordered P2 t128 b4 np2 u4", reps, 1024, &keepP);
+    const int n = (N + 511) / 512;
+    for (int bj = 256; bj >= 64; bj >>= 1) {
+      const int units = (sym_max_partner_count(n) + 1) * (512 / bj);
+      int lastS = -1;
+      for (int per = units; per >= 1; --per) {
+        const int S = (units + per - 1) / per;
+        if (S == lastS || (size_t)S > smax || (long long)n * S > 24LL * sms * 3) continue;
+        if (per > 4 && per % 2 && S > 4) continue;   // thin out the long tail of large CTAs
+        lastS = S;
+        char tag[96];
+        snprintf(tag, sizeof(tag), "scan bj%d S%d per_cta%d ctas%d", bj, S, per, n * S);
+        run_sym<P2, true, false, 128, 3, 2, 4>(pb, tag, reps, bj, &keepP, true, S);
+      }
+    }
+    return 0;
+  }
   //                 V   PER    RDF   THR MINB NPAIR UNROLL
   run_variant<P2, true, false, 128, 4, 2, 4>(pb, "periodic ordered P2 t128 b4 np2 u4", reps, 1024, &keepP);
   run_variant<S2, true, false, 128, 4, 2, 4>(pb, "periodic ordered S2(scalar) t128 b4 np2 u4", reps, 1024, &keepP);
   run_sym<P2, true, false, 128, 3, 2, 4>(pb, "periodic sym t128 b3 np2 uk4 bj256", reps, 256, &keepP);
   run_sym<P2, true, false, 128, 4, 2, 4>(pb, "periodic sym t128 b4 np2 uk4 bj256", reps, 256, &keepP);
+  run_sym<P2, true, false, 128, 3, 2, 4>(pb, "periodic sym t128 b3 np2 uk4 bj128", reps, 128, &keepP);
+  run_sym<P2, true, false, 128, 3, 2, 4>(pb, "periodic sym t128 b3 np2 uk4 bj64", reps, 64, &keepP);
+  run_sym<P2, true, false, 128, 3, 2, 4>(pb, "periodic sym t128 b3 np2 uk4 bj32", reps, 32, &keepP);
   run_variant<P2, true, true, 128, 3, 2, 4>(pb, "periodic+RDF ordered t128 b3 np2 u4", reps, 1024, &keepP);
   run_sym<P2, true, true, 128, 3, 2, 4>(pb, "periodic+RDF sym t128 b3 np2 uk4 bj256", reps, 256, &keepP);
   run_sym<P2, true, true, 128, 3, 2, 4>(pb, "periodic+RDF sym, no box pruning", reps, 256, &keepP, false);
