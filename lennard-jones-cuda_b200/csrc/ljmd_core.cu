@@ -77,6 +77,12 @@ struct ljmd_system {
   float4* rsum = nullptr;    // [npad] rank-local column sums of the reaction rows (world > 1)
   float4* rshard = nullptr;  // [cnt]  reaction totals of this rank's particles after the reduce-scatter
   uint4* bbox = nullptr;     // [nblk][2] block bounding boxes (RDF pruning in the Newton-3 kernel)
+  // CUDA graph of `graph_period` steady-state steps of a batched ljmd_step (single GPU, no instrumentation)
+  cudaGraphExec_t graph_exec = nullptr;
+  int graph_period = 0, graph_rdf_every = -1, graph_canonical = -1, graph_bc = -1;
+  double graph_dt = 0., graph_T0 = 0.;
+  long long graph_launches = 0;   // kernel launches / RDF accumulations one replay stands for
+  int graph_rdf_nacc = 0;
   // observation trace (ljmd_trace_*)
   int trace_on = 0, trace_cap = 0, trace_n = 0, trace_row = 0, trace_ncounters = 0;
   int trace_nbins[kMaxTraceCounters] = {0};
@@ -173,12 +179,12 @@ struct Plan {
 // faster the MORE and SMALLER its CTAs are — down to one or two units per CTA — because the hardware block
 // scheduler then balances the SMs and the tail in which an SM runs a single CTA (one warp per scheduler, well
 // under half the issue rate) shrinks to one unit.  Few large CTAs sized to "whole waves" lost 5 % (65 536),
-// 16 % (32 768) and 15 % (16 384) against that.  So: aim for ~19 CTAs per slot, never fewer than ~4.5 per slot
+// 16 % (32 768) and 15 % (16 384) against that.  So: aim for ~10 CTAs per slot, never fewer than ~4.5 per slot
 // (finer units instead: bj 128 or 64), and stop there — every split adds one row of partial forces that
-// k_gather has to read back.
+// k_gather has to read back (at 65 536: 65 splits 1.774 ms + 76 us of k_gather, 33 splits 1.788 ms + ~40 us).
 static void choose_sym_split(int n_itiles, int nblk, int num_sms, int nloc, int* out_s, int* out_bj) {
   const long long slots = (long long)num_sms * kSymMinBlocks;
-  const long long want_lo = (9 * slots) / 2, want_hi = 19 * slots;
+  const long long want_lo = (9 * slots) / 2, want_hi = 10 * slots;
   const int partners = sym_max_partner_count(nblk) + 1;
   int bj = kSymBJ;
   while (bj > 64 && (long long)n_itiles * partners * (kITile / bj) < want_lo) bj >>= 1;
@@ -529,6 +535,7 @@ static int destroy_impl(ljmd_system* s) {
   cudaFree(s->counter); cudaFree(s->velh); cudaFree(s->sc); cudaFree(s->rdf_cur); cudaFree(s->rdf_acc);
   cudaFree(s->flush_buf);
   cudaFree(s->rpart); cudaFree(s->rshard); cudaFree(s->bbox);
+  if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
   trace_free(s);
   cudaFreeHost(s->h_sc); cudaFreeHost(s->h_rdf);
   for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
@@ -870,7 +877,52 @@ extern "C" int ljmd_step(ljmd_system* s, double dt, int nsteps, int rdf_every) {
   StepParams p = make_step_params(s, dt);
   if (s->timing) CU(cudaEventRecord(s->ev_begin, s->stream));
   bool drifted = false;
+  // Steady-state steps of a batch (previous step fused this one's drift, this one fuses the next) are the same
+  // launches with the same arguments, RDF cadence included: capture `period` of them once in a CUDA graph and
+  // replay it.  For small systems the step is launch-bound (N = 400: three ~5 us kernels), and a graph launch
+  // replaces 3-6 kernel launches per step by one submission per period.  Off with instrumentation (event
+  // timing, L2 flush, trace), on more than one GPU, and with LJMD_GRAPH=0.
+  const int period = rdf_every > 0 ? rdf_every : 16;
+  const char* genv = getenv("LJMD_GRAPH");
+  const bool use_graph = s->world == 1 && !s->timing && !s->trace_on && s->flush_bytes == 0 && period <= 64 &&
+                         nsteps - 2 >= 2 * period && !(genv && genv[0] == '0');
   for (int k = 0; k < nsteps; ++k) {
+    if (use_graph && k == 1) {
+      const bool fresh = s->graph_exec && s->graph_period == period && s->graph_rdf_every == rdf_every &&
+                         s->graph_canonical == s->canonical && s->graph_bc == s->bc && s->graph_dt == dt &&
+                         s->graph_T0 == s->T0;
+      if (!fresh) {
+        if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
+        const long long l0 = s->launches;
+        const int r0 = s->rdf_nacc;
+        CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = LJMD_OK;
+        for (int j = 0; j < period && rc == LJMD_OK; ++j) {
+          const int kk = 1 + j;
+          rc = one_step(s, p, rdf_every > 0 && ((kk + 1) % rdf_every == 0), true, true);
+        }
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(s->stream, &graph);
+        s->graph_launches = s->launches - l0;
+        s->graph_rdf_nacc = s->rdf_nacc - r0;
+        s->launches = l0;      // nothing ran yet
+        s->rdf_nacc = r0;
+        if (rc != LJMD_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) return set_err(LJMD_ERR_CUDA, "graph capture: %s", cudaGetErrorString(ce));
+        const cudaError_t ie = cudaGraphInstantiate(&s->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { s->graph_exec = nullptr; return set_err(LJMD_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(ie)); }
+        s->graph_period = period; s->graph_rdf_every = rdf_every; s->graph_canonical = s->canonical;
+        s->graph_bc = s->bc; s->graph_dt = dt; s->graph_T0 = s->T0;
+      }
+      const int reps = (nsteps - 2) / period;
+      for (int r = 0; r < reps; ++r) {
+        CU(cudaGraphLaunch(s->graph_exec, s->stream));
+        s->launches += s->graph_launches;
+        s->rdf_nacc += s->graph_rdf_nacc;
+      }
+      k += reps * period;    // the steps left (at least the last one) run below, with the same cadence
+    }
     const bool rdf = rdf_every > 0 && ((k + 1) % rdf_every == 0);
     if (s->flush_bytes) CU(cudaMemsetAsync(s->flush_buf, k & 0xff, s->flush_bytes, s->stream));
     cudaEvent_t e0 = nullptr, e1 = nullptr;

@@ -284,6 +284,29 @@ def test_batched_steps_equal_single_steps(pkg, gpu_lib, kernel, name):
         assert np.array_equal(a.rdf_counts(), b.rdf_counts())
 
 
+@pytest.mark.parametrize("name,rdf_every", [("c1_gas_tvn_periodic", 0), ("liquid_evn_periodic", 7),
+                                            ("ragged_tvn_hardwall", 3)])
+def test_graph_replay_equals_plain_launches(pkg, gpu_lib, monkeypatch, name, rdf_every):
+    """Long batches replay a captured CUDA graph of their steady-state steps; the kernels and their arguments
+    are the ones the plain path launches, so state, scalars, RDF accumulation and launch count are identical."""
+    g = load_golden(name)
+    nsteps = 75
+    outs = []
+    for graph in ("1", "0"):
+        monkeypatch.setenv("LJMD_GRAPH", graph)
+        with make_system(pkg, g) as s:
+            s.set_state(g["pos0"], g["vel0"])
+            l0 = s.launch_count()
+            s.step(g["dt"], nsteps, rdf_every=rdf_every)
+            s.step(g["dt"], nsteps, rdf_every=rdf_every)       # second batch: the cached graph is reused
+            outs.append((s.get_state(), s.scalars(), s.rdf_accum(), s.rdf_counts(), s.launch_count() - l0))
+    (sa, sca, (ra, na), ca, la), (sb, scb, (rb, nb), cb, lb) = outs
+    assert all(np.array_equal(x, y) for x, y in zip(sa, sb))
+    assert sca == scb and sca["av_iters"] == 2 * nsteps
+    assert na == nb == (2 * (nsteps // rdf_every) if rdf_every else 0) and np.array_equal(ra, rb)
+    assert np.array_equal(ca, cb) and la == lb
+
+
 def test_runs_are_deterministic(pkg, gpu_lib, kernel):
     g = load_golden("mixed_tvn_periodic")
     outs = []
