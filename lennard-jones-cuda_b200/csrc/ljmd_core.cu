@@ -222,6 +222,12 @@ static Plan make_plan(int N, int rank, int world, int num_sms, bool force_ordere
   pl.bj = kSymBJ;
   if (pl.use_sym) {
     choose_sym_split(pl.n_itiles, pl.nblk, num_sms, pl.cnt, &pl.nsplit, &pl.bj);
+  } else if (N <= 4096) {
+    // small systems are latency-bound: a CTA's fixed cost is worth ~16-32 j-iterations, not the 128 of the wave
+    // model, and the kernel keeps getting faster down to 16 (N <= 1 536) / 32 j-records per CTA
+    // (tools/tune_force N reps scan_ordered: N = 400 11.3 -> 6.8 us, N = 1 024 10.8 -> 7.2 us, N = 2 048 11.2 -> 10.0 us)
+    const int per = N <= 1536 ? 16 : 32;
+    pl.nsplit = std::max(1, (N + per - 1) / per);
   } else {
     pl.nsplit = choose_split(pl.n_itiles, N, N / 64, num_sms, kMinBlocks, pl.cnt);
   }

@@ -102,4 +102,4 @@ def test_semigce_driver_starts_and_reports(gpu_lib):
         mean = float(f[1])
         assert abs(mean - frac * 512) < 0.2 * frac * 512 + 6.0
     mid = lines[9]                       # alpha = 0.5
-    assert 0.05 < float(mid[7]) < 3.0    # omega / (1 - alpha) after only 10 events
+    assert 0.05 < float(mid[7]) < 12.0   # omega / (1 - alpha) after only 10 events, at the LJ critical point

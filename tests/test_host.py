@@ -82,7 +82,7 @@ def test_launch_plan_tiles_the_problem(pkg, N, world):
             continue
         assert p["i_begin"] % p["i_tile"] == 0          # shards are whole blocks
         assert p["i_tiles"] * p["i_tile"] >= n_loc > (p["i_tiles"] - 1) * p["i_tile"]
-        assert 1 <= p["j_splits"] <= max(1, N // 64)
+        assert 1 <= p["j_splits"] <= max(1, N // 8)
         assert p["newton3"] == (N >= 8 * 512 - 511)
         assert p["force_ctas"] == p["i_tiles"] * p["j_splits"]
         if p["newton3"]:

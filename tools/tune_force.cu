@@ -128,6 +128,7 @@ static int pick_split(int n_it, int N, int sms, int minb) {
   return best;
 }
 
+static int g_force_split = 0;   // scan_ordered: overrides the split of run_variant
 template <typename V, bool PERIODIC, bool RDF, int THREADS, int MINB, int NPAIR, int UNROLL>
 static void run_variant(const Problem& pb, const char* tag, int reps, int tile_j, std::vector<float4>* keep) {
   auto kern = k_force<V, PERIODIC, RDF, THREADS, MINB, NPAIR, UNROLL>;
@@ -139,7 +140,7 @@ static void run_variant(const Problem& pb, const char* tag, int reps, int tile_j
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
   const int itile = THREADS * 2 * NPAIR;
   const int n_it = (pb.N + itile - 1) / itile;
-  const int S = pick_split(n_it, pb.N, pb.sms, occ > 0 ? occ : MINB);
+  const int S = g_force_split > 0 ? g_force_split : pick_split(n_it, pb.N, pb.sms, occ > 0 ? occ : MINB);
   ForceParams fp;
   memset(&fp, 0, sizeof(fp));
   fp.jrec = PERIODIC ? pb.upos : reinterpret_cast<const uint4*>(pb.posf);
@@ -328,7 +329,7 @@ int main(int argc, char** argv) {
   pb.N = N; pb.L = L; pb.sms = sms;
   CK(cudaMalloc(&pb.upos, (size_t)N * 16));
   CK(cudaMalloc(&pb.posf, (size_t)N * 16));
-  const size_t smax = std::min<size_t>(8 * sms, std::max(1, N / 64));
+  const size_t smax = std::min<size_t>(8 * sms, std::max(1, N / 8));
   CK(cudaMalloc(&pb.fpart, smax * N * 16));
   CK(cudaMalloc(&pb.blockW, smax * (N / 64 + 1) * sizeof(double)));
   CK(cudaMalloc(&pb.rdf, 256 * 8));
@@ -344,6 +345,16 @@ int main(int argc, char** argv) {
   if (argc > 3 && !strcmp(argv[3], "shipped")) {   // only the shipped Newton-3 variants (A/B of builds)
     run_sym<P2, true, false, 128, 3, 2, 4>(pb, "periodic sym t128 b3 np2 uk4 bj256", reps, 256, &keepP);
     run_sym<P2, false, false, 128, 3, 2, 4>(pb, "open sym t128 b3 np2 uk4 bj256", reps, 256, &keepO);
+    return 0;
+  }
+  if (argc > 3 && !strcmp(argv[3], "scan_ordered")) {   // ordered kernel, small N: how fine should the j-split be?
+    for (int per = 256; per >= 8; per >>= 1) {
+      g_force_split = (N + per - 1) / per;
+      if ((size_t)g_force_split > smax) continue;
+      char tag[96];
+      snprintf(tag, sizeof(tag), "scan_ordered j_per_cta%d S%d", per, g_force_split);
+      run_variant<P2, true, false, 128, 4, 2, 4>(pb, tag, reps, 1024, &keepP);
+    }
     return 0;
   }
   if (argc > 3 && !strcmp(argv[3], "scan")) {
