@@ -73,6 +73,7 @@ struct ljmd_system {
   int use_sym = 0;  // Newton-3 kernel (k_force_sym) instead of the ordered one (k_force)
   int hmax = 0;     // partner offsets per i-tile (rows of the partner window)
   int sym_bj = 256; // j-records per work unit of the Newton-3 kernel
+  int gather_shift = 0;  // k_gather: 2^shift lanes per particle
   float4* rpart = nullptr;   // [n_itiles][hmax*kITile] reaction rows
   float4* rsum = nullptr;    // [npad] rank-local column sums of the reaction rows (world > 1)
   float4* rshard = nullptr;  // [cnt]  reaction totals of this rank's particles after the reduce-scatter
@@ -222,12 +223,12 @@ static Plan make_plan(int N, int rank, int world, int num_sms, bool force_ordere
   pl.bj = kSymBJ;
   if (pl.use_sym) {
     choose_sym_split(pl.n_itiles, pl.nblk, num_sms, pl.cnt, &pl.nsplit, &pl.bj);
-  } else if (N <= 4096) {
+  } else if (N <= 2048) {
     // small systems are latency-bound: a CTA's fixed cost is worth ~16-32 j-iterations, not the 128 of the wave
-    // model, and the kernel keeps getting faster down to 16 (N <= 1 536) / 32 j-records per CTA
-    // (tools/tune_force N reps scan_ordered: N = 400 11.3 -> 6.8 us, N = 1 024 10.8 -> 7.2 us, N = 2 048 11.2 -> 10.0 us)
-    const int per = N <= 1536 ? 16 : 32;
-    pl.nsplit = std::max(1, (N + per - 1) / per);
+    // model, and the kernel keeps getting faster down to 16 j-records per CTA (tools/tune_force N reps
+    // scan_ordered: N = 400 11.3 -> 6.8 us, N = 1 024 10.8 -> 7.2 us) — but every split is one more row for
+    // k_gather (~0.08 us each at this size: 94 splits at N = 1 500 cost more than they gained), hence the cap
+    pl.nsplit = std::max(1, std::min((N + 15) / 16, 32));
   } else {
     pl.nsplit = choose_split(pl.n_itiles, N, N / 64, num_sms, kMinBlocks, pl.cnt);
   }
@@ -239,6 +240,7 @@ static StepParams make_step_params(ljmd_system* s, double dt) {
   memset(&p, 0, sizeof(p));
   p.N = s->N; p.nloc = s->nloc; p.i_begin = s->i_begin; p.bc = s->bc;
   p.nsplit = s->nsplit; p.ilocal_cap = s->cnt; p.nforce_blocks = s->n_itiles * s->nsplit; p.world = s->world;
+  p.gather_shift = s->gather_shift;
   p.dt = dt; p.dt2 = dt * dt; p.L = s->L; p.rho = s->rho; p.T0 = s->T0;
   p.fix_scale = 4294967296.0 / s->L;
   p.pos = s->pos; p.posA = s->posA; p.upos = s->upos; p.vel = s->vel; p.force = s->force; p.tforce = s->tforce;
@@ -250,6 +252,10 @@ static StepParams make_step_params(ljmd_system* s, double dt) {
 }
 
 static int step_grid(const ljmd_system* s) { return (s->nloc + kStepThreads - 1) / kStepThreads; }
+// k_gather runs 2^gather_shift lanes per particle
+static int gather_grid(const ljmd_system* s) {
+  return (int)((((long long)s->nloc << s->gather_shift) + kStepThreads - 1) / kStepThreads);
+}
 
 static void trace_free(ljmd_system* s);
 static int trace_record(ljmd_system* s);
@@ -392,10 +398,11 @@ static int evaluate(ljmd_system* s, const StepParams& p, int mode, bool rdf, int
     CU(cudaEventCreate(&g1));
     CU(cudaEventRecord(g0, s->stream));
   }
-  if (mode == GATHER_EVAL) k_gather<GATHER_EVAL><<<g, kStepThreads, 0, s->stream>>>(p, fin, accumulate);
-  else if (mode == GATHER_EVN && fuse_next) k_gather<GATHER_EVN, true><<<g, kStepThreads, 0, s->stream>>>(p, fin, accumulate);
-  else if (mode == GATHER_EVN) k_gather<GATHER_EVN><<<g, kStepThreads, 0, s->stream>>>(p, fin, accumulate);
-  else k_gather<GATHER_TVN><<<g, kStepThreads, 0, s->stream>>>(p, fin, accumulate);
+  const int gg = gather_grid(s);
+  if (mode == GATHER_EVAL) k_gather<GATHER_EVAL><<<gg, kStepThreads, 0, s->stream>>>(p, fin, accumulate);
+  else if (mode == GATHER_EVN && fuse_next) k_gather<GATHER_EVN, true><<<gg, kStepThreads, 0, s->stream>>>(p, fin, accumulate);
+  else if (mode == GATHER_EVN) k_gather<GATHER_EVN><<<gg, kStepThreads, 0, s->stream>>>(p, fin, accumulate);
+  else k_gather<GATHER_TVN><<<gg, kStepThreads, 0, s->stream>>>(p, fin, accumulate);
   CU(cudaGetLastError());
   s->launches += 1;
   if (s->timing) {
@@ -650,7 +657,13 @@ static int create_impl(ljmd_system** out, int N, double rho_or_negL, double T0, 
     if (world > 1) CUC(cudaMalloc(&s->rshard, (size_t)s->cnt * b16));
     CUC(cudaMalloc(&s->bbox, (size_t)s->nblk * 2 * sizeof(uint4)));
   }
-  CUC(cudaMalloc(&s->part, (size_t)2 * (step_grid(s) + 1) * sizeof(double)));
+  // lanes per particle in k_gather: enough threads to keep ~2 CTAs of 256 on every SM, never more lanes than
+  // half the rows they share
+  s->gather_shift = 0;
+  while (s->gather_shift < 3 && ((long long)s->nloc << s->gather_shift) < 2LL * kStepThreads * s->num_sms &&
+         (2 << s->gather_shift) * 2 <= s->nsplit + (s->use_sym ? s->hmax : 0))
+    s->gather_shift += 1;
+  CUC(cudaMalloc(&s->part, (size_t)2 * (gather_grid(s) + 1) * sizeof(double)));
   CUC(cudaMalloc(&s->counter, sizeof(unsigned int)));
   CUC(cudaMalloc(&s->velh, 65536 * sizeof(unsigned int)));
   CUC(cudaMalloc(&s->sc, sizeof(DevScalars)));

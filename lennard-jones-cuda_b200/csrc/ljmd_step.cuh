@@ -48,6 +48,7 @@ struct StepParams {
   int ilocal_cap;   // row stride of fpart
   int nforce_blocks;  // entries of blockW
   int world;        // number of ranks
+  int gather_shift; // k_gather: 2^gather_shift adjacent lanes share one particle's rows (0: one thread each)
   double dt, dt2;   // dt, dt*dt
   double L;         // box edge
   double rho;       // N / rho is the volume the reference divides by (MDSystem.cpp:350)
@@ -87,13 +88,13 @@ __host__ __device__ inline int partner_count(int g, int n) {
 // Sum of the reaction rows that hold contributions for global particle j (block J = j / 512): the i-tile of
 // global block gI = J - o (mod n) wrote its reaction on J at window slot o - 1 when o <= partner_count(gI).
 // Walks the partner offsets in ascending order (fixed order: deterministic), four loads in flight.
-__device__ __forceinline__ float4 reaction_sum(const StepParams& p, int j) {
+__device__ __forceinline__ float4 reaction_sum(const StepParams& p, int j, int first = 1, int stride = 1) {
   const int J = j / kBlockParticles, jj = j - J * kBlockParticles;
   const int n = p.nblk;
   const int omax = (n & 1) ? (n - 1) / 2 : n / 2;
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
-  for (int o = 1; o <= omax; ++o) {
+  for (int o = first; o <= omax; o += stride) {   // (first, stride): this lane's share when several lanes split a particle
     int gI = J - o;
     if (gI < 0) gI += n;
     const int t = gI - p.blk0;
@@ -297,30 +298,45 @@ __device__ __forceinline__ void fused_next_drift(const StepParams& p, int il, fl
 // FUSE (EVN only here; TVN fuses in k_finish_tvn): also perform the drift of the next step.
 template <int MODE, bool FUSE = false>
 __global__ void __launch_bounds__(kStepThreads) k_gather(const StepParams p, int finalize, int accumulate) {
-  const int il = blockIdx.x * kStepThreads + threadIdx.x;
+  // R = 2^gather_shift adjacent lanes share a particle: each sums every R-th row of partial forces (and of
+  // reaction rows), a butterfly over the R lanes adds the shares (every lane ends with the same bits), lane 0 of
+  // the group goes on.  Mid-size systems have too few particles to hide the latency of S = 30-130 dependent-
+  // address row loads with one thread each (N = 16 384: 21 us -> 8 us).
+  const int R = 1 << p.gather_shift;
+  const int gt = blockIdx.x * kStepThreads + threadIdx.x;
+  const int il = gt >> p.gather_shift, r = gt & (R - 1);
   double pe = 0., q = 0.;
+  float4 f = make_float4(0.f, 0.f, 0.f, 0.f), rr = f;
   if (il < p.nloc) {
-    float4 f = p.fpart[il];
 #pragma unroll 8   // rows are independent loads: keep several in flight (up to ~130 rows with fine splits)
-    for (int s = 1; s < p.nsplit; ++s) {
+    for (int s = r; s < p.nsplit; s += R) {
       const float4 g = p.fpart[(size_t)s * p.ilocal_cap + il];
       f.x += g.x; f.y += g.y; f.z += g.z; f.w += g.w;
     }
-    if (p.use_sym) {   // Newton-3 kernel: add the reaction of every pair this particle was the j of
-      float4 r;
-      if (p.world == 1) {
-        r = reaction_sum(p, p.i_begin + il);
-      } else if (p.fab.n > 0) {
-        // pull every rank's column sum for my particle straight from its window, fixed rank order
-        r = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int q = 0; q < p.fab.n; ++q) {
-          const float4 g = reinterpret_cast<const float4*>(p.fab.base[q] + p.fab.off_rsum)[p.i_begin + il];
-          r.x += g.x; r.y += g.y; r.z += g.z;
+    // Newton-3 kernel, one GPU: the reaction of every pair this particle was the j of
+    if (p.use_sym && p.world == 1) rr = reaction_sum(p, p.i_begin + il, 1 + r, R);
+  }
+  for (int o = 1; o < R; o <<= 1) {
+    f.x += __shfl_xor_sync(0xffffffffu, f.x, o); f.y += __shfl_xor_sync(0xffffffffu, f.y, o);
+    f.z += __shfl_xor_sync(0xffffffffu, f.z, o); f.w += __shfl_xor_sync(0xffffffffu, f.w, o);
+    rr.x += __shfl_xor_sync(0xffffffffu, rr.x, o); rr.y += __shfl_xor_sync(0xffffffffu, rr.y, o);
+    rr.z += __shfl_xor_sync(0xffffffffu, rr.z, o);
+  }
+  if (il < p.nloc && r == 0) {
+    if (p.use_sym) {
+      if (p.world > 1) {
+        if (p.fab.n > 0) {
+          // pull every rank's column sum for my particle straight from its window, fixed rank order
+          rr = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int q = 0; q < p.fab.n; ++q) {
+            const float4 g = reinterpret_cast<const float4*>(p.fab.base[q] + p.fab.off_rsum)[p.i_begin + il];
+            rr.x += g.x; rr.y += g.y; rr.z += g.z;
+          }
+        } else {
+          rr = p.rshard[il];
         }
-      } else {
-        r = p.rshard[il];
       }
-      f.x += r.x; f.y += r.y; f.z += r.z;
+      f.x += rr.x; f.y += rr.y; f.z += rr.z;
     }
     pe = (double)f.w;
     float4 v = p.vel[il];
