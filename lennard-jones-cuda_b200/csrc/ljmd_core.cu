@@ -74,6 +74,7 @@ struct ljmd_system {
   int hmax = 0;     // partner offsets per i-tile (rows of the partner window)
   int sym_bj = 256; // j-records per work unit of the Newton-3 kernel
   int gather_shift = 0;  // k_gather: 2^shift lanes per particle
+  int pdl = 0;           // launch the step chain with programmatic dependent launch (ordered kernel, one GPU)
   float4* rpart = nullptr;   // [n_itiles][hmax*kITile] reaction rows
   float4* rsum = nullptr;    // [npad] rank-local column sums of the reaction rows (world > 1)
   float4* rshard = nullptr;  // [cnt]  reaction totals of this rank's particles after the reduce-scatter
@@ -257,6 +258,21 @@ static int gather_grid(const ljmd_system* s) {
   return (int)((((long long)s->nloc << s->gather_shift) + kStepThreads - 1) / kStepThreads);
 }
 
+// Launch with programmatic stream serialization when `pdl` (the kernel calls pdl_trigger / pdl_wait first).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 static void trace_free(ljmd_system* s);
 static int trace_record(ljmd_system* s);
 
@@ -268,8 +284,7 @@ static cudaError_t launch_force_t(ljmd_system* s, const ForceParams& fp) {
   static_assert(2 * kTileJ * 16 + 16 + 64 + (kForceThreads / 32) * (kRdfBins * 4 + kRdfQueueCap * 8) <= 48 * 1024,
                 "dynamic shared memory must stay under the 48 KB default (no per-device opt-in needed)");
   dim3 grid(s->n_itiles, s->nsplit);
-  kern<<<grid, kForceThreads, smem, s->stream>>>(fp);
-  return cudaGetLastError();
+  return launch_k(s->pdl != 0, kern, grid, dim3(kForceThreads), smem, s->stream, fp);
 }
 
 template <bool PERIODIC, bool RDF>
@@ -399,11 +414,12 @@ static int evaluate(ljmd_system* s, const StepParams& p, int mode, bool rdf, int
     CU(cudaEventRecord(g0, s->stream));
   }
   const int gg = gather_grid(s);
-  if (mode == GATHER_EVAL) k_gather<GATHER_EVAL><<<gg, kStepThreads, 0, s->stream>>>(p, fin, accumulate);
-  else if (mode == GATHER_EVN && fuse_next) k_gather<GATHER_EVN, true><<<gg, kStepThreads, 0, s->stream>>>(p, fin, accumulate);
-  else if (mode == GATHER_EVN) k_gather<GATHER_EVN><<<gg, kStepThreads, 0, s->stream>>>(p, fin, accumulate);
-  else k_gather<GATHER_TVN><<<gg, kStepThreads, 0, s->stream>>>(p, fin, accumulate);
-  CU(cudaGetLastError());
+  const bool pdl = s->pdl != 0;
+  const dim3 gb(kStepThreads);
+  if (mode == GATHER_EVAL) CU(launch_k(pdl, k_gather<GATHER_EVAL, false>, dim3(gg), gb, 0, s->stream, p, fin, accumulate));
+  else if (mode == GATHER_EVN && fuse_next) CU(launch_k(pdl, k_gather<GATHER_EVN, true>, dim3(gg), gb, 0, s->stream, p, fin, accumulate));
+  else if (mode == GATHER_EVN) CU(launch_k(pdl, k_gather<GATHER_EVN, false>, dim3(gg), gb, 0, s->stream, p, fin, accumulate));
+  else CU(launch_k(pdl, k_gather<GATHER_TVN, false>, dim3(gg), gb, 0, s->stream, p, fin, accumulate));
   s->launches += 1;
   if (s->timing) {
     CU(cudaEventRecord(g1, s->stream));
@@ -412,9 +428,8 @@ static int evaluate(ljmd_system* s, const StepParams& p, int mode, bool rdf, int
   }
   if (mode == GATHER_TVN) {
     if ((rc = allreduce_sums(s, SUM_PE, 3))) return rc;  // PE, W, TV2
-    if (fuse_next) k_finish_tvn<true><<<g, kStepThreads, 0, s->stream>>>(p, fin);
-    else k_finish_tvn<false><<<g, kStepThreads, 0, s->stream>>>(p, fin);
-    CU(cudaGetLastError());
+    if (fuse_next) CU(launch_k(pdl, k_finish_tvn<true>, dim3(g), gb, 0, s->stream, p, fin));
+    else CU(launch_k(pdl, k_finish_tvn<false>, dim3(g), gb, 0, s->stream, p, fin));
     s->launches += 1;
     if (s->world > 1) {
       if ((rc = allreduce_sums(s, SUM_K, 1))) return rc;
@@ -445,9 +460,8 @@ static int one_step(ljmd_system* s, const StepParams& p, bool rdf, bool drifted 
   const int g = step_grid(s);
   int rc;
   if (!drifted) {
-    if (s->canonical) k_drift<true><<<g, kStepThreads, 0, s->stream>>>(p);
-    else k_drift<false><<<g, kStepThreads, 0, s->stream>>>(p);
-    CU(cudaGetLastError());
+    if (s->canonical) CU(launch_k(s->pdl != 0, k_drift<true>, dim3(g), dim3(kStepThreads), 0, s->stream, p));
+    else CU(launch_k(s->pdl != 0, k_drift<false>, dim3(g), dim3(kStepThreads), 0, s->stream, p));
     s->launches += 1;
     if ((rc = allgather_positions(s))) return rc;
   }
@@ -659,6 +673,10 @@ static int create_impl(ljmd_system** out, int N, double rho_or_negL, double T0, 
   }
   // lanes per particle in k_gather: enough threads to keep ~2 CTAs of 256 on every SM, never more lanes than
   // half the rows they share
+  {
+    const char* e = getenv("LJMD_PDL");
+    s->pdl = (world == 1 && !s->use_sym && !(e && e[0] == '0')) ? 1 : 0;
+  }
   s->gather_shift = 0;
   while (s->gather_shift < 3 && ((long long)s->nloc << s->gather_shift) < 2LL * kStepThreads * s->num_sms &&
          (2 << s->gather_shift) * 2 <= s->nsplit + (s->use_sym ? s->hmax : 0))

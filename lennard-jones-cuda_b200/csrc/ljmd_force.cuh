@@ -77,6 +77,14 @@ __device__ __forceinline__ float rcp_approx(float x) {
   float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
 }
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in
+// the stream still runs: pdl_trigger() lets the NEXT kernel begin launching, pdl_wait() blocks until the
+// PREVIOUS one has completed and its writes are visible.  Both are no-ops for a plain launch.  Used by the
+// small-system step chain (force -> gather -> finish), where launch latency is most of the step.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- mbarrier + 1-D bulk copy ----------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -368,6 +376,8 @@ inline size_t rdf_smem_bytes(int threads) {
 // was measured 2-10 % slower and removed: profiles/r01_tune_force_65536_pipelined.log.)
 template <typename V, bool PERIODIC, bool RDF, int THREADS, int MINB, int NPAIR, int UNROLL>
 __global__ void __launch_bounds__(THREADS, MINB) k_force(const ForceParams p) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int IPT = 2 * NPAIR;
   constexpr int NW = THREADS / 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];

@@ -190,6 +190,8 @@ __device__ __forceinline__ void finalize_params(const StepParams& p, int accumul
 
 template <bool CANON>
 __global__ void __launch_bounds__(kStepThreads) k_drift(const StepParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int il = blockIdx.x * kStepThreads + threadIdx.x;
   if (il >= p.nloc) return;
   float4 x = p.pos[il];
@@ -298,6 +300,8 @@ __device__ __forceinline__ void fused_next_drift(const StepParams& p, int il, fl
 // FUSE (EVN only here; TVN fuses in k_finish_tvn): also perform the drift of the next step.
 template <int MODE, bool FUSE = false>
 __global__ void __launch_bounds__(kStepThreads) k_gather(const StepParams p, int finalize, int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   // R = 2^gather_shift adjacent lanes share a particle: each sums every R-th row of partial forces (and of
   // reaction rows), a butterfly over the R lanes adds the shares (every lane ends with the same bits), lane 0 of
   // the group goes on.  Mid-size systems have too few particles to hide the latency of S = 30-130 dependent-
@@ -376,6 +380,8 @@ __global__ void __launch_bounds__(kStepThreads) k_gather(const StepParams p, int
 // TVN velocity update with chi = sqrt(T0 / Tkin(t_Vel)), boundaries, K  (MDSystem.cpp:498-506,578-579)
 template <bool FUSE = false>
 __global__ void __launch_bounds__(kStepThreads) k_finish_tvn(const StepParams p, int finalize) {
+  pdl_trigger();
+  pdl_wait();
   const int il = blockIdx.x * kStepThreads + threadIdx.x;
   double Tkin = p.sc->sums[SUM_TV2];
   Tkin *= 1. / 3. / p.N;                                     // :370
