@@ -74,7 +74,7 @@ struct ljmd_system {
   int hmax = 0;     // partner offsets per i-tile (rows of the partner window)
   int sym_bj = 256; // j-records per work unit of the Newton-3 kernel
   int gather_shift = 0;  // k_gather: 2^shift lanes per particle
-  int pdl = 0;           // launch the step chain with programmatic dependent launch (ordered kernel, one GPU)
+  int pdl = 0;           // launch the step chain with programmatic dependent launch (one GPU)
   float4* rpart = nullptr;   // [n_itiles][hmax*kITile] reaction rows
   float4* rsum = nullptr;    // [npad] rank-local column sums of the reaction rows (world > 1)
   float4* rshard = nullptr;  // [cnt]  reaction totals of this rank's particles after the reduce-scatter
@@ -296,8 +296,7 @@ static cudaError_t launch_force_sym_t(ljmd_system* s, const SymParams& sp) {
                         (kForceThreads / 32) * (kRdfBins * 4 + kRdfQueueCap * 8) <= 48 * 1024,
                 "dynamic shared memory must stay under the 48 KB default (no per-device opt-in needed)");
   dim3 grid(s->n_itiles, s->nsplit);
-  kern<<<grid, kForceThreads, smem, s->stream>>>(sp);
-  return cudaGetLastError();
+  return launch_k(s->pdl != 0, kern, grid, dim3(kForceThreads), smem, s->stream, sp);
 }
 
 static int launch_force(ljmd_system* s, bool rdf) {
@@ -675,7 +674,7 @@ static int create_impl(ljmd_system** out, int N, double rho_or_negL, double T0, 
   // half the rows they share
   {
     const char* e = getenv("LJMD_PDL");
-    s->pdl = (world == 1 && !s->use_sym && !(e && e[0] == '0')) ? 1 : 0;
+    s->pdl = (world == 1 && !(e && e[0] == '0')) ? 1 : 0;
   }
   s->gather_shift = 0;
   while (s->gather_shift < 3 && ((long long)s->nloc << s->gather_shift) < 2LL * kStepThreads * s->num_sms &&

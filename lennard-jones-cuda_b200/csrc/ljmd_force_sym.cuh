@@ -233,6 +233,8 @@ __device__ __forceinline__ void pair_sym(const uint4& uj, const PairI<V>& pi, Pa
 
 template <typename V, bool PERIODIC, bool RDF, int THREADS, int MINB, int NPAIR, int UNROLLK = 4>
 __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int IPT = 2 * NPAIR;
   constexpr int B = THREADS * IPT;
   constexpr int NW = THREADS / 32;
