@@ -31,8 +31,9 @@ REACTION_FLOP = 6                        # Newton-3 kernel: 3 more FMAs per unor
 FP32_LANE_INSTR = {0: 14, 1: 16, 2: 16}
 SM_COUNT, FP32_LANES = 148, 128
 # dram__bytes_read.sum + dram__bytes_write.sum of the force kernel per launch on one GPU, from the ncu captures
-# under profiles/ (r01_launches_benchC5_newton3.csv, r01_force_sym_kernel_ncu.md); null where not captured
-TRAFFIC_NOTE = {"C5": 1.79e10, "C3": 2.06e7}
+# under profiles/ (r01_launches_benchC5_newton3.csv, r01_force_sym_kernel_ncu.md: 1.1 MB read + 42 MB of partial-
+# force and reaction rows written at C3); null where not captured
+TRAFFIC_NOTE = {"C5": 1.79e10, "C3": 4.32e7}
 
 
 def measured_peaks():
