@@ -45,7 +45,14 @@ def main():
         sc1 = s.scalars()
         rdf1, nacc = s.rdf_accum()
         vh = s.velocity_histogram(0.12, 101)
+        # observation trace and sub-volume counters on the sharded state (counts are all-reduced on read-out)
+        sub = s.subvolume_counts(3, 0.05)
+        s.trace_begin([(0, 0.05), (3, 0.1), (5, 0.05, 3.0)], 8)
+        s.step(0.004, 3)
+        tr = s.trace_read()
+        s.trace_end()
         np.savez(os.path.join(outdir, f"{name}_rank{rank}.npz"), f0=f0, rdf0=rdf0, p1=p1, v1=v1, f1=f1, rdf1=rdf1,
+                 sub=sub, tr_counts=tr["counts"], tr_scal=tr["scalars"], tr_mv=tr["mean_velocity"],
                  vh=vh, sc0=np.array([sc0[k] for k in sorted(sc0)]), sc1=np.array([sc1[k] for k in sorted(sc1)]))
         res = dict(rank=rank, world=world, nacc=nacc, info=s.launch_info(), fabric=bool(fabric))
         s.close()

@@ -45,6 +45,18 @@ def test_two_gpu_step_matches_single_gpu(pkg, gpu_lib, tmp_path, name, canonical
         sc1 = s.scalars()
         rdf1, _ = s.rdf_accum()
         vh = s.velocity_histogram(0.12, 101)
+        sub = s.subvolume_counts(3, 0.05)
+        s.trace_begin([(0, 0.05), (3, 0.1), (5, 0.05, 3.0)], 8)
+        s.step(0.004, 3)
+        tr = s.trace_read()
+        s.trace_end()
+    # sharded counters and trace rows: the same occupancies up to a particle within 1e-6 of a sub-volume face
+    assert r0["sub"].shape == sub.shape and np.abs(r0["sub"] - sub).max() <= 2
+    assert r0["tr_counts"].shape == tr["counts"].shape == (3, 19 + 9 + 20)
+    assert np.abs(r0["tr_counts"] - tr["counts"]).max() <= 2
+    assert (r0["tr_counts"] <= N).all() and (r0["tr_counts"][:, -1] > 0.99 * N).all()      # |vy| < 3 sigma: 99.7 %
+    assert np.allclose(r0["tr_scal"], tr["scalars"], rtol=1e-5, atol=1e-7)
+    assert np.allclose(r0["tr_mv"], tr["mean_velocity"], rtol=0, atol=1e-6)
     fscale = np.abs(f0[:, :3]).max()
     assert np.abs(r0["f0"][:, :3] - f0[:, :3]).max() <= 2e-6 * fscale
     assert np.array_equal(r0["rdf0"], rdf0)
