@@ -143,8 +143,10 @@ int ljmd_get_state(ljmd_system* s, float* pos4, float* vel4, float* force4);
  * evaluation, EVN half-kick or TVN chi-rescale, boundary conditions,
  * CalculateParameters, t += dt.  Everything stays on the device; returns after
  * the last step completed.  Inside the batch the kernel finishing step k also
- * performs the drift of step k+1 (kick-drift-wrap fusion); results are bit-identical
- * to nsteps single calls.  rdf_every > 0: the RDF histogram is rebuilt on
+ * performs the drift of step k+1 (kick-drift-wrap fusion), and on one GPU the
+ * steady-state steps of a long batch are replayed from a captured CUDA graph
+ * (LJMD_GRAPH=0 disables it); results are bit-identical to nsteps single calls.
+ * rdf_every > 0: the RDF histogram is rebuilt on
  * every rdf_every-th step of this call (and accumulated, see ljmd_get_rdf_accum);
  * 0: no RDF work (ljmd_get_rdf evaluates it lazily when asked).
  */
