@@ -174,3 +174,18 @@ def test_snapshots_are_deterministic_and_exact(pkg):
     g = snap.random_gas(2000, 0.3, min_sep=0.9, seed=5)
     from scipy.spatial import cKDTree
     assert len(cKDTree(g[:, :3].astype(np.float64), boxsize=snap.box_length(2000, 0.3) + 1e-6).query_pairs(0.899)) == 0
+
+
+def test_host_class_is_source_compatible_with_the_reference_header():
+    """The callers' view of MDSystem (tests/data/api_probe.cpp) compiles against the product's header, and —
+    where the reference tree exists — against the reference's own header too, so the probe is a fair witness."""
+    import subprocess
+    probe = os.path.join(ROOT, "tests", "data", "api_probe.cpp")
+    mine = os.path.join(ROOT, "lennard-jones-cuda_b200", "host")
+    r = subprocess.run(["g++", "-std=c++11", "-fsyntax-only", "-I", mine, probe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    ref = "/root/reference/src/library"
+    if os.path.exists(os.path.join(ref, "MDSystem.h")):
+        r = subprocess.run(["g++", "-std=c++11", "-fsyntax-only", "-w", "-I", ref, "-I", "/root/reference/thirdparty", probe],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
