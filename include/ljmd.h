@@ -248,8 +248,10 @@ int ljmd_plan(int N, int rank, int world, int num_sms, int* out8);
  * need vcut_max[c]; the entry is ignored for kinds 0-3, vcut_max may be NULL
  * when there is no velocity counter).  At most 8 counters.  While a trace is
  * active ljmd_step appends one row per step and refuses to run past
- * capacity_steps unread rows; the kick-drift fusion inside a batch is off
- * (a row needs the end-of-step velocities).
+ * capacity_steps unread rows; EVN batches run without the kick-drift fusion
+ * (a row needs the end-of-step velocities; TVN has no first half-kick and keeps
+ * it).  The row index lives on the device, so traced batches are replayed from
+ * a CUDA graph like plain ones.
  */
 int ljmd_trace_begin(ljmd_system* s, int ncounters, const int* kinds, const double* alpha_steps,
                      const double* vcut_max, int capacity_steps);

@@ -91,6 +91,8 @@ struct ljmd_system {
   SubvolSpec* trace_specs = nullptr;            // device copy of the counter specifications
   unsigned long long* trace_counts = nullptr;   // [trace_cap][trace_row]
   double* trace_scal = nullptr;                 // [trace_cap][kTraceScalars]
+  int* trace_idx = nullptr;                     // device: {next row, ticket}
+  int graph_trace = -1, graph_trace_rows = 0;   // trace state the cached graph was captured with / rows per replay
   // fabric (world > 1): one window allocation holding posA | upos | rsum | slots | flags, exported through
   // CUDA IPC; once the peers' windows are mapped the per-step collectives run over peer memory, not NCCL
   char* win = nullptr;
@@ -561,8 +563,7 @@ static int destroy_impl(ljmd_system* s) {
   cudaFree(s->counter); cudaFree(s->velh); cudaFree(s->sc); cudaFree(s->rdf_cur); cudaFree(s->rdf_acc);
   cudaFree(s->flush_buf);
   cudaFree(s->rpart); cudaFree(s->rshard); cudaFree(s->bbox);
-  if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
-  trace_free(s);
+  trace_free(s);   // also destroys the cached graph
   cudaFreeHost(s->h_sc); cudaFreeHost(s->h_rdf);
   for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
   if (s->ev_begin) cudaEventDestroy(s->ev_begin);
@@ -920,42 +921,52 @@ extern "C" int ljmd_step(ljmd_system* s, double dt, int nsteps, int rdf_every) {
   // timing, L2 flush, trace), on more than one GPU, and with LJMD_GRAPH=0.
   const int period = rdf_every > 0 ? rdf_every : 16;
   const char* genv = getenv("LJMD_GRAPH");
-  const bool use_graph = s->world == 1 && !s->timing && !s->trace_on && s->flush_bytes == 0 && period <= 64 &&
+  const bool use_graph = s->world == 1 && !s->timing && s->flush_bytes == 0 && period <= 64 &&
                          nsteps - 2 >= 2 * period && !(genv && genv[0] == '0');
+  // Kick-drift-wrap fusion inside a batch.  With the fabric an EVN step of the ordered kernel has no barrier
+  // between a peer's force kernel and this rank's finishing kernel, so its position pushes must not be fused.
+  // A trace row needs the end-of-step velocities: the fused EVN half-kick of the next step would be in them
+  // (TVN has no first half-kick, so traced TVN batches keep the fusion).
+  const bool steady_fuse = ((s->world == 1) || s->fab.n == 0 || s->use_sym || s->canonical) &&
+                           !(s->trace_on && !s->canonical);
   for (int k = 0; k < nsteps; ++k) {
     if (use_graph && k == 1) {
       const bool fresh = s->graph_exec && s->graph_period == period && s->graph_rdf_every == rdf_every &&
                          s->graph_canonical == s->canonical && s->graph_bc == s->bc && s->graph_dt == dt &&
-                         s->graph_T0 == s->T0;
+                         s->graph_T0 == s->T0 && s->graph_trace == s->trace_on;
       if (!fresh) {
         if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
         const long long l0 = s->launches;
-        const int r0 = s->rdf_nacc;
+        const int r0 = s->rdf_nacc, t0 = s->trace_n;
         CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
         int rc = LJMD_OK;
         for (int j = 0; j < period && rc == LJMD_OK; ++j) {
           const int kk = 1 + j;
-          rc = one_step(s, p, rdf_every > 0 && ((kk + 1) % rdf_every == 0), true, true);
+          rc = one_step(s, p, rdf_every > 0 && ((kk + 1) % rdf_every == 0), steady_fuse, steady_fuse);
+          if (rc == LJMD_OK && s->trace_on) rc = trace_record(s);
         }
         cudaGraph_t graph = nullptr;
         const cudaError_t ce = cudaStreamEndCapture(s->stream, &graph);
         s->graph_launches = s->launches - l0;
         s->graph_rdf_nacc = s->rdf_nacc - r0;
+        s->graph_trace_rows = s->trace_n - t0;
         s->launches = l0;      // nothing ran yet
         s->rdf_nacc = r0;
+        s->trace_n = t0;
         if (rc != LJMD_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
         if (ce != cudaSuccess) return set_err(LJMD_ERR_CUDA, "graph capture: %s", cudaGetErrorString(ce));
         const cudaError_t ie = cudaGraphInstantiate(&s->graph_exec, graph, 0);
         cudaGraphDestroy(graph);
         if (ie != cudaSuccess) { s->graph_exec = nullptr; return set_err(LJMD_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(ie)); }
         s->graph_period = period; s->graph_rdf_every = rdf_every; s->graph_canonical = s->canonical;
-        s->graph_bc = s->bc; s->graph_dt = dt; s->graph_T0 = s->T0;
+        s->graph_bc = s->bc; s->graph_dt = dt; s->graph_T0 = s->T0; s->graph_trace = s->trace_on;
       }
       const int reps = (nsteps - 2) / period;
       for (int r = 0; r < reps; ++r) {
         CU(cudaGraphLaunch(s->graph_exec, s->stream));
         s->launches += s->graph_launches;
         s->rdf_nacc += s->graph_rdf_nacc;
+        s->trace_n += s->graph_trace_rows;
       }
       k += reps * period;    // the steps left (at least the last one) run below, with the same cadence
     }
@@ -967,11 +978,7 @@ extern "C" int ljmd_step(ljmd_system* s, double dt, int nsteps, int rdf_every) {
       CU(cudaEventCreate(&e1));
       CU(cudaEventRecord(e0, s->stream));
     }
-    // Kick-drift-wrap fusion inside a batch.  With the fabric an EVN step of the ordered kernel has no barrier
-    // between a peer's force kernel and this rank's finishing kernel, so its position pushes must not be fused.
-    const bool can_fuse = (s->world == 1) || s->fab.n == 0 || s->use_sym || s->canonical;
-    // a trace row needs the end-of-step velocities: no fused half-kick of the next step behind them
-    const bool fuse_next = can_fuse && (k + 1 < nsteps) && !s->trace_on;
+    const bool fuse_next = steady_fuse && (k + 1 < nsteps);
     int rc = one_step(s, p, rdf, drifted, fuse_next);
     if (rc) return rc;
     if (s->trace_on && (rc = trace_record(s))) return rc;
@@ -1188,8 +1195,9 @@ static int subvolume_impl(ljmd_system* s, int type, double alpha_step, double vc
 
 // ---- observation trace ---------------------------------------------------------------------------
 static void trace_free(ljmd_system* s) {
-  cudaFree(s->trace_specs); cudaFree(s->trace_counts); cudaFree(s->trace_scal);
-  s->trace_specs = nullptr; s->trace_counts = nullptr; s->trace_scal = nullptr;
+  cudaFree(s->trace_specs); cudaFree(s->trace_counts); cudaFree(s->trace_scal); cudaFree(s->trace_idx);
+  s->trace_specs = nullptr; s->trace_counts = nullptr; s->trace_scal = nullptr; s->trace_idx = nullptr;
+  if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }   // it holds the old buffers
   s->trace_on = 0; s->trace_cap = s->trace_n = s->trace_row = s->trace_ncounters = 0;
 }
 
@@ -1215,6 +1223,8 @@ extern "C" int ljmd_trace_begin(ljmd_system* s, int ncounters, const int* kinds,
   CU(cudaMalloc(&s->trace_counts, (size_t)capacity_steps * row * sizeof(unsigned long long)));
   CU(cudaMalloc(&s->trace_scal, (size_t)capacity_steps * kTraceScalars * sizeof(double)));
   CU(cudaMemsetAsync(s->trace_counts, 0, (size_t)capacity_steps * row * sizeof(unsigned long long), s->stream));
+  CU(cudaMalloc(&s->trace_idx, 2 * sizeof(int)));
+  CU(cudaMemsetAsync(s->trace_idx, 0, 2 * sizeof(int), s->stream));
   s->trace_on = 1; s->trace_cap = capacity_steps; s->trace_n = 0; s->trace_row = row; s->trace_ncounters = ncounters;
   return LJMD_OK;
 }
@@ -1232,8 +1242,10 @@ static int trace_record(ljmd_system* s) {
   TraceParams q;
   q.pos = s->pos; q.vel = s->vel; q.n = s->nloc;
   q.ncounters = s->trace_ncounters; q.row = s->trace_row; q.specs = s->trace_specs; q.sc = s->sc;
-  q.counts = s->trace_counts + (size_t)s->trace_n * s->trace_row;
-  q.scal = s->trace_scal + (size_t)s->trace_n * kTraceScalars;
+  q.counts = s->trace_counts;
+  q.scal = s->trace_scal;
+  q.row_idx = s->trace_idx;
+  q.ticket = reinterpret_cast<unsigned int*>(s->trace_idx + 1);
   const int g = std::max(1, std::min(step_grid(s), 4 * s->num_sms));
   k_trace<<<g, kStepThreads, (size_t)(s->trace_row - 3 + 1) * sizeof(unsigned int), s->stream>>>(q);
   CU(cudaGetLastError());
@@ -1260,6 +1272,7 @@ extern "C" int ljmd_trace_read(ljmd_system* s, int max_steps, int* nsteps, doubl
   if (scalars)
     CU(cudaMemcpyAsync(scalars, s->trace_scal, (size_t)n * kTraceScalars * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   CU(cudaMemsetAsync(s->trace_counts, 0, (size_t)n * row * sizeof(unsigned long long), s->stream));
+  CU(cudaMemsetAsync(s->trace_idx, 0, 2 * sizeof(int), s->stream));
   CU(cudaStreamSynchronize(s->stream));
   for (int k = 0; k < n; ++k) {
     const unsigned long long* r = h.data() + (size_t)k * row;

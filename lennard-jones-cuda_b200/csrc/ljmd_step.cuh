@@ -556,12 +556,16 @@ struct TraceParams {
   int ncounters, row;          // row = sum of nbins + 3
   const SubvolSpec* specs;     // [ncounters], device memory
   const DevScalars* sc;
-  unsigned long long* counts;  // row of this step
-  double* scal;                // kTraceScalars doubles of this step
+  unsigned long long* counts;  // [capacity][row]
+  double* scal;                // [capacity][kTraceScalars]
+  int* row_idx;                // device-resident index of the row this launch fills: the launch arguments are the
+  unsigned int* ticket;        // same for every step, so a traced batch can be replayed from a CUDA graph
 };
 __global__ void __launch_bounds__(kStepThreads) k_trace(const TraceParams q) {
   extern __shared__ unsigned int th[];   // row - 3 bins
   const int nb = q.row - 3;
+  const int r = *q.row_idx;              // every CTA reads it before the last one to finish advances it
+  unsigned long long* counts = q.counts + (size_t)r * q.row;
   for (int k = threadIdx.x; k < nb; k += kStepThreads) th[k] = 0u;
   __syncthreads();
   long long sx = 0, sy = 0, sz = 0;
@@ -585,16 +589,25 @@ __global__ void __launch_bounds__(kStepThreads) k_trace(const TraceParams q) {
     sz += __shfl_xor_sync(0xffffffffu, sz, o);
   }
   if ((threadIdx.x & 31) == 0) {
-    atomicAdd(&q.counts[nb + 0], (unsigned long long)sx);
-    atomicAdd(&q.counts[nb + 1], (unsigned long long)sy);
-    atomicAdd(&q.counts[nb + 2], (unsigned long long)sz);
+    atomicAdd(&counts[nb + 0], (unsigned long long)sx);
+    atomicAdd(&counts[nb + 1], (unsigned long long)sy);
+    atomicAdd(&counts[nb + 2], (unsigned long long)sz);
   }
   __syncthreads();
   for (int k = threadIdx.x; k < nb; k += kStepThreads)
-    if (th[k]) atomicAdd(&q.counts[k], (unsigned long long)th[k]);
+    if (th[k]) atomicAdd(&counts[k], (unsigned long long)th[k]);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    q.scal[0] = q.sc->t; q.scal[1] = q.sc->U; q.scal[2] = q.sc->T; q.scal[3] = q.sc->P;
-    q.scal[4] = q.sc->K; q.scal[5] = q.sc->V; q.scal[6] = q.sc->Pvirial; q.scal[7] = 0.;
+    double* scal = q.scal + (size_t)r * kTraceScalars;
+    scal[0] = q.sc->t; scal[1] = q.sc->U; scal[2] = q.sc->T; scal[3] = q.sc->P;
+    scal[4] = q.sc->K; scal[5] = q.sc->V; scal[6] = q.sc->Pvirial; scal[7] = 0.;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(q.ticket, 1u) == gridDim.x - 1) {   // last CTA: the row is complete
+      *q.ticket = 0u;
+      *q.row_idx = r + 1;
+    }
   }
 }
 
