@@ -1247,7 +1247,8 @@ static int trace_record(ljmd_system* s) {
   q.row_idx = s->trace_idx;
   q.ticket = reinterpret_cast<unsigned int*>(s->trace_idx + 1);
   const int g = std::max(1, std::min(step_grid(s), 4 * s->num_sms));
-  k_trace<<<g, kStepThreads, (size_t)(s->trace_row - 3 + 1) * sizeof(unsigned int), s->stream>>>(q);
+  const size_t smem = (size_t)s->trace_ncounters * sizeof(SubvolSpec) + (size_t)(s->trace_row - 3 + 1) * sizeof(unsigned int);
+  k_trace<<<g, kStepThreads, smem, s->stream>>>(q);
   CU(cudaGetLastError());
   s->launches += 1;
   s->trace_n += 1;

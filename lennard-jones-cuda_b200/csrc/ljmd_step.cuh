@@ -562,10 +562,20 @@ struct TraceParams {
   unsigned int* ticket;        // same for every step, so a traced batch can be replayed from a CUDA graph
 };
 __global__ void __launch_bounds__(kStepThreads) k_trace(const TraceParams q) {
-  extern __shared__ unsigned int th[];   // row - 3 bins
+  // dynamic smem: the counter specifications (the cube counter binary-searches its table of edges: 21 dependent
+  // loads per particle, 13 us per launch at N = 400 when they came from global memory), then row - 3 bins
+  extern __shared__ __align__(8) unsigned char trace_smem[];
+  SubvolSpec* sspec = reinterpret_cast<SubvolSpec*>(trace_smem);
+  unsigned int* th = reinterpret_cast<unsigned int*>(trace_smem + (size_t)q.ncounters * sizeof(SubvolSpec));
   const int nb = q.row - 3;
   const int r = *q.row_idx;              // every CTA reads it before the last one to finish advances it
   unsigned long long* counts = q.counts + (size_t)r * q.row;
+  {
+    const int nw = q.ncounters * (int)(sizeof(SubvolSpec) / sizeof(int));
+    const int* src = reinterpret_cast<const int*>(q.specs);
+    int* dst = reinterpret_cast<int*>(sspec);
+    for (int k = threadIdx.x; k < nw; k += kStepThreads) dst[k] = src[k];
+  }
   for (int k = threadIdx.x; k < nb; k += kStepThreads) th[k] = 0u;
   __syncthreads();
   long long sx = 0, sy = 0, sz = 0;
@@ -573,7 +583,7 @@ __global__ void __launch_bounds__(kStepThreads) k_trace(const TraceParams q) {
     const float4 x = q.pos[i], v = q.vel[i];
     int off = 0;
     for (int c = 0; c < q.ncounters; ++c) {
-      const SubvolSpec& sp = q.specs[c];
+      const SubvolSpec& sp = sspec[c];
       const int bin = subvol_bin(sp, sp.type <= 3 ? x : v);
       if (bin >= 0 && bin < sp.nbins) atomicAdd(&th[off + bin], 1u);
       off += sp.nbins;
