@@ -124,3 +124,20 @@ def test_fraction_grids(tasklib):
     n = tasklib.ljtasks_momentum_cuts(1.4, 0.05, 3.0, out.ctypes.data, 256)
     assert n == 20 and abs(out[n - 1] - 3.0 * np.sqrt(1.4)) < 1e-12
     assert tasklib.ljtasks_coordinate_fractions(0.5, out.ctypes.data, 256) == 1 and out[0] == 0.5
+
+
+@pytest.mark.parametrize("exe,args", [("run-fluctuations", ["tests/data/N400.short.input"]), ("run-isotherm", []),
+                                      ("semiGCEfluctuations", ["1"])])
+def test_task_drivers_fail_loudly_without_a_gpu(exe, args):
+    """No CPU fallback: on a machine without a CUDA device the drivers say so and exit non-zero before any work."""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the drivers run (tests/test_tasks_gpu.py)")
+    path = os.path.join(TASKS, "bin", exe)
+    if not os.path.exists(path):
+        pytest.fail(f"{path} not built: run __graft_entry__.build()")
+    out = subprocess.run([path] + [os.path.join(ROOT, a) if a.endswith(".input") else a for a in args],
+                         capture_output=True, text=True, timeout=60, cwd=os.path.join(ROOT, "tests"))
+    assert out.returncode != 0
+    assert "CUDA device" in out.stderr
