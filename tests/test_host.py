@@ -189,3 +189,27 @@ def test_host_class_is_source_compatible_with_the_reference_header():
         r = subprocess.run(["g++", "-std=c++11", "-fsyntax-only", "-w", "-I", ref, "-I", "/root/reference/thirdparty", probe],
                            capture_output=True, text=True)
         assert r.returncode == 0, r.stderr[-3000:]
+
+
+def test_launch_plan_is_near_the_measured_optimum(pkg):
+    """The Newton-3 launch planner against the split scan it was calibrated on (profiles/, measured on a B200):
+    at every scanned size the number of splits it picks is one of the measured configurations, and that
+    configuration ran within 4 % of the best one found for the size."""
+    path = os.path.join(ROOT, "profiles", "r01_tune_force_sym_split_scan.log")
+    table, N = {}, None
+    for ln in open(path):
+        m = re.match(r"== N=(\d+)", ln)
+        if m:
+            N = int(m.group(1))
+            continue
+        m = re.search(r"scan bj(\d+) S(\d+) per_cta(\d+) ctas(\d+).*?best\s+([\d.]+) ms", ln)
+        if m and N is not None:
+            table.setdefault(N, []).append((int(m.group(2)), float(m.group(5))))
+    sizes = [n for n in sorted(table) if n >= 8192]
+    assert len(sizes) >= 5
+    for n in sizes:
+        best = min(t for _, t in table[n])
+        splits = pkg.ljmd.plan(n, 0, 1, 148)["j_splits"]
+        mine = [t for s_, t in table[n] if s_ == splits]
+        assert mine, (n, splits)
+        assert min(mine) <= 1.04 * best, (n, splits, min(mine), best)
