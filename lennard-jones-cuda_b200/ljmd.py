@@ -39,6 +39,22 @@ class LJMDError(RuntimeError):
     pass
 
 
+def _preload_bundled_nccl():
+    """libljmd.so needs `libnccl.so.2`; PyTorch ships its own, newer one under the same soname.  Whichever is
+    loaded first serves both, and torch does not import against the system's older NCCL — so a process that loads
+    this library before `import torch` would break torch.  Loading torch's copy first (when there is one) makes
+    the import order irrelevant; the collectives this library calls exist in both."""
+    import sys
+    for base in sys.path:
+        cand = os.path.join(base, "nvidia", "nccl", "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            try:
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+            except OSError:
+                pass
+            return
+
+
 def load_library(path=None):
     """Load libljmd.so; raise (never fall back) when it is missing."""
     global _lib
@@ -48,6 +64,7 @@ def load_library(path=None):
     if not os.path.exists(p):
         raise LJMDError(f"{p} not found: build it with __graft_entry__.build() (make -C lennard-jones-cuda_b200/csrc); "
                         "there is no CPU fallback")
+    _preload_bundled_nccl()
     lib = C.CDLL(p, mode=C.RTLD_GLOBAL)
     vp, ip, dp, fp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_float)
     lib.ljmd_last_error.restype = C.c_char_p

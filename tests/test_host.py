@@ -213,3 +213,16 @@ def test_launch_plan_is_near_the_measured_optimum(pkg):
         mine = [t for s_, t in table[n] if s_ == splits]
         assert mine, (n, splits)
         assert min(mine) <= 1.04 * best, (n, splits, min(mine), best)
+
+
+def test_library_and_torch_import_in_either_order():
+    """libljmd.so and PyTorch both need `libnccl.so.2`; loading the library first must not break `import torch`
+    (the binding preloads torch's bundled copy), and the other order is what bench.py does."""
+    import subprocess
+    import sys
+    for first in ("lib", "torch"):
+        code = ("import sys; sys.path.insert(0, %r); import ljpkg; pkg = ljpkg.load();\n" % ROOT +
+                ("pkg.ljmd.load_library(); import torch\n" if first == "lib" else "import torch; pkg.ljmd.load_library()\n") +
+                "print('ok', torch.__version__)")
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "ok" in r.stdout, (first, r.stderr[-1500:])

@@ -128,11 +128,10 @@ def test_fraction_grids(tasklib):
 
 @pytest.mark.parametrize("exe,args", [("run-fluctuations", ["tests/data/N400.short.input"]), ("run-isotherm", []),
                                       ("semiGCEfluctuations", ["1"])])
-def test_task_drivers_fail_loudly_without_a_gpu(exe, args):
+def test_task_drivers_fail_loudly_without_a_gpu(pkg, exe, args):
     """No CPU fallback: on a machine without a CUDA device the drivers say so and exit non-zero before any work."""
     import subprocess
-    import torch
-    if torch.cuda.is_available():
+    if pkg.ljmd.load_library().ljmd_device_count() > 0:
         pytest.skip("a GPU is present: the drivers run (tests/test_tasks_gpu.py)")
     path = os.path.join(TASKS, "bin", exe)
     if not os.path.exists(path):
