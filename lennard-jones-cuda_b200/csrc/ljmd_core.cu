@@ -15,6 +15,7 @@
 #ifdef LJMD_WITH_NCCL
 #include <nccl.h>
 #endif
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges around force / gather / exchange / step
 
 #include "ljmd_force_sym.cuh"
 #include "ljmd_step.cuh"
@@ -46,6 +47,13 @@ extern "C" const char* ljmd_last_error(void) { return g_err; }
       return set_err(LJMD_ERR_NCCL, "%s:%d %s -> %s", __FILE__, __LINE__, #call, ncclGetErrorString(r_)); \
   } while (0)
 #endif
+
+// NVTX range for the enclosing scope (host-side: the launches are asynchronous, the range marks their submission;
+// a timeline tool attributes the kernels launched inside it).
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 // --------------------------------------------------------------------------------- the handle
 constexpr int kForceThreads = 128;
@@ -302,6 +310,7 @@ static cudaError_t launch_force_sym_t(ljmd_system* s, const SymParams& sp) {
 }
 
 static int launch_force(ljmd_system* s, bool rdf) {
+  NvtxRange nvtx_(rdf ? "ljmd:force+rdf" : "ljmd:force");
   ForceParams fp;
   memset(&fp, 0, sizeof(fp));
   const bool periodic = (s->bc == LJMD_BC_PERIODIC);
@@ -359,6 +368,7 @@ static int launch_force(ljmd_system* s, bool rdf) {
 // Two transports: the fabric (peer windows over NVLink, ljmd_fabric_connect) and NCCL (always available,
 // and still used for the rare read-out collectives).
 static int fabric_sync(ljmd_system* s, int first, int count) {
+  NvtxRange nvtx_("ljmd:exchange(fabric barrier)");
   s->epoch += 1;
   k_fabric_sync<<<1, 32, 0, s->stream>>>(s->fab, s->epoch, first, count, s->sc);
   CU(cudaGetLastError());
@@ -369,6 +379,7 @@ static int fabric_sync(ljmd_system* s, int first, int count) {
 static int allgather_positions(ljmd_system* s) {
   if (s->world == 1) return LJMD_OK;
   if (s->fab.n > 0) return fabric_sync(s, 0, 0);   // the kernels pushed the records themselves: barrier only
+  NvtxRange nvtx_("ljmd:exchange(nccl all-gather)");
 #ifdef LJMD_WITH_NCCL
   const size_t bytes = (size_t)s->cnt * 16;
   NC(ncclAllGather((const char*)s->posA + (size_t)s->rank * bytes, s->posA, bytes, ncclChar, s->comm, s->stream));
@@ -380,6 +391,7 @@ static int allgather_positions(ljmd_system* s) {
 static int allreduce_sums(ljmd_system* s, int first, int count) {
   if (s->world == 1) return LJMD_OK;
   if (s->fab.n > 0) return fabric_sync(s, first, count);
+  NvtxRange nvtx_("ljmd:exchange(nccl all-reduce)");
 #ifdef LJMD_WITH_NCCL
   double* ptr = s->sc->sums + first;
   NC(ncclAllReduce(ptr, ptr, count, ncclDouble, ncclSum, s->comm, s->stream));
@@ -414,6 +426,7 @@ static int evaluate(ljmd_system* s, const StepParams& p, int mode, bool rdf, int
     CU(cudaEventCreate(&g1));
     CU(cudaEventRecord(g0, s->stream));
   }
+  NvtxRange nvtx_("ljmd:gather+finish");
   const int gg = gather_grid(s);
   const bool pdl = s->pdl != 0;
   const dim3 gb(kStepThreads);
@@ -458,9 +471,11 @@ static int evaluate(ljmd_system* s, const StepParams& p, int mode, bool rdf, int
 // One Integrate.  drifted: the previous step's finishing kernel already did this step's drift (fusion);
 // fuse_next: do the next step's drift in this step's finishing kernel.
 static int one_step(ljmd_system* s, const StepParams& p, bool rdf, bool drifted = false, bool fuse_next = false) {
+  NvtxRange nvtx_("ljmd:integrate");
   const int g = step_grid(s);
   int rc;
   if (!drifted) {
+    NvtxRange nvtx_d("ljmd:drift");
     if (s->canonical) CU(launch_k(s->pdl != 0, k_drift<true>, dim3(g), dim3(kStepThreads), 0, s->stream, p));
     else CU(launch_k(s->pdl != 0, k_drift<false>, dim3(g), dim3(kStepThreads), 0, s->stream, p));
     s->launches += 1;
@@ -503,6 +518,8 @@ static void collect_timing(ljmd_system* s) {
     cudaEventDestroy(s->gath_ev[k + 1]);
   }
   s->gath_ev.clear();
+  for (cudaEvent_t e : s->step_ev) cudaEventDestroy(e);   // per-step pairs are consumed by ljmd_step before this
+  s->step_ev.clear();
 }
 
 // ------------------------------------------------------------------------------------ C ABI: A
@@ -566,6 +583,8 @@ static int destroy_impl(ljmd_system* s) {
   trace_free(s);   // also destroys the cached graph
   cudaFreeHost(s->h_sc); cudaFreeHost(s->h_rdf);
   for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : s->step_ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : s->gath_ev) cudaEventDestroy(e);
   if (s->ev_begin) cudaEventDestroy(s->ev_begin);
   if (s->ev_end) cudaEventDestroy(s->ev_end);
   if (s->stream) cudaStreamDestroy(s->stream);
@@ -1111,6 +1130,9 @@ extern "C" int ljmd_velocity_histogram(ljmd_system* s, double step, int nbins, i
   if (!out || nbins < 1 || nbins > 65536 / 2 || !(step > 0.)) return set_err(LJMD_ERR_ARG, "bad histogram arguments");
   CU(cudaMemsetAsync(s->velh, 0, (size_t)nbins * 4, s->stream));
   const int g = std::min(step_grid(s), 4 * s->num_sms);
+  // up to 32 768 bins = 128 KB of dynamic shared memory: beyond the 48 KB default a per-function opt-in is needed
+  if ((size_t)nbins * 4 > 48 * 1024)
+    CU(cudaFuncSetAttribute(k_velhist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)nbins * 4)));
   k_velhist<<<g, kStepThreads, (size_t)nbins * 4, s->stream>>>(s->vel, s->nloc, step, nbins, s->velh);
   CU(cudaGetLastError());
   s->launches += 1;
@@ -1351,6 +1373,9 @@ extern "C" int ljmd_get_launch_info(ljmd_system* s, int* out8) {
 // Worker for the legacy seam (ljmd_legacy.cu): forces on caller-owned device arrays.
 int ljmd_legacy_forces(ljmd_system* s, const float* d_pos, float* d_force, float* pressure, int* rdf256) {
   CHECK_S(s);
+  // The caller's copyArrayToDevice (a pageable-memory cudaMemcpy on the legacy default stream) may return before
+  // its DMA has landed, and this handle's stream is non-blocking: order explicitly after the legacy stream.
+  CU(cudaStreamSynchronize(cudaStreamLegacy));
   CU(cudaMemcpyAsync(s->pos, d_pos, (size_t)s->N * 16, cudaMemcpyDeviceToDevice, s->stream));
   StepParams p = make_step_params(s, 0.);
   k_prepare<<<step_grid(s), kStepThreads, 0, s->stream>>>(p);

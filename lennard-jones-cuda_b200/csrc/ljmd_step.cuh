@@ -446,38 +446,63 @@ __global__ void __launch_bounds__(kStepThreads) k_velhist(const float4* __restri
 // sums into its slot of every peer's window, raises its flag there to `epoch`, waits until all its own flags
 // reached `epoch`, and adds the slots up in rank order (bit-identical totals on every rank).  Slots are
 // double-buffered on the epoch parity: a fast rank can be one sync ahead of a slow one, never two.
+// Release / acquire at system scope (PTX memory model): the flag store publishes every earlier store of this
+// rank's kernels to the peers (.release orders them before the flag becomes visible), the flag load makes
+// the peers' earlier stores visible to this rank (.acquire orders the following loads after it).
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+constexpr unsigned long long kFabricTimeoutNs = 10ull * 1000ull * 1000ull * 1000ull;   // 10 s of wall time
+
 __global__ void k_fabric_sync(const Fabric f, unsigned long long epoch, int first, int count, DevScalars* sc) {
   const int lane = threadIdx.x;
   const int par = (int)(epoch & 1ull);
   if (lane < f.n) {
     if (count > 0) {
-      volatile double* dst = reinterpret_cast<volatile double*>(f.base[lane] + f.off_slots) +
-                             ((size_t)par * kMaxPeers + f.me) * kSlotDoubles;
+      double* dst = reinterpret_cast<double*>(f.base[lane] + f.off_slots) + ((size_t)par * kMaxPeers + f.me) * kSlotDoubles;
       for (int k = 0; k < count; ++k) dst[k] = sc->sums[first + k];
     }
-    __threadfence_system();
-    reinterpret_cast<volatile unsigned long long*>(f.base[lane] + f.off_flags)[f.me] = epoch;
-    // wait for rank `lane` to arrive
-    volatile unsigned long long* mine = reinterpret_cast<volatile unsigned long long*>(f.base[f.me] + f.off_flags);
-    const long long t0 = clock64();
-    while (mine[lane] < epoch) {
-      if (clock64() - t0 > 20000000000ll) {   // ~10 s: a peer died; fail the step instead of hanging the GPU
+    // everything this rank's earlier kernels in the stream stored into peer windows (positions, reaction sums)
+    // and the slot above become visible to rank `lane` before it sees the flag
+    st_release_sys(reinterpret_cast<unsigned long long*>(f.base[lane] + f.off_flags) + f.me, epoch);
+    // wait for rank `lane` to arrive: acquire load, exponential back-off, wall-clock watchdog
+    const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(f.base[f.me] + f.off_flags) + lane;
+    const unsigned long long t0 = global_timer_ns();
+    unsigned int ns = 32;
+    while (ld_acquire_sys(mine) < epoch) {
+      __nanosleep(ns);
+      if (ns < 1024) ns <<= 1;
+      if (global_timer_ns() - t0 > kFabricTimeoutNs) {   // a peer died: fail the step instead of hanging the GPU
         sc->fabric_timeout = 1;
         break;
       }
     }
   }
   __syncwarp();
-  __threadfence_system();
   if (count > 0 && lane == 0) {
-    const volatile double* src = reinterpret_cast<const volatile double*>(f.base[f.me] + f.off_slots) +
-                                 (size_t)par * kMaxPeers * kSlotDoubles;
+    // lane 0 reads slots written by peers whose flags OTHER lanes acquired: order those loads after the
+    // warp-level rendezvous with a system-scope fence
+    __threadfence_system();
+    const double* src = reinterpret_cast<const double*>(f.base[f.me] + f.off_slots) + (size_t)par * kMaxPeers * kSlotDoubles;
     for (int k = 0; k < count; ++k) {
       double t = 0.;
-      for (int r = 0; r < f.n; ++r) t += src[(size_t)r * kSlotDoubles + k];
+      for (int r = 0; r < f.n; ++r) t += __ldcv(src + (size_t)r * kSlotDoubles + k);
       sc->sums[first + k] = t;
     }
   }
+  // the kernels that follow in the stream read peer-written data with plain loads: make this kernel's acquires
+  // cover them (kernel boundary orders; the fence makes the visibility explicit for every lane)
+  __threadfence_system();
 }
 
 // Sub-volume occupancy histograms for the fluctuation tasks

@@ -246,6 +246,13 @@ class LJSystem:
 
     def integrate_host(self, dt, pos, vel, force=None):
         """Drop-in single Integrate(dt) on caller-owned host arrays (updated in place)."""
+        for name, a in (("pos", pos), ("vel", vel), ("force", force)):
+            if a is None and name == "force":
+                continue
+            # raw pointers cross the C ABI: anything but a writable C-contiguous float32 [N,4] would corrupt memory
+            if not (isinstance(a, np.ndarray) and a.dtype == np.float32 and a.flags.c_contiguous and a.flags.writeable
+                    and a.size == 4 * self.N):
+                raise ValueError(f"{name} must be a writable C-contiguous float32 array of {self.N} x 4 values")
         self._check(self._lib.ljmd_integrate_host(self._h, float(dt), _ptr(pos), _ptr(vel),
                                                   _ptr(force) if force is not None else None))
 

@@ -148,6 +148,73 @@ void ljo_forces_f64(int N, const float* pos, double L, int bc,
   scal[3] = Pabs * 4. / 3. / 2.;
 }
 
+/*
+ * FP64 arbiter on a SUBSAMPLE of the particles, for sizes where the O(N^2) arbiter above takes hours
+ * (N = 65 536 ... 1 048 576): the force on each of the nsub particles idx[k] from all N, every operation and
+ * accumulator in double, image rule as in ljo_forces_f64 (the reference's MDSystem.cpp:269-277 in exact
+ * arithmetic).  O(nsub * N), split over `threads` host threads (independent particles; no shared writes).
+ * out: frc[3*nsub] (x4 applied), fterm[nsub] = 4*sum_j (12 r^-13 + 6 r^-7) (the tolerance scale),
+ * pe[2*nsub] = per particle {sum_j (r^-12 - r^-6) (what force.w carries, MDSystem.cu:52), sum_j (r^-12 + r^-6)}.
+ */
+#include <pthread.h>
+typedef struct {
+  int N, bc, k0, k1;
+  const float* pos;
+  const int* idx;
+  double L;
+  double *frc, *fterm, *pe;
+} ljo_sub_job;
+
+static void* ljo_sub_worker(void* arg)
+{
+  const ljo_sub_job* q = (const ljo_sub_job*)arg;
+  int k, j;
+  for (k = q->k0; k < q->k1; ++k) {
+    const int i = q->idx[k];
+    const double xi = q->pos[4 * i], yi = q->pos[4 * i + 1], zi = q->pos[4 * i + 2];
+    double fx = 0., fy = 0., fz = 0., ft = 0., pe = 0., pa = 0.;
+    for (j = 0; j < q->N; ++j) {
+      double rx, ry, rz, r2, ir2, r6, s;
+      if (j == i) continue;
+      rx = xi - q->pos[4 * j]; ry = yi - q->pos[4 * j + 1]; rz = zi - q->pos[4 * j + 2];
+      if (q->bc == 0) {
+        rx -= q->L * rint(rx / q->L); ry -= q->L * rint(ry / q->L); rz -= q->L * rint(rz / q->L);
+      }
+      r2 = rx * rx + ry * ry + rz * rz;
+      ir2 = 1. / r2; r6 = ir2 * ir2 * ir2;
+      s = ir2 * (12. * r6 * r6 - 6. * r6);
+      fx += s * rx; fy += s * ry; fz += s * rz;
+      ft += ir2 * (12. * r6 * r6 + 6. * r6) * sqrt(r2);
+      pe += r6 * r6 - r6;
+      pa += r6 * r6 + r6;
+    }
+    q->frc[3 * k] = 4. * fx; q->frc[3 * k + 1] = 4. * fy; q->frc[3 * k + 2] = 4. * fz;
+    q->fterm[k] = 4. * ft;
+    q->pe[2 * k] = pe;
+    q->pe[2 * k + 1] = pa;
+  }
+  return 0;
+}
+
+void ljo_forces_f64_subset(int N, const float* pos, double L, int bc, int nsub, const int* idx, int threads,
+                           double* frc, double* fterm, double* pe)
+{
+  enum { MAXT = 64 };
+  pthread_t th[MAXT];
+  ljo_sub_job job[MAXT];
+  int t, nt = threads < 1 ? 1 : (threads > MAXT ? MAXT : threads);
+  if (nt > nsub) nt = nsub > 0 ? nsub : 1;
+  for (t = 0; t < nt; ++t) {
+    job[t].N = N; job[t].bc = bc; job[t].pos = pos; job[t].idx = idx; job[t].L = L;
+    job[t].frc = frc; job[t].fterm = fterm; job[t].pe = pe;
+    job[t].k0 = (int)((long long)nsub * t / nt);
+    job[t].k1 = (int)((long long)nsub * (t + 1) / nt);
+  }
+  for (t = 1; t < nt; ++t) pthread_create(&th[t], 0, ljo_sub_worker, &job[t]);
+  ljo_sub_worker(&job[0]);
+  for (t = 1; t < nt; ++t) pthread_join(th[t], 0);
+}
+
 /* MDSystem.cpp:361-373 */
 double ljo_kinetic_temperature(int N, const float* vel)
 {

@@ -47,6 +47,7 @@ class Oracle:
         lib.ljo_box_length.argtypes = [C.c_int, C.c_double]
         lib.ljo_forces.argtypes = [C.c_int, vp, C.c_double, C.c_int, C.c_float, vp, vp, vp]
         lib.ljo_forces_f64.argtypes = [C.c_int, vp, C.c_double, C.c_int, vp, vp, vp]
+        lib.ljo_forces_f64_subset.argtypes = [C.c_int, vp, C.c_double, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp]
         lib.ljo_kinetic_temperature.restype = C.c_double
         lib.ljo_kinetic_temperature.argtypes = [C.c_int, vp]
         lib.ljo_apply_boundary.argtypes = [C.c_int, vp, vp, C.c_double, C.c_int]
@@ -84,6 +85,21 @@ class Oracle:
         scal = np.zeros(4, dtype=np.float64)
         self.lib.ljo_forces_f64(N, _p(pos), L, bc, _p(frc), _p(fa), _p(scal))
         return frc, fa[:N].copy(), dict(V=scal[0], Pvirial=scal[1], Vabs=scal[2], Pabs=scal[3], fterm_sum=fa[N:].copy())
+
+    def forces_f64_subset(self, pos, L, bc, idx, threads=None):
+        """FP64 arbiter for the particles `idx` only (O(len(idx) * N), host threads): -> frc[n,3] float64,
+        fterm[n] (tolerance scale: 4 sum_j (12 r^-13 + 6 r^-7)), pe[n] = sum_j (r^-12 - r^-6), peabs[n] = sum_j (r^-12 + r^-6)."""
+        pos = _f4(pos)
+        N = pos.size // 4
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        n = idx.size
+        frc = np.zeros((n, 3), dtype=np.float64)
+        fterm = np.zeros(n, dtype=np.float64)
+        pe = np.zeros((n, 2), dtype=np.float64)
+        if threads is None:
+            threads = max(1, min(64, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count() or 1))
+        self.lib.ljo_forces_f64_subset(N, _p(pos), L, bc, n, _p(idx), int(threads), _p(frc), _p(fterm), _p(pe))
+        return frc, fterm, pe[:, 0].copy(), pe[:, 1].copy()
 
     def parameters(self, N, rho, vel, V, Pvirial, Pshear_conf=0.0):
         vel = _f4(vel)

@@ -47,7 +47,7 @@ def load_golden(name):
 
 @pytest.fixture(params=["default", "ordered", "sym"])
 def kernel(request, monkeypatch):
-    """Force-kernel choice for systems created inside the test: the library's own (ordered below 16 blocks,
+    """Force-kernel choice for systems created inside the test: the library's own (ordered below 8 blocks of 512 particles,
     Newton-3 above), or one of the two forced through LJMD_KERNEL (read at ljmd_create)."""
     if request.param == "default":
         monkeypatch.delenv("LJMD_KERNEL", raising=False)

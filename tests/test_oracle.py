@@ -104,3 +104,24 @@ def test_restatement_equals_reference_live(oracle, pkg, N, T, rho, canonical, bc
     assert np.array_equal(rx, ox) and np.array_equal(rg, og)
     vx, vd = ref.velocity_histogram(12.0, 0.12)
     assert np.array_equal(np.rint(vd * 0.12 * N).astype(np.int32), oracle.velocity_histogram(v2, 0.12, len(vx)))
+
+
+def test_subset_arbiter_equals_full_arbiter(oracle):
+    """ljo_forces_f64_subset (the full-size checker: O(nsub * N), threaded) is the FP64 arbiter restricted to
+    the sampled particles, bit for bit, for periodic and open boxes and any thread count."""
+    import ljpkg
+    pkg = ljpkg.load()
+    N, rho = 1500, 0.6
+    pos = pkg.snapshots.lattice(N, rho, jitter=0.08, seed=11)
+    L = oracle.box_length(N, rho)
+    idx = np.array([0, 1, 17, 511, 512, 733, N - 1], dtype=np.int32)
+    for bc in (0, 1):
+        f64, _, sc = oracle.forces_f64(pos, L, bc)
+        for threads in (1, 3, 16):
+            f, fterm, pe, peabs = oracle.forces_f64_subset(pos, L, bc, idx, threads=threads)
+            assert np.array_equal(f, f64[idx])
+            assert np.array_equal(fterm, sc["fterm_sum"][idx])
+            assert (peabs >= np.abs(pe)).all()
+        # the per-particle potentials add up to V = 4/2 * sum_i pe_i (MDSystem.cpp:297,308)
+        _, _, pe_all, _ = oracle.forces_f64_subset(pos, L, bc, np.arange(N, dtype=np.int32))
+        assert abs(2.0 * pe_all.sum() - sc["V"]) <= 1e-12 * sc["Vabs"]

@@ -509,6 +509,56 @@ def test_long_run_statistics_match_reference(pkg, gpu_lib):
     assert abs(gs["av_p_tot"] - rs["av_p_tot"]) / nsteps <= 0.05 * max(1.0, abs(rs["av_p_tot"]) / nsteps)
 
 
+# ------------------------------------------------------------------ full-size forces: FP64 arbiter on a subsample
+def subsample_force_error(oracle, pos, L, bc, frc, nsample=512, seed=2024, interior=0.0):
+    """Worst per-particle force error (max-norm over the pair-term scale) and potential error of `nsample`
+    seeded particles against the FP64 arbiter evaluated over ALL N partners (oracle.forces_f64_subset)."""
+    N = pos.shape[0]
+    idx = np.sort(np.random.default_rng(seed).choice(N, size=min(nsample, N), replace=False)).astype(np.int32)
+    # always include the first / last particle and both sides of every 512-block seam near the middle
+    idx = np.unique(np.concatenate([idx, [0, N - 1, N // 2 - 1, N // 2, 511, 512]])).astype(np.int32)
+    if interior > 0.0:   # keep clear of the faces: a particle (or a near neighbour) that was wrapped by +-L in
+        # float after the force evaluation sits ulp(L)/2 away from where the force was computed
+        inside = ((pos[idx, :3] > interior) & (pos[idx, :3] < L - interior)).all(axis=1)
+        idx = idx[inside]
+    f64, fterm, pe, peabs = oracle.forces_f64_subset(pos, L, bc, idx)
+    err_f = np.abs(frc[idx, :3].astype(np.float64) - f64).max(axis=1) / fterm
+    err_w = np.abs(frc[idx, 3].astype(np.float64) - pe) / peabs
+    return err_f.max(), err_w.max(), len(idx)
+
+
+@pytest.mark.parametrize("config", ["C3", "C4", "C5"])
+def test_full_size_forces_subsample(pkg, oracle, gpu_lib, kernel, config):
+    """The three largest BASELINE configurations (C5 = the benchmark workload): per-particle force and potential
+    of 512+ seeded particles against the FP64 arbiter over all N partners, <= 1e-5 of the pair-term scale, under
+    the default, the ordered and the Newton-3 kernel.  (At N = 1M every force is a float sum of split rows and
+    reaction rows; this measures that error growth.)"""
+    if kernel == "default":
+        pytest.skip("default == sym at these sizes")
+    cfg = pkg.snapshots.CONFIGS[config]
+    N = cfg["N"]
+    pos, vel = pkg.snapshots.make(config)
+    with pkg.ljmd.LJSystem(N, T0=cfg["T"], rho=cfg["rho"], canonical=cfg["canonical"], bc=cfg["bc"]) as s:
+        assert s.launch_info()["newton3"] == (kernel == "sym")
+        s.set_state(pos, vel)
+        _, _, frc = s.get_state()
+        sc = s.scalars()
+        err_f, err_w, n = subsample_force_error(oracle, pos, s.L, cfg["bc"], frc)
+        assert err_f <= FORCE_TOL, f"{config} {kernel}: force error {err_f:.3e} on {n} particles"
+        if kernel == "ordered":   # the Newton-3 kernel books a pair's potential on its "i" side: only the sum compares
+            assert err_w <= SCALAR_TOL, f"{config} {kernel}: per-particle potential error {err_w:.3e}"
+        assert abs(2.0 * frc[:, 3].astype(np.float64).sum() - sc["V"]) <= 1e-6 * np.abs(frc[:, 3]).astype(np.float64).sum() * 2
+        # after a few steps (fused drift, reaction rows reused) the forces of the new positions still hold
+        s.step(0.004, 2)
+        p2, _, f2 = s.get_state()
+        err_f2, err_w2, _ = subsample_force_error(oracle, p2, s.L, cfg["bc"], f2, nsample=160, seed=7, interior=3.0)
+    # the positions the caller reads are wrapped once after the step; the force was evaluated before the wrap,
+    # which for a periodic box is the same minimum image (sample away from the faces, see `interior`)
+    assert err_f2 <= 2 * FORCE_TOL, f"{config} {kernel}: force error after 2 steps {err_f2:.3e}"
+    if kernel == "ordered":
+        assert err_w2 <= 2 * SCALAR_TOL
+
+
 # ------------------------------------------------------------------ full-size properties (no O(N^2) oracle)
 def test_full_size_properties_c3(pkg, gpu_lib):
     """N = 65 536 solid (C3): Newton's third law, RDF against the k-d-tree restatement (bit-exact),
