@@ -232,6 +232,11 @@ int ljmd_get_launch_info(ljmd_system* s, int* out8);
  *   out[6] = 1 when the Newton-3 kernel is used, out[7] = partner blocks per i-tile, for `num_sms` SMs. */
 float ljmd_image_threshold(double L, int k);
 int ljmd_plan(int N, int rank, int world, int num_sms, int* out8);
+/* Super-tile geometry of the Newton-3 kernel for the same arguments (csrc/ljmd_force_sym.cuh): out[0] = records per
+ *   unit (0: the ordered kernel is used), out[1] = i-tiles per super-tile, out[2] = units per window, out[3] =
+ *   windows per super-tile, out[4] = super-tiles of this rank, out[5] = launch-order shift of the windows,
+ *   out[6] = global number of 512-particle blocks, out[7] = first global block of this rank. */
+int ljmd_plan_newton3(int N, int rank, int world, int num_sms, int* out8);
 
 /*
  * Observation trace: everything the fluctuation tasks read after EVERY step,

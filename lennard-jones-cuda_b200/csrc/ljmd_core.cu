@@ -65,6 +65,8 @@ constexpr int kMinBlocks = 4;                 // resident CTAs/SM the ordered no
 constexpr int kSymMinBlocks = 3;              // Newton-3 kernel: 139 registers, 3 CTAs/SM measured 4 % faster than 4 (128 regs)
 constexpr int kMinBlocksRdf = 3;
 constexpr int kSymBJ = 256;                   // largest j-chunk (work unit) of the Newton-3 kernel; 128 or 64 for small N
+constexpr int kSymMaxMJU = 16;                // units per window: 16 x 256 records x 12 B = 48 KB of shared memory, 3 CTAs/SM
+constexpr int kSymMaxMI = 16;                 // i-tiles per super-tile
 constexpr int kSymMinBlocksN = 8;             // Newton-3 kernel from this many 512-particle blocks on (N = 4 096: 20.2 vs 22.0 us ordered)
 
 struct ljmd_system {
@@ -79,11 +81,12 @@ struct ljmd_system {
   int nsplit = 1, n_itiles = 1;
   int nblk = 1;     // global number of kITile-blocks
   int use_sym = 0;  // Newton-3 kernel (k_force_sym) instead of the ordered one (k_force)
-  int hmax = 0;     // partner offsets per i-tile (rows of the partner window)
+  int hmax = 0;     // partner offsets per i-tile
   int sym_bj = 256; // j-records per work unit of the Newton-3 kernel
+  int sym_mi = 1, sym_mju = 1, sym_nwin = 1, n_super = 1, sym_win_shift = 0;   // super-tile geometry (ljmd_force_sym.cuh)
   int gather_shift = 0;  // k_gather: 2^shift lanes per particle
   int pdl = 0;           // launch the step chain with programmatic dependent launch (one GPU)
-  float4* rpart = nullptr;   // [n_itiles][hmax*kITile] reaction rows
+  float4* rpart = nullptr;   // [n_super][sym_nwin][sym_mju*sym_bj] reaction sums of the super-tiles' windows
   float4* rsum = nullptr;    // [npad] rank-local column sums of the reaction rows (world > 1)
   float4* rshard = nullptr;  // [cnt]  reaction totals of this rank's particles after the reduce-scatter
   uint4* bbox = nullptr;     // [nblk][2] block bounding boxes (RDF pruning in the Newton-3 kernel)
@@ -183,34 +186,45 @@ static int choose_split(int n_itiles, long long work, int smax, int num_sms, int
 
 struct Plan {
   int nblk, bpr, cnt, i_begin, i_end, nloc, n_itiles, use_sym, hmax, nsplit, bj;
+  int mi, mju, nwin, n_super, win_shift;   // Newton-3 kernel: super-tile geometry (nsplit == nwin)
 };
 
-// Newton-3 kernel: an i-tile's work is `units` chunks of bj j-records that cannot be cut further; a CTA of a
-// split into S parts does ceil(units/S) of them.  Measured on the B200 (tools/tune_force N reps scan,
-// profiles/r01_tune_force_sym_split_scan.log): at every size from 8 192 to 131 072 particles the kernel gets
-// faster the MORE and SMALLER its CTAs are — down to one or two units per CTA — because the hardware block
-// scheduler then balances the SMs and the tail in which an SM runs a single CTA (one warp per scheduler, well
-// under half the issue rate) shrinks to one unit.  Few large CTAs sized to "whole waves" lost 5 % (65 536),
-// 16 % (32 768) and 15 % (16 384) against that.  So: aim for ~10 CTAs per slot, never fewer than ~4.5 per slot
-// (finer units instead: bj 128 or 64), and stop there — every split adds one row of partial forces that
-// k_gather has to read back (at 65 536: 65 splits 1.774 ms + 76 us of k_gather, 33 splits 1.788 ms + ~40 us).
-static void choose_sym_split(int n_itiles, int nblk, int num_sms, int nloc, int* out_s, int* out_bj) {
+// Newton-3 kernel: an i-tile's work is `units` chunks of bj j-records that cannot be cut further.  Measured on
+// the B200 (tools/tune_force N reps scan, profiles/r01_tune_force_sym_split_scan.log): at every size from 8 192
+// to 131 072 particles the kernel gets faster the MORE and SMALLER its CTAs are — down to one or two units per
+// CTA — because the hardware block scheduler then balances the SMs and the tail in which an SM runs a single CTA
+// (one warp per scheduler, well under half the issue rate) shrinks to one unit.  Few large CTAs sized to "whole
+// waves" lost 5 % (65 536), 16 % (32 768) and 15 % (16 384) against that.  So: aim for ~10 CTAs per slot, never
+// fewer than ~4.5 per slot (finer units instead: bj 128 or 64).  Large systems have units to spare: there a CTA
+// takes a super-tile of mi i-tiles x mju units (up to 16 x 16), which divides the partial-force and reaction
+// traffic by mju and mi, as long as ~32 CTAs per slot remain (tail under ~1.5 %).
+static void choose_sym_plan(int n_itiles, int nblk, int num_sms, Plan* pl) {
   const long long slots = (long long)num_sms * kSymMinBlocks;
   const long long want_lo = (9 * slots) / 2, want_hi = 10 * slots;
-  const int partners = sym_max_partner_count(nblk) + 1;
+  const int hmax = sym_max_partner_count(nblk);
+  const int partners = hmax + 1;
   int bj = kSymBJ;
   while (bj > 64 && (long long)n_itiles * partners * (kITile / bj) < want_lo) bj >>= 1;
-  const int units = partners * (kITile / bj);
+  const int cpb = kITile / bj;
+  const int units = partners * cpb;
   const long long total = (long long)n_itiles * units;
   int per_cta = (int)std::max<long long>(1, (total + want_hi - 1) / want_hi);
   // CTAs of 8+ units amortise their prologue and partial-force row: go on to ~60 CTAs per slot, which keeps the
   // tail (about half a CTA duration at low residency) under 1 % of the launch
   if (per_cta >= 8) per_cta = (int)std::max<long long>(8, (total + 60 * slots - 1) / (60 * slots));
-  int sp = (units + per_cta - 1) / per_cta;
-  sp = std::min(sp, 8 * num_sms);
-  while (sp > 1 && (double)sp * nloc * 16. > 1.5e9) --sp;   // partial-force buffer cap
-  *out_s = std::max(1, sp);
-  *out_bj = bj;
+  int mju = std::min(per_cta, kSymMaxMJU);
+  int mi = 1;
+  if (per_cta > mju) {
+    mi = (int)std::min<long long>(kSymMaxMI, total / ((long long)mju * 32 * slots));
+    mi = std::max(1, std::min(mi, std::min(n_itiles, nblk / 2)));
+  }
+  const int band = sym_band_units(mi, hmax, nblk, cpb);
+  pl->bj = bj; pl->mi = mi; pl->mju = mju;
+  pl->nwin = (band + mju - 1) / mju;
+  pl->n_super = (n_itiles + mi - 1) / mi;
+  // the first ceil((mi-1)*cpb / mju) windows are triangles (tile t starts at its own diagonal): launch them last
+  pl->win_shift = std::min(pl->nwin - 1, ((mi - 1) * cpb + mju - 1) / mju);
+  pl->nsplit = pl->nwin;
 }
 // Shards are whole kITile-blocks so that an i-tile never straddles two ranks (the Newton-3 block pairing
 // needs global block indices).  LJMD_KERNEL=ordered|sym overrides the kernel choice (force_ordered: internal).
@@ -231,9 +245,9 @@ static Plan make_plan(int N, int rank, int world, int num_sms, bool force_ordere
   if (force_ordered) pl.use_sym = 0;
   pl.hmax = std::max(1, sym_max_partner_count(pl.nblk));
   if (pl.nloc <= 0) { pl.nsplit = 0; return pl; }
-  pl.bj = kSymBJ;
+  pl.bj = kSymBJ; pl.mi = 1; pl.mju = 1; pl.nwin = 1; pl.n_super = pl.n_itiles; pl.win_shift = 0;
   if (pl.use_sym) {
-    choose_sym_split(pl.n_itiles, pl.nblk, num_sms, pl.cnt, &pl.nsplit, &pl.bj);
+    choose_sym_plan(pl.n_itiles, pl.nblk, num_sms, &pl);
   } else if (N <= 2048) {
     // small systems are latency-bound: a CTA's fixed cost is worth ~16-32 j-iterations, not the 128 of the wave
     // model, and the kernel keeps getting faster down to 16 j-records per CTA (tools/tune_force N reps
@@ -250,14 +264,16 @@ static StepParams make_step_params(ljmd_system* s, double dt) {
   StepParams p;
   memset(&p, 0, sizeof(p));
   p.N = s->N; p.nloc = s->nloc; p.i_begin = s->i_begin; p.bc = s->bc;
-  p.nsplit = s->nsplit; p.ilocal_cap = s->cnt; p.nforce_blocks = s->n_itiles * s->nsplit; p.world = s->world;
+  p.nsplit = s->nsplit; p.ilocal_cap = s->cnt; p.world = s->world;
+  p.nforce_blocks = (s->use_sym ? s->n_super : s->n_itiles) * s->nsplit;
   p.gather_shift = s->gather_shift;
   p.dt = dt; p.dt2 = dt * dt; p.L = s->L; p.rho = s->rho; p.T0 = s->T0;
   p.fix_scale = 4294967296.0 / s->L;
   p.pos = s->pos; p.posA = s->posA; p.upos = s->upos; p.vel = s->vel; p.force = s->force; p.tforce = s->tforce;
   p.fpart = s->fpart; p.blockW = s->blockW; p.part = s->part; p.counter = s->counter; p.sc = s->sc;
   p.use_sym = s->use_sym; p.nblk = s->nblk; p.blk0 = s->i_begin / kITile; p.n_itiles = s->n_itiles;
-  p.rp_stride = s->hmax * kITile; p.rpart = s->rpart; p.rsum = s->rsum; p.rshard = s->rshard; p.npad = s->npad;
+  p.rp_stride = s->sym_mju * s->sym_bj; p.sym_bj = s->sym_bj; p.sym_mi = s->sym_mi; p.sym_mju = s->sym_mju;
+  p.sym_nwin = s->sym_nwin; p.n_super = s->n_super; p.rpart = s->rpart; p.rsum = s->rsum; p.rshard = s->rshard; p.npad = s->npad;
   p.fab = s->fab;
   return p;
 }
@@ -301,12 +317,18 @@ template <bool PERIODIC, bool RDF>
 static cudaError_t launch_force_sym_t(ljmd_system* s, const SymParams& sp) {
   constexpr int MINB = RDF ? kMinBlocksRdf : kSymMinBlocks;
   auto kern = k_force_sym<P2, PERIODIC, RDF, kForceThreads, MINB, kNPair>;
-  const size_t smem = force_sym_smem_bytes(RDF, s->sym_bj, kForceThreads);
-  static_assert(2 * kSymBJ * 16 + (kForceThreads / 32) * (kSymBJ + 64) * 16 + 16 + 64 +
-                        (kForceThreads / 32) * (kRdfBins * 4 + kRdfQueueCap * 8) <= 48 * 1024,
-                "dynamic shared memory must stay under the 48 KB default (no per-device opt-in needed)");
-  dim3 grid(s->n_itiles, s->nsplit);
+  const size_t smem = force_sym_smem_bytes(RDF, s->sym_bj, kForceThreads, s->sym_mju);
+  dim3 grid(s->n_super, s->sym_nwin);
   return launch_k(s->pdl != 0, kern, grid, dim3(kForceThreads), smem, s->stream, sp);
+}
+// The window accumulator takes the Newton-3 kernel past the 48 KB default of dynamic shared memory: opt in once
+// per device, for the largest window the planner can choose.
+template <bool PERIODIC, bool RDF>
+static cudaError_t sym_smem_opt_in() {
+  constexpr int MINB = RDF ? kMinBlocksRdf : kSymMinBlocks;
+  auto kern = k_force_sym<P2, PERIODIC, RDF, kForceThreads, MINB, kNPair>;
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)force_sym_smem_bytes(RDF, kSymBJ, kForceThreads, kSymMaxMJU));
 }
 
 static int launch_force(ljmd_system* s, bool rdf) {
@@ -347,7 +369,8 @@ static int launch_force(ljmd_system* s, bool rdf) {
     SymParams sp;
     sp.f = fp;
     sp.f.tile_j = s->sym_bj;
-    sp.rpart = s->rpart; sp.ncols = s->hmax * kITile; sp.nblk = s->nblk; sp.bj = s->sym_bj;
+    sp.rpart = s->rpart; sp.ncols = 0; sp.nblk = s->nblk; sp.bj = s->sym_bj;
+    sp.mi = s->sym_mi; sp.mju = s->sym_mju; sp.nwin = s->sym_nwin; sp.win_shift = s->sym_win_shift;
     sp.bbox = bbox; sp.bbox_cut2 = (float)(cut * 1.002 + 1e-3);
     if (periodic) e = rdf ? launch_force_sym_t<true, true>(s, sp) : launch_force_sym_t<true, false>(s, sp);
     else e = rdf ? launch_force_sym_t<false, true>(s, sp) : launch_force_sym_t<false, false>(s, sp);
@@ -557,7 +580,17 @@ extern "C" int ljmd_plan(int N, int rank, int world, int num_sms, int* out8) {
     return set_err(LJMD_ERR_ARG, "bad arguments to ljmd_plan");
   const Plan pl = make_plan(N, rank, world, num_sms);
   out8[0] = pl.i_begin; out8[1] = pl.i_end; out8[2] = pl.n_itiles; out8[3] = pl.nsplit;
-  out8[4] = pl.n_itiles * pl.nsplit; out8[5] = kITile; out8[6] = pl.use_sym; out8[7] = pl.use_sym ? pl.hmax : 0;
+  out8[4] = (pl.use_sym ? pl.n_super : pl.n_itiles) * pl.nsplit; out8[5] = kITile; out8[6] = pl.use_sym;
+  out8[7] = pl.use_sym ? pl.hmax : 0;
+  return LJMD_OK;
+}
+
+extern "C" int ljmd_plan_newton3(int N, int rank, int world, int num_sms, int* out8) {
+  if (!out8 || N < 2 || world < 1 || rank < 0 || rank >= world || num_sms < 1)
+    return set_err(LJMD_ERR_ARG, "bad arguments to ljmd_plan_newton3");
+  const Plan pl = make_plan(N, rank, world, num_sms);
+  out8[0] = pl.use_sym ? pl.bj : 0; out8[1] = pl.mi; out8[2] = pl.mju; out8[3] = pl.nwin; out8[4] = pl.n_super;
+  out8[5] = pl.win_shift; out8[6] = pl.nblk; out8[7] = pl.i_begin / kITile;
   return LJMD_OK;
 }
 
@@ -620,6 +653,7 @@ static int create_impl(ljmd_system** out, int N, double rho_or_negL, double T0, 
     const Plan pl = make_plan(N, rank, world, sms);
     s->nblk = pl.nblk; s->cnt = pl.cnt; s->npad = pl.cnt * world; s->i_begin = pl.i_begin; s->i_end = pl.i_end;
     s->nloc = pl.nloc; s->n_itiles = pl.n_itiles; s->use_sym = pl.use_sym; s->hmax = pl.hmax; s->nsplit = pl.nsplit; s->sym_bj = pl.bj;
+    s->sym_mi = pl.mi; s->sym_mju = pl.mju; s->sym_nwin = pl.nwin; s->n_super = pl.n_super; s->sym_win_shift = pl.win_shift;
     s->num_sms = sms;
   }
   if (s->nloc < 1) { delete s; return set_err(LJMD_ERR_ARG, "rank %d of %d has no particles for N=%d", rank, world, N); }
@@ -669,26 +703,29 @@ static int create_impl(ljmd_system** out, int N, double rho_or_negL, double T0, 
   CUC(cudaMalloc(&s->force, (size_t)s->cnt * b16));
   CUC(cudaMalloc(&s->tforce, (size_t)s->cnt * b16));
   if (s->use_sym) {
-    // the reaction rows grow as N^2 / (1024 G) * 16 B: fall back to the ordered kernel when they would not fit
-    size_t free_b = 0, total_b = 0;
-    CUC(cudaMemGetInfo(&free_b, &total_b));
-    const size_t need = (size_t)s->n_itiles * s->hmax * kITile * b16;
-    if (need > free_b / 2) {
+    // Partial-force rows and reaction blocks grow as N^2 / G (divided by mju and mi): fall back to the ordered
+    // kernel when they would take more than 45 % of the device's memory.  The test depends on N, the rank count and
+    // the device model only — never on the momentary free memory — so every rank of a sharded system takes the
+    // same decision (a rank on its own kernel would miss the reaction exchange of its peers).
+    const size_t need = ((size_t)s->nsplit * s->cnt + (size_t)s->n_super * s->sym_nwin * s->sym_mju * s->sym_bj) * b16;
+    if ((double)need > 0.45 * (double)prop.totalGlobalMem) {
       s->use_sym = 0;
       const Plan po = make_plan_ordered(N, rank, world, s->num_sms);
       s->nsplit = po.nsplit;
     }
   }
   CUC(cudaMalloc(&s->fpart, (size_t)s->nsplit * s->cnt * b16));
-  CUC(cudaMalloc(&s->blockW, (size_t)s->n_itiles * s->nsplit * sizeof(double)));
+  CUC(cudaMalloc(&s->blockW, (size_t)std::max(s->n_itiles, s->n_super) * s->nsplit * sizeof(double)));
   if (s->use_sym) {
-    // reaction rows: one partner window (hmax blocks) per local i-tile; entries no unit ever writes
-    // (the antipodal block of the upper half, ragged last block) must read as zero forever
-    const size_t rp = (size_t)s->n_itiles * s->hmax * kITile * b16;
+    // every entry of rpart is rewritten by every launch (ljmd_force_sym.cuh): no clearing needed, ever
+    const size_t rp = (size_t)s->n_super * s->sym_nwin * s->sym_mju * s->sym_bj * b16;
     CUC(cudaMalloc(&s->rpart, rp));
-    CUC(cudaMemsetAsync(s->rpart, 0, rp, s->stream));
     if (world > 1) CUC(cudaMalloc(&s->rshard, (size_t)s->cnt * b16));
     CUC(cudaMalloc(&s->bbox, (size_t)s->nblk * 2 * sizeof(uint4)));
+    CUC((sym_smem_opt_in<true, false>()));
+    CUC((sym_smem_opt_in<true, true>()));
+    CUC((sym_smem_opt_in<false, false>()));
+    CUC((sym_smem_opt_in<false, true>()));
   }
   // lanes per particle in k_gather: enough threads to keep ~2 CTAs of 256 on every SM, never more lanes than
   // half the rows they share
@@ -698,7 +735,7 @@ static int create_impl(ljmd_system** out, int N, double rho_or_negL, double T0, 
   }
   s->gather_shift = 0;
   while (s->gather_shift < 3 && ((long long)s->nloc << s->gather_shift) < 2LL * kStepThreads * s->num_sms &&
-         (2 << s->gather_shift) * 2 <= s->nsplit + (s->use_sym ? s->hmax : 0))
+         (2 << s->gather_shift) * 2 <= s->nsplit + (s->use_sym ? (s->n_super + 1) / 2 : 0))
     s->gather_shift += 1;
   CUC(cudaMalloc(&s->part, (size_t)2 * (gather_grid(s) + 1) * sizeof(double)));
   CUC(cudaMalloc(&s->counter, sizeof(unsigned int)));
@@ -1354,8 +1391,10 @@ extern "C" int ljmd_last_gather_timing(ljmd_system* s, double* gather_ms, int* l
     // algorithmic bytes of one k_gather launch: per local particle it reads the S direct
     // partial rows, the reaction rows that target it (one per partner block, or one pre-reduced record per
     // rank when sharded), velocity and old force, and writes force plus t_Force (TVN) or velocity and position
+    // reaction blocks that cover a particle: the super-tiles whose band reaches its block
+    const double covering = std::min<double>(s->n_super, (double)(s->sym_mi + sym_max_partner_count(s->nblk)) / s->sym_mi);
     const double per_particle_reads =
-        16. * s->nsplit + (s->use_sym ? 16. * (s->world == 1 ? sym_max_partner_count(s->nblk) : s->world) : 0.) + 32.;
+        16. * s->nsplit + (s->use_sym ? 16. * (s->world == 1 ? covering : s->world) : 0.) + 32.;
     *bytes_per_launch = (per_particle_reads + 48.) * (double)s->nloc;
   }
   return LJMD_OK;
@@ -1364,7 +1403,7 @@ extern "C" int ljmd_last_gather_timing(ljmd_system* s, double* gather_ms, int* l
 extern "C" int ljmd_get_launch_info(ljmd_system* s, int* out8) {
   CHECK_S(s);
   if (!out8) return set_err(LJMD_ERR_ARG, "out8 is NULL");
-  out8[0] = s->num_sms; out8[1] = kITile; out8[2] = s->nsplit; out8[3] = s->n_itiles * s->nsplit;
+  out8[0] = s->num_sms; out8[1] = kITile; out8[2] = s->nsplit; out8[3] = (s->use_sym ? s->n_super : s->n_itiles) * s->nsplit;
   out8[4] = s->world; out8[5] = s->nloc; out8[6] = s->use_sym; out8[7] = s->use_sym ? s->sym_bj : kTileJ;
   return LJMD_OK;
 }

@@ -2,11 +2,21 @@
 // applied to both particles, which halves the pair evaluations of the reference's ordered double loop
 // (/root/reference/src/library/MDSystem.cpp:260-302, MDSystem.cu:60-111 evaluate (i,j) and (j,i)).
 //
-// Work decomposition (DESIGN.md §N3L): particles are cut in blocks of B = 2*NPAIR*THREADS.  Block I interacts
+// Work decomposition (DESIGN.md 4.2): particles are cut in blocks of B = 2*NPAIR*THREADS.  Block I interacts
 // with itself (ordered loop, self pair excluded) and with the next h blocks cyclically, h = (n-1)/2 (+ the
 // antipodal block for the lower half when the block count n is even): every unordered block pair appears
-// exactly once and every i-tile has the same amount of work.  A CTA owns one i-tile (its i-particles live in
-// registers, as in k_force) and a contiguous share of that tile's (partner block, j-chunk) units.
+// exactly once and every i-tile has the same amount of work.
+//
+// Super-tiles.  A CTA owns a SUPER-TILE: `mi` consecutive i-tiles of this rank (first global block I0) times a
+// WINDOW of `mju` consecutive j-units (chunks of bj records) counted from block I0: unit u covers records
+// [((I0 + u / cpb) mod n) * B + (u % cpb) * bj, +bj), cpb = B / bj.  Tile t of the super-tile (block I0 + t) owns
+// the units of blocks q = u / cpb with q == t (its diagonal) or 1 <= q - t <= partner_count(I0 + t).  The CTA
+// walks its tiles one after the other (i-particles in registers, as in k_force) and, inside a tile, the owned
+// units of its window; the reaction forces of the window's records accumulate in shared memory ACROSS the
+// tiles and leave the CTA once, as one block of rpart; the direct forces of a tile leave it once per window, as
+// one row segment of fpart.  Output per CTA is (mi*B + mju*bj) records for mi*B*mju*bj pair evaluations, so the
+// partial-force traffic and footprint fall as 1/mi + 1/mju (round 1 had mi = 1 and one reaction row per unit:
+// 17 GB at N = 1M; mi = 16, mju = 16: 3.3 GB).
 //
 // Reaction forces without atomics: inside a warp the 32 j-records of a chunk ROTATE through the lanes, so at
 // every step each lane works on a different j: lane l handles record (l + k) mod 32 at step k.  The record is
@@ -14,8 +24,8 @@
 // base + (l + k) with no wrap arithmetic and does not depend on the previous step; the three reaction
 // accumulators travel with their j through one shuffle each per step.  After 32 steps a packet is home and has
 // met all 32 lanes x 2*NPAIR i-particles; the warps' packets go to per-warp shared-memory slices, are summed in
-// warp order and written as one row of rpart[partner offset][j]; the gather kernel adds the rows in a fixed
-// order.  No floating-point atomics anywhere: runs are bit-reproducible.
+// warp order and added to the window's accumulator in tile order; the gather kernel adds the blocks of the
+// super-tiles in a fixed order.  No floating-point atomics anywhere: runs are bit-reproducible.
 // Measured alternatives at N = 65 536 periodic (profiles/r01_tune_force_sym_*.log): ordered kernel 2.82 ms;
 // rotating positions and accumulators by shuffle (6 SHFL per step) 1.92 ms; broadcast j + 5-level butterfly
 // sum of the reaction (15 SHFL + 15 FADD per j) 2.37 ms.
@@ -31,9 +41,8 @@ struct SymParams {
   char perturb_[LJMD_PERTURB];
 #endif
   ForceParams f;   // jrec, posf, fpart, blockW, rdf, N, i_begin (multiple of B), i_end, ilocal_cap, constants
-  float4* rpart;   // [local i-tiles][ncols] reaction rows (fx,fy,fz,0): row = i-tile of this rank, column =
-                   // (partner offset - 1) * B + index inside the partner block (the tile's partner window)
-  int ncols;       // row stride = hmax * B
+  float4* rpart;   // [super-tiles of this rank][nwin][mju * bj] reaction sums (fx,fy,fz,0) of the window's records
+  int ncols;       // unused (kept: the byte offsets of the fields below steer ptxas' schedule of the hot loop)
   int nblk;        // global number of blocks = ceil(N / B)
   int bj;          // j-records per unit (multiple of 32, divides B)
   // RDF pruning.  Appended here (not to ForceParams) so that every parameter offset the plain kernels read is
@@ -41,7 +50,21 @@ struct SymParams {
   float bbox_cut2;    // squared histogram range (real units, with margin) for the box-gap test
   const uint4* bbox;  // [nblk][2] per-block bounding boxes (lo.xyz, hi.xyz) or nullptr; periodic: fixed-point
                       // coordinates, open: float bits
+  // super-tile geometry (see the header comment)
+  int mi;          // i-tiles per super-tile
+  int mju;         // j-units per window
+  int nwin;        // windows per super-tile = gridDim.y
+  int win_shift;   // blockIdx.y -> window (blockIdx.y + win_shift) mod nwin: the partial windows at both ends of
+                   // the band are launched last, so the tail of the launch is made of the short CTAs
 };
+
+// Units of a super-tile's band: tile t = 0..mi-1 owns blocks q in [t, t + h_t] counted from the super-tile's
+// first block; q never reaches n (the planner keeps mi <= n/2), so a record appears at most once in the band.
+__host__ __device__ inline int sym_band_units(int mi, int hmax, int n, int cpb) {
+  int qmax = mi - 1 + hmax;
+  if (qmax > n - 1) qmax = n - 1;
+  return (qmax + 1) * cpb;
+}
 
 // number of partner offsets of global block g among n blocks
 __host__ __device__ inline int sym_partner_count(int g, int n) {
@@ -227,7 +250,8 @@ __device__ __forceinline__ void pair_sym(const uint4& uj, const PairI<V>& pi, Pa
           rjz = __shfl_sync(0xffffffffu, rjz, nxt_lane);                                                         \
         }                                                                                                        \
       }                                                                                                          \
-      myslice[jl] = make_float4(rjx, rjy, rjz, 0.f); /* the accumulators are home again; jl < BJ always */       \
+      /* the accumulators are home again; jl < BJ always.  12-byte entries: stride 3 words, conflict-free */     \
+      myslice[3 * jl] = rjx; myslice[3 * jl + 1] = rjy; myslice[3 * jl + 2] = rjz;                                \
     }                                                                                                            \
   }
 
@@ -242,24 +266,27 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int BJ = sp.bj;
+  const int MJU = sp.mju;
   uint4* tile_u = reinterpret_cast<uint4*>(smem_raw);  // [2][BJ]
   unsigned char* after_tiles = smem_raw + (size_t)2 * BJ * 16;
-  float4* slices = reinterpret_cast<float4*>(after_tiles);                     // [NW][BJ]
-  uint4* stage = reinterpret_cast<uint4*>(after_tiles + (size_t)NW * BJ * 16);  // [NW][64]
-  unsigned char* tail = after_tiles + (size_t)NW * BJ * 16 + (size_t)NW * 64 * 16;
+  uint4* stage = reinterpret_cast<uint4*>(after_tiles);                          // [NW][64]
+  float* slices = reinterpret_cast<float*>(after_tiles + (size_t)NW * 64 * 16);  // [NW][BJ][3]
+  float* racc = slices + (size_t)NW * BJ * 3;                                    // [MJU][BJ][3] window accumulator
+  unsigned char* tail = reinterpret_cast<unsigned char*>(racc + (size_t)MJU * BJ * 3);
+  tail += (16 - (reinterpret_cast<uintptr_t>(tail) & 15)) & 15;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);          // [2]
   double* red = reinterpret_cast<double*>(tail + 16);          // [NW]
   unsigned int* hist = reinterpret_cast<unsigned int*>(tail + 16 + 8 * NW);         // [NW][256] (RDF)
   uint2* queues = reinterpret_cast<uint2*>(tail + 16 + 8 * NW + NW * kRdfBins * 4);  // [NW][cap] (RDF)
 
-  const int ibase = p.i_begin + blockIdx.x * B;
-  const int gI = ibase / B;  // global block index (i_begin is a multiple of B)
   const int n = sp.nblk;
-  const int h = sym_partner_count(gI, n);
   const int cpb = B / BJ;
-  const int U = (h + 1) * cpb;  // off-diagonal units first, then the diagonal block's chunks
-  const int ub = (int)(((long long)U * blockIdx.y) / gridDim.y);
-  const int ue = (int)(((long long)U * (blockIdx.y + 1)) / gridDim.y);
+  const int ibase0 = p.i_begin + blockIdx.x * sp.mi * B;   // first particle of the super-tile
+  const int I0 = ibase0 / B;                               // its global block (i_begin is a multiple of B)
+  const int ntiles = min(sp.mi, (p.i_end - ibase0 + B - 1) / B);   // the rank's last super-tile may be short
+  int win = (int)blockIdx.y + sp.win_shift;
+  if (win >= sp.nwin) win -= sp.nwin;
+  const int u0 = win * MJU, u1 = u0 + MJU;                 // this CTA's window of the band, in units
 
   if (tid == 0) {
     mbar_init(&bars[0], 1);
@@ -269,40 +296,49 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
   if (RDF) {
     for (int k = tid; k < NW * kRdfBins; k += THREADS) hist[k] = 0u;
   }
+  for (int k = tid; k < MJU * BJ * 3; k += THREADS) racc[k] = 0.f;
   __syncthreads();
 
-  // unit -> (first j, count, partner offset or 0 for the diagonal)
-  auto unit_j0 = [&](int u, int& o) {
-    const int ob = u / cpb, q = u - ob * cpb;
-    o = (ob < h) ? ob + 1 : 0;
-    int J = gI + o;
+  // first record and record count of band unit u (0 when the unit lies beyond N: ragged last block)
+  auto unit_j0 = [&](int u) {
+    const int q = u / cpb;
+    int J = I0 + q;
     if (J >= n) J -= n;
-    return J * B + q * BJ;
+    return J * B + (u - q * cpb) * BJ;
   };
   auto unit_nj = [&](int j0) {
     const int blk_end = min(p.N, (j0 / B + 1) * B);
     return min(BJ, blk_end - j0);
   };
-  auto next_nonempty = [&](int u) {
-    while (u < ue) {
-      int o;
-      if (unit_nj(unit_j0(u, o)) > 0) break;
-      ++u;
+  // units of the window that tile t owns: blocks q in [t, t + partner_count(I0 + t)]
+  auto tile_ub = [&](int t) { return max(u0, t * cpb); };
+  auto tile_ue = [&](int t) {
+    int g = I0 + t;
+    if (g >= n) g -= n;
+    return min(u1, (t + sym_partner_count(g, n) + 1) * cpb);
+  };
+  // the CTA's work list: (tile, unit) in tile-major order, empty units skipped
+  auto advance = [&](int& t, int& u) {   // step to the next non-empty item at or after (t, u)
+    while (t < ntiles) {
+      const int ue = tile_ue(t);
+      while (u < ue && unit_nj(unit_j0(u)) <= 0) ++u;
+      if (u < ue) return;
+      ++t;
+      if (t < ntiles) u = tile_ub(t);
     }
-    return u;
   };
   auto issue = [&](int u, int st) {
-    int o;
-    const int j0 = unit_j0(u, o);
+    const int j0 = unit_j0(u);
     const uint32_t bytes = (uint32_t)unit_nj(j0) * 16u;
     mbar_expect_tx(&bars[st], bytes);
     bulk_g2s(tile_u + (size_t)st * BJ, p.jrec + j0, bytes, &bars[st]);
   };
 
-  int cur = next_nonempty(ub);
+  int ct = 0, cu = tile_ub(0);
+  advance(ct, cu);
   int nload = 0, ncons = 0;
-  if (cur < ue) {
-    if (tid == 0) issue(cur, 0);
+  if (ct < ntiles) {
+    if (tid == 0) issue(cu, 0);
     nload = 1;
   }
 
@@ -310,103 +346,153 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
   PairAcc<V> acc[NPAIR];
   V s6run[NPAIR], wrun[NPAIR], fxrun[NPAIR], fyrun[NPAIR], fzrun[NPAIR];
   const V zero2 = bc2<V>(0.f);
-  const bool all_valid = load_i_particles<V, PERIODIC, THREADS, NPAIR>(p, ibase, pi);
 #pragma unroll
   for (int q = 0; q < NPAIR; ++q) {
     acc[q].fx = acc[q].fy = acc[q].fz = acc[q].s6 = acc[q].w = zero2;
     s6run[q] = wrun[q] = fxrun[q] = fyrun[q] = fzrun[q] = zero2;
   }
-  // is every lane of this warp holding real particles? (warp-uniform choice of the unmasked fast path)
-  const bool warp_all_valid = __all_sync(0xffffffffu, all_valid);
   RdfCtx R;
   R.q = queues + warp * kRdfQueueCap;
   R.hist = hist + warp * kRdfBins;
   R.n = 0;
-  float4* myslice = slices + (size_t)warp * BJ;
+  float* myslice = slices + (size_t)warp * BJ * 3;
   uint4* mystage = stage + warp * 64;
-  uint4 my_lo = make_uint4(0u, 0u, 0u, 0u), my_hi = my_lo;   // bounding box of my own block (RDF pruning)
-  if (RDF && sp.bbox != nullptr) { my_lo = sp.bbox[2 * gI]; my_hi = sp.bbox[2 * gI + 1]; }
+  double wsum = 0.;
+  float4* out = p.fpart + (size_t)blockIdx.y * p.ilocal_cap;
 
-  while (cur < ue) {
-    const int nxt = next_nonempty(cur + 1);
-    if (nxt < ue) {
-      if (tid == 0) issue(nxt, nload & 1);
-      ++nload;
-    }
-    const int st = ncons & 1;
-    mbar_wait(&bars[st], (uint32_t)((ncons >> 1) & 1));
-    ++ncons;
-    int o;
-    const int j0 = unit_j0(cur, o);
-    const int nj = unit_nj(j0);
-    const uint4* tu = tile_u + (size_t)st * BJ;
-    float wgt;
-    if (o == 0) {
-      // ---- diagonal block: ordered loop over its own particles, self pair excluded ----
-      wgt = 1.f;
-      const int jrel0 = j0 - ibase - tid;
+  for (int t = 0; t < ntiles; ++t) {
+    // ---- tile t: its i-particles into registers
+    const int ibase = ibase0 + t * B;
+    int gI = I0 + t;
+    if (gI >= n) gI -= n;
+    const bool all_valid = load_i_particles<V, PERIODIC, THREADS, NPAIR>(p, ibase, pi);
+    // is every lane of this warp holding real particles? (warp-uniform choice of the unmasked fast path)
+    const bool warp_all_valid = __all_sync(0xffffffffu, all_valid);
+    uint4 my_lo = make_uint4(0u, 0u, 0u, 0u), my_hi = my_lo;   // bounding box of my own block (RDF pruning)
+    if (RDF && sp.bbox != nullptr) { my_lo = sp.bbox[2 * gI]; my_hi = sp.bbox[2 * gI + 1]; }
+
+    while (ct == t) {
+      const int cur = cu;
+      int nt = ct, nu = cu + 1;
+      advance(nt, nu);
+      if (nt < ntiles) {
+        if (tid == 0) issue(nu, nload & 1);
+        ++nload;
+      }
+      const int st = ncons & 1;
+      mbar_wait(&bars[st], (uint32_t)((ncons >> 1) & 1));
+      ++ncons;
+      const int j0 = unit_j0(cur);
+      const int nj = unit_nj(j0);
+      const bool diag = (cur / cpb == t);
+      const uint4* tu = tile_u + (size_t)st * BJ;
+      float wgt;
+      if (diag) {
+        // ---- diagonal block: ordered loop over its own particles, self pair excluded ----
+        wgt = 1.f;
+        const int jrel0 = j0 - ibase - tid;
 #pragma unroll 2
-      for (int j = 0; j < nj; ++j) {
-        const uint4 uj = tu[j];
-        const int jr = jrel0 + j;
+        for (int j = 0; j < nj; ++j) {
+          const uint4 uj = tu[j];
+          const int jr = jrel0 + j;
 #pragma unroll
-        for (int q = 0; q < NPAIR; ++q)
-          pair_body<V, PERIODIC, true, RDF>(uj, pi[q], acc[q], jr == (2 * q) * THREADS, jr == (2 * q + 1) * THREADS,
-                                            p, (unsigned)(j0 + j), R);
-      }
-    } else {
-      // ---- partner block: each unordered pair once, reaction accumulators travel with the rotating j ----
-      wgt = 2.f;
-      if (RDF) {
-        // bounding boxes of the two blocks farther apart than the histogram range: no pair of this unit can
-        // count, run the plain loop (uniform: every thread of the CTA sees the same two boxes)
-        bool near = true;
-        if (sp.bbox != nullptr) {
-          const int J = j0 / B;
-          near = boxes_in_range<PERIODIC>(my_lo, my_hi, sp.bbox[2 * J], sp.bbox[2 * J + 1], p.L, sp.bbox_cut2);
+          for (int q = 0; q < NPAIR; ++q)
+            pair_body<V, PERIODIC, true, RDF>(uj, pi[q], acc[q], jr == (2 * q) * THREADS, jr == (2 * q + 1) * THREADS,
+                                              p, (unsigned)(j0 + j), R);
         }
-        if (near) { LJMD_SYM_PARTNER_CHUNKS(true) } else { LJMD_SYM_PARTNER_CHUNKS(false) }
       } else {
-        LJMD_SYM_PARTNER_CHUNKS(false)
-      }
-    }
-    // fold the unit's tile-level accumulators into the run-level ones (two-level float summation);
-    // an unordered pair of a partner block stands for two ordered pairs in the potential / virial sums
-    const V w2 = bc2<V>(wgt);
-#pragma unroll
-    for (int q = 0; q < NPAIR; ++q) {
-      s6run[q] = fma2(acc[q].s6, w2, s6run[q]);
-      wrun[q] = fma2(acc[q].w, w2, wrun[q]);
-      fxrun[q] = add2(fxrun[q], acc[q].fx);
-      fyrun[q] = add2(fyrun[q], acc[q].fy);
-      fzrun[q] = add2(fzrun[q], acc[q].fz);
-      acc[q].s6 = acc[q].w = acc[q].fx = acc[q].fy = acc[q].fz = zero2;
-    }
-    __syncthreads();  // slices complete; stage st free for the load after next
-    if (o != 0) {
-      // reaction row of this unit: sum the warps' slices in warp order, scale, one coalesced store per j
-      float4* row = sp.rpart + (size_t)blockIdx.x * sp.ncols + (size_t)(o - 1) * B + (j0 % B);
-      const float fs = p.fscale;
-      for (int jj = tid; jj < nj; jj += THREADS) {
-        float4 a = slices[jj];
-#pragma unroll
-        for (int w = 1; w < NW; ++w) {
-          const float4 b = slices[(size_t)w * BJ + jj];
-          a.x += b.x; a.y += b.y; a.z += b.z;
+        // ---- partner block: each unordered pair once, reaction accumulators travel with the rotating j ----
+        wgt = 2.f;
+        if (RDF) {
+          // bounding boxes of the two blocks farther apart than the histogram range: no pair of this unit can
+          // count, run the plain loop (uniform: every thread of the CTA sees the same two boxes)
+          bool near = true;
+          if (sp.bbox != nullptr) {
+            const int J = j0 / B;
+            near = boxes_in_range<PERIODIC>(my_lo, my_hi, sp.bbox[2 * J], sp.bbox[2 * J + 1], p.L, sp.bbox_cut2);
+          }
+          if (near) { LJMD_SYM_PARTNER_CHUNKS(true) } else { LJMD_SYM_PARTNER_CHUNKS(false) }
+        } else {
+          LJMD_SYM_PARTNER_CHUNKS(false)
         }
-        row[jj] = make_float4(a.x * fs, a.y * fs, a.z * fs, 0.f);
       }
-      __syncthreads();  // slices are rewritten by the next partner unit
+      // fold the unit's tile-level accumulators into the run-level ones (two-level float summation);
+      // an unordered pair of a partner block stands for two ordered pairs in the potential / virial sums
+      const V w2 = bc2<V>(wgt);
+#pragma unroll
+      for (int q = 0; q < NPAIR; ++q) {
+        s6run[q] = fma2(acc[q].s6, w2, s6run[q]);
+        wrun[q] = fma2(acc[q].w, w2, wrun[q]);
+        fxrun[q] = add2(fxrun[q], acc[q].fx);
+        fyrun[q] = add2(fyrun[q], acc[q].fy);
+        fzrun[q] = add2(fzrun[q], acc[q].fz);
+        acc[q].s6 = acc[q].w = acc[q].fx = acc[q].fy = acc[q].fz = zero2;
+      }
+      __syncthreads();  // slices complete; stage st free for the load after next
+      if (!diag) {
+        // reaction of this unit: sum the warps' slices in warp order, add to the window accumulator
+        float* ra = racc + (size_t)(cur - u0) * BJ * 3;
+        for (int k = tid; k < nj * 3; k += THREADS) {
+          float a = slices[k];
+#pragma unroll
+          for (int w = 1; w < NW; ++w) a += slices[(size_t)w * BJ * 3 + k];
+          ra[k] += a;
+        }
+        __syncthreads();  // slices are rewritten by the next partner unit
+      }
+      ct = nt;
+      cu = nu;
     }
-    cur = nxt;
+    // ---- tile t done for this window: its partial forces leave the CTA (zeros when it owned no unit here)
+    {
+      const float fs = p.fscale;
+#pragma unroll
+      for (int q = 0; q < NPAIR; ++q) {
+        const float2 fx = upk(fxrun[q]), fy = upk(fyrun[q]), fz = upk(fzrun[q]);
+        const float2 s6 = upk(s6run[q]), w = upk(wrun[q]);
+        const int il = (ibase - p.i_begin) + (2 * q) * THREADS + tid;
+        // r^-12 - r^-6 = u/12 - r^-6/2
+        if (pi[q].v_lo) {
+          out[il] = make_float4(fx.x * fs, fy.x * fs, fz.x * fs, w.x * (1.f / 12.f) - 0.5f * s6.x);
+          wsum += (double)w.x;
+        }
+        if (pi[q].v_hi) {
+          out[il + THREADS] = make_float4(fx.y * fs, fy.y * fs, fz.y * fs, w.y * (1.f / 12.f) - 0.5f * s6.y);
+          wsum += (double)w.y;
+        }
+        s6run[q] = wrun[q] = fxrun[q] = fyrun[q] = fzrun[q] = zero2;
+      }
+    }
   }
 
-  force_epilogue<V, PERIODIC, RDF, THREADS, NPAIR>(p, ibase, pi, fxrun, fyrun, fzrun, s6run, wrun, red, hist, R);
+  // ---- the window's reaction sums leave the CTA: one block of rpart, every entry written (zeros included),
+  // so the gather kernels never read stale data and nothing has to be cleared between steps
+  {
+    float4* dst = sp.rpart + ((size_t)blockIdx.x * sp.nwin + win) * ((size_t)MJU * BJ);
+    const float fs = p.fscale;
+    for (int k = tid; k < MJU * BJ; k += THREADS)
+      dst[k] = make_float4(racc[3 * k] * fs, racc[3 * k + 1] * fs, racc[3 * k + 2] * fs, 0.f);
+  }
+  const double wtot = block_sum<THREADS>(wsum, red);
+  if (tid == 0) p.blockW[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = wtot;
+  if (RDF) {
+    rdf_drain<PERIODIC>(R, p, true);
+    __syncthreads();
+    for (int b = tid; b < kRdfBins; b += THREADS) {
+      unsigned int c = 0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) c += hist[w * kRdfBins + b];
+      if (c) atomicAdd(&p.rdf[b], (unsigned long long)c);
+    }
+  }
 }
 #undef LJMD_SYM_PARTNER_CHUNKS
 
-inline size_t force_sym_smem_bytes(bool rdf, int bj, int threads) {
-  return (size_t)2 * bj * 16 + (size_t)(threads / 32) * (bj + 64) * 16 + 16 + 8 * (threads / 32) +
+inline size_t force_sym_smem_bytes(bool rdf, int bj, int threads, int mju) {
+  const int nw = threads / 32;
+  // j-chunk double buffer, per-warp rotation stages, per-warp reaction slices (12 B), window accumulator (12 B),
+  // alignment slack, barriers, block-sum scratch, RDF scratch
+  return (size_t)2 * bj * 16 + (size_t)nw * 64 * 16 + (size_t)nw * bj * 12 + (size_t)mju * bj * 12 + 16 + 16 + 8 * nw +
          (rdf ? rdf_smem_bytes(threads) : 0);
 }
 

@@ -70,9 +70,14 @@ struct StepParams {
   int nblk;         // global number of 512-particle blocks
   int blk0;         // global index of this rank's first block
   int n_itiles;     // i-tiles (rows) of this rank
-  int rp_stride;    // row stride of rpart = hmax * 512
+  int rp_stride;    // records per rpart block = sym_mju * sym_bj
+  int sym_bj;       // j-records per unit of the Newton-3 kernel
+  int sym_mi;       // i-tiles per super-tile
+  int sym_mju;      // units per window
+  int sym_nwin;     // windows per super-tile
+  int n_super;      // super-tiles of this rank
   int npad;         // padded particle count (world * shard capacity)
-  const float4* rpart;    // [n_itiles][rp_stride]
+  const float4* rpart;    // [n_super][sym_nwin][rp_stride]
   float4* rsum;           // [npad] rank-local column sums (world > 1)
   const float4* rshard;   // [nloc] reaction totals after the reduce-scatter (world > 1, NCCL path)
   Fabric fab;             // peer windows (world > 1, fabric path)
@@ -85,21 +90,28 @@ __host__ __device__ inline int partner_count(int g, int n) {
   return n / 2 - 1 + (g < n / 2 ? 1 : 0);
 }
 
-// Sum of the reaction rows that hold contributions for global particle j (block J = j / 512): the i-tile of
-// global block gI = J - o (mod n) wrote its reaction on J at window slot o - 1 when o <= partner_count(gI).
-// Walks the partner offsets in ascending order (fixed order: deterministic), four loads in flight.
-__device__ __forceinline__ float4 reaction_sum(const StepParams& p, int j, int first = 1, int stride = 1) {
+// Sum of the reaction blocks that hold contributions for global particle j (block J = j / 512).  Super-tile a of
+// this rank (first global block I0 = blk0 + a * mi) accumulated the reaction on J in band unit
+// u = ((J - I0) mod n) * cpb + jj / bj when u lies inside its band (ljmd_force_sym.cuh); every entry of a band is
+// written on every launch (zeros included).  Walks the super-tiles in ascending order (fixed order:
+// deterministic), several loads in flight.
+__device__ __forceinline__ float4 reaction_sum(const StepParams& p, int j, int first = 0, int stride = 1) {
   const int J = j / kBlockParticles, jj = j - J * kBlockParticles;
   const int n = p.nblk;
-  const int omax = (n & 1) ? (n - 1) / 2 : n / 2;
+  const int hmax = (n & 1) ? (n - 1) / 2 : n / 2;
+  const int cpb = kBlockParticles / p.sym_bj;
+  int qmax = p.sym_mi - 1 + hmax;
+  if (qmax > n - 1) qmax = n - 1;
+  const int c = jj / p.sym_bj, jr = jj - c * p.sym_bj;
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
-  for (int o = first; o <= omax; o += stride) {   // (first, stride): this lane's share when several lanes split a particle
-    int gI = J - o;
-    if (gI < 0) gI += n;
-    const int t = gI - p.blk0;
-    if (t >= 0 && t < p.n_itiles && o <= partner_count(gI, n)) {
-      const float4 g = p.rpart[(size_t)t * p.rp_stride + (size_t)(o - 1) * kBlockParticles + jj];
+  for (int t = first; t < p.n_super; t += stride) {   // (first, stride): this lane's share when several lanes split a particle
+    int q = J - (p.blk0 + t * p.sym_mi);
+    if (q < 0) q += n;
+    if (q <= qmax) {
+      const int u = q * cpb + c;
+      const int w = u / p.sym_mju;
+      const float4 g = p.rpart[((size_t)t * p.sym_nwin + w) * p.rp_stride + (size_t)(u - w * p.sym_mju) * p.sym_bj + jr];
       a.x += g.x; a.y += g.y; a.z += g.z;
     }
   }
@@ -318,7 +330,7 @@ __global__ void __launch_bounds__(kStepThreads) k_gather(const StepParams p, int
       f.x += g.x; f.y += g.y; f.z += g.z; f.w += g.w;
     }
     // Newton-3 kernel, one GPU: the reaction of every pair this particle was the j of
-    if (p.use_sym && p.world == 1) rr = reaction_sum(p, p.i_begin + il, 1 + r, R);
+    if (p.use_sym && p.world == 1) rr = reaction_sum(p, p.i_begin + il, r, R);
   }
   for (int o = 1; o < R; o <<= 1) {
     f.x += __shfl_xor_sync(0xffffffffu, f.x, o); f.y += __shfl_xor_sync(0xffffffffu, f.y, o);

@@ -26,7 +26,7 @@ API_SYMBOLS = [
     "ljmd_get_scalars", "ljmd_reset_averaging", "ljmd_get_rdf", "ljmd_get_rdf_accum", "ljmd_velocity_histogram", "ljmd_subvolume_counts", "ljmd_velocity_subvolume_counts",
     "ljmd_trace_begin", "ljmd_trace_row_length", "ljmd_trace_read", "ljmd_trace_end",
     "ljmd_launch_count", "ljmd_set_event_timing", "ljmd_last_step_timing", "ljmd_last_gather_timing", "ljmd_get_launch_info",
-    "ljmd_image_threshold", "ljmd_plan", "ljmd_set_l2_flush",
+    "ljmd_image_threshold", "ljmd_plan", "ljmd_plan_newton3", "ljmd_set_l2_flush",
     # legacy seam (MDSystem.cpp:9-25)
     "allocateArray", "deleteArray", "copyArrayToDevice", "copyArrayFromDevice", "calculateNForces", "threadExit",
     "allocateNBodyArrays", "deleteNBodyArrays", "registerGLBufferObject", "unregisterGLBufferObject", "threadSync",
@@ -372,6 +372,16 @@ def plan(N, rank=0, world=1, num_sms=148):
         raise LJMDError(lib.ljmd_last_error().decode())
     return dict(i_begin=buf[0], i_end=buf[1], i_tiles=buf[2], j_splits=buf[3], force_ctas=buf[4], i_tile=buf[5],
                 newton3=bool(buf[6]), partner_blocks=buf[7])
+
+
+def plan_newton3(N, rank=0, world=1, num_sms=148):
+    """Super-tile geometry of the Newton-3 kernel (host logic only; no device needed)."""
+    lib = load_library()
+    buf = (C.c_int * 8)()
+    rc = lib.ljmd_plan_newton3(int(N), int(rank), int(world), int(num_sms), buf)
+    if rc != 0:
+        raise LJMDError(lib.ljmd_last_error().decode())
+    return dict(bj=buf[0], mi=buf[1], mju=buf[2], nwin=buf[3], n_super=buf[4], win_shift=buf[5], nblk=buf[6], blk0=buf[7])
 
 
 def rdf_curve(N, L, dr2, counts):

@@ -84,15 +84,102 @@ def test_launch_plan_tiles_the_problem(pkg, N, world):
         assert p["i_tiles"] * p["i_tile"] >= n_loc > (p["i_tiles"] - 1) * p["i_tile"]
         assert 1 <= p["j_splits"] <= max(1, N // 8)
         assert p["newton3"] == (N >= 8 * 512 - 511)
-        assert p["force_ctas"] == p["i_tiles"] * p["j_splits"]
+        if p["newton3"]:
+            g = pkg.ljmd.plan_newton3(N, r, world, 148)
+            assert p["j_splits"] == g["nwin"] and p["force_ctas"] == g["n_super"] * g["nwin"]
+            assert g["n_super"] == -(-p["i_tiles"] // g["mi"]) and 1 <= g["mi"] <= max(1, g["nblk"] // 2)
+        else:
+            assert p["force_ctas"] == p["i_tiles"] * p["j_splits"]
         if p["newton3"]:
             # many small CTAs (measured optimum, profiles/r01_tune_force_sym_split_scan.log): at least ~4.5 per
             # resident slot so the hardware scheduler can balance the SMs, at most ~60 so the partial-force rows
             # k_gather reads back stay a small fraction of the step
             slots = 148 * 3
             assert 4.4 * slots <= p["force_ctas"] <= 61 * slots
-            assert p["j_splits"] * n_loc * 16 <= 1.5e9
+            # partial-force rows + reaction blocks of the super-tiles: a few GB at N = 1M on one GPU (round 1: 17 GB)
+            cnt = -(-g["nblk"] // world) * 512
+            assert (g["nwin"] * cnt + g["n_super"] * g["nwin"] * g["mju"] * g["bj"]) * 16 <= 4.0e9
     assert covered == N
+
+
+def _partner_count(g, n):
+    return (n - 1) // 2 if n & 1 else n // 2 - 1 + (1 if g < n // 2 else 0)
+
+
+@pytest.mark.parametrize("N,world,sms", [(4096, 1, 148), (5000, 1, 148), (16384, 1, 148), (65536, 1, 148), (65536, 2, 148),
+                                         (100003, 3, 148), (262144, 8, 148), (1048576, 1, 148), (1048576, 8, 148),
+                                         (524288, 1, 16)])
+def test_newton3_super_tiles_cover_every_block_pair_once(pkg, N, world, sms):
+    """Python model of the work list of k_force_sym (csrc/ljmd_force_sym.cuh) and of reaction_sum
+    (csrc/ljmd_step.cuh) for the planner's geometry: every unordered pair of 512-blocks is evaluated by exactly one
+    CTA unit-by-unit, every block's diagonal once, and the gather finds, for every (block, chunk), exactly the
+    reaction entries of the blocks that own it — all of them inside blocks the force kernel writes."""
+    B = 512
+    n = -(-N // B)
+    done = {}                 # (I, J) -> set of chunks of J processed with I's particles in registers
+    racc = {}                 # (rank, super, window, slot) -> set of (I, J, chunk)
+    geo = []
+    for r in range(world):
+        g = pkg.ljmd.plan_newton3(N, r, world, sms)
+        p = pkg.ljmd.plan(N, r, world, sms)
+        geo.append((g, p))
+        if p["i_end"] == p["i_begin"]:
+            continue
+        assert g["bj"] in (64, 128, 256) and g["nblk"] == n
+        cpb = B // g["bj"]
+        for a in range(g["n_super"]):
+            I0 = g["blk0"] + a * g["mi"]
+            ibase0 = p["i_begin"] + a * g["mi"] * B
+            ntiles = min(g["mi"], -(-(p["i_end"] - ibase0) // B))
+            for by in range(g["nwin"]):
+                win = (by + g["win_shift"]) % g["nwin"]
+                for slot in range(g["mju"]):
+                    racc[(r, a, win, slot)] = set()
+                for t in range(ntiles):
+                    gI = (I0 + t) % n
+                    ub = max(win * g["mju"], t * cpb)
+                    ue = min((win + 1) * g["mju"], (t + _partner_count(gI, n) + 1) * cpb)
+                    for u in range(ub, ue):
+                        q = u // cpb
+                        assert q < n
+                        J = (I0 + q) % n
+                        c = u % cpb
+                        if min(g["bj"], min(N, (J + 1) * B) - (J * B + c * g["bj"])) <= 0:
+                            continue
+                        assert (J == gI) == (q == t)
+                        key = (gI, J)
+                        assert c not in done.setdefault(key, set()), "a unit is evaluated twice"
+                        done[key].add(c)
+                        if J != gI:
+                            racc[(r, a, win, u - win * g["mju"])].add((gI, J, c))
+    # coverage: the diagonal of every block, and every unordered pair under exactly one of its two orders
+    bj = geo[0][0]["bj"]
+    cpb = B // bj
+
+    def chunks(J):
+        return {c for c in range(cpb) if min(N, (J + 1) * B) - (J * B + c * bj) > 0}
+    for I in range(n):
+        assert done.get((I, I)) == chunks(I)
+        for J in range(I + 1, n):
+            a_, b_ = done.get((I, J)), done.get((J, I))
+            assert (a_ is None) != (b_ is None), (I, J)
+            assert (a_ == chunks(J)) if a_ is not None else (b_ == chunks(I))
+    # the gather's index arithmetic (reaction_sum)
+    hmax = (n - 1) // 2 if n & 1 else n // 2
+    for J in range(0, n, max(1, n // 61)):
+        for c in chunks(J):
+            found = set()
+            for r, (g, p) in enumerate(geo):
+                if p["i_end"] == p["i_begin"]:
+                    continue
+                qmax = min(g["mi"] - 1 + hmax, n - 1)
+                for t in range(g["n_super"]):
+                    q = (J - (g["blk0"] + t * g["mi"])) % n
+                    if q <= qmax:
+                        u = q * cpb + c
+                        w = u // g["mju"]
+                        found |= racc[(r, t, w, u - w * g["mju"])]       # KeyError = the kernel never writes it
+            assert found == {(I, J, c) for I in range(n) if I != J and (I, J) in done}
 
 
 def _emulate_image(d, L, thr1, thr2):

@@ -113,6 +113,7 @@ struct Problem {
   uint4* bbox;     // [n][2] block bounding boxes
   int hmax;
   int sms;
+  size_t fpart_elems, rpart_elems;   // capacity of the scratch buffers, in float4 records
 };
 
 static int pick_split(int n_it, int N, int sms, int minb) {
@@ -193,29 +194,33 @@ static void run_variant(const Problem& pb, const char* tag, int reps, int tile_j
   fflush(stdout);
 }
 
+// mju: units per window, mi: i-tiles per super-tile (0: pick like the library's planner for this N)
 template <typename V, bool PERIODIC, bool RDF, int THREADS, int MINB, int NPAIR, int UNROLLK = 4>
 static void run_sym(const Problem& pb, const char* tag, int reps, int bj, std::vector<float4>* keep,
-                    bool prune = true, int force_S = 0) {
+                    bool prune = true, int mju = 0, int mi = 1) {
   auto kern = k_force_sym<V, PERIODIC, RDF, THREADS, MINB, NPAIR, UNROLLK>;
-  const size_t smem = force_sym_smem_bytes(RDF, bj, THREADS);
+  const int B = THREADS * 2 * NPAIR;
+  const int n = (pb.N + B - 1) / B;
+  const int cpb = B / bj;
+  const int hmax = std::max(1, sym_max_partner_count(n));
+  const int units = (hmax + 1) * cpb;
+  if (mju <= 0) {   // ~10 CTAs per slot, as the library
+    const long long slots = (long long)pb.sms * MINB;
+    const long long total = (long long)n * units;
+    int per = (int)std::max<long long>(1, (total + 10 * slots - 1) / (10 * slots));
+    if (per >= 8) per = (int)std::max<long long>(8, (total + 60 * slots - 1) / (60 * slots));
+    mju = std::min(per, 16);
+  }
+  mi = std::max(1, std::min(mi, n / 2));
+  const int band = sym_band_units(mi, hmax, n, cpb);
+  const int nwin = (band + mju - 1) / mju;
+  const int nsup = (n + mi - 1) / mi;
+  const size_t smem = force_sym_smem_bytes(RDF, bj, THREADS, mju);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaFuncAttributes fa;
   CK(cudaFuncGetAttributes(&fa, kern));
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
-  const int B = THREADS * 2 * NPAIR;
-  const int n = (pb.N + B - 1) / B;
-  const int units = (sym_max_partner_count(n) + 1) * (B / bj);
-  // splits: fill the machine with whole waves of equal-work CTAs
-  const long long slots = (long long)pb.sms * (occ > 0 ? occ : MINB);
-  int S = 1;
-  double bc = 1e300;
-  for (int s = 1; s <= units; ++s) {
-    const long long waves = ((long long)n * s + slots - 1) / slots;
-    const double cost = (double)waves * (ceil((double)units / s) + 0.5);
-    if (cost < bc * 0.999) { bc = cost; S = s; }
-  }
-  if (force_S > 0) S = force_S;
   SymParams sp;
   memset(&sp, 0, sizeof(sp));
   ForceParams& fp = sp.f;
@@ -234,14 +239,19 @@ static void run_sym(const Problem& pb, const char* tag, int reps, int bj, std::v
     CK(cudaGetLastError());
     sp.bbox = pb.bbox;
   }
-  const int hmax = std::max(1, sym_max_partner_count(n));
-  sp.rpart = pb.rpart; sp.ncols = hmax * B; sp.nblk = n; sp.bj = bj;
-  dim3 grid(n, S);
+  sp.rpart = pb.rpart; sp.ncols = 0; sp.nblk = n; sp.bj = bj;
+  sp.mi = mi; sp.mju = mju; sp.nwin = nwin; sp.win_shift = std::min(nwin - 1, ((mi - 1) * cpb + mju - 1) / mju);
+  const size_t rp_elems = (size_t)nsup * nwin * mju * bj;
+  if ((size_t)nwin * pb.N > pb.fpart_elems || rp_elems > pb.rpart_elems) {
+    printf("sym   %-44s skipped: needs %zu + %zu records of scratch\n", tag, (size_t)nwin * pb.N, rp_elems);
+    return;
+  }
+  dim3 grid(nsup, nwin);
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
-  const size_t rp_elems = (size_t)n * std::max(1, sym_max_partner_count(n)) * B;
-  CK(cudaMemset(pb.rpart, 0, rp_elems * 16));
+  CK(cudaMemset(pb.rpart, 0xff, rp_elems * 16));   // NaN fill: the kernel must write every entry the gather reads
+  CK(cudaMemset(pb.fpart, 0xff, (size_t)nwin * pb.N * 16));
   CK(cudaMemset(pb.rdf, 0, 256 * 8));
   kern<<<grid, THREADS, smem>>>(sp);
   CK(cudaGetLastError());
@@ -262,38 +272,41 @@ static void run_sym(const Problem& pb, const char* tag, int reps, int bj, std::v
   }
   const double pairs = (double)pb.N * (pb.N - 1);
   const double flop = PERIODIC ? 37. : 25.;
-  std::vector<float4> h((size_t)S * pb.N), hr(rp_elems);
-  CK(cudaMemcpy(h.data(), pb.fpart, h.size() * 16, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(hr.data(), pb.rpart, hr.size() * 16, cudaMemcpyDeviceToHost));
   double maxdiff = 0., scale = 0., maxw = 0.;
-  for (int i = 0; i < pb.N; ++i) {
-    float4 a = h[i];
-    for (int s = 1; s < S; ++s) { float4 g = h[(size_t)s * pb.N + i]; a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w; }
-    {
-      const int J = i / B, jj = i % B;
-      for (int I = 0; I < n; ++I) {
-        int o = J - I;
-        if (o < 0) o += n;
-        if (o >= 1 && o <= sym_partner_count(I, n)) {
-          float4 g = hr[(size_t)I * hmax * B + (size_t)(o - 1) * B + jj];
+  if (pb.N <= 262144) {   // host-side gather of the partial rows and reaction blocks (the library's index rule)
+    std::vector<float4> h((size_t)nwin * pb.N), hr(rp_elems);
+    CK(cudaMemcpy(h.data(), pb.fpart, h.size() * 16, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hr.data(), pb.rpart, hr.size() * 16, cudaMemcpyDeviceToHost));
+    int qmax = mi - 1 + hmax;
+    if (qmax > n - 1) qmax = n - 1;
+    for (int i = 0; i < pb.N; ++i) {
+      float4 a = h[i];
+      for (int s = 1; s < nwin; ++s) { float4 g = h[(size_t)s * pb.N + i]; a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w; }
+      const int J = i / B, jj = i % B, c = jj / bj, jr = jj % bj;
+      for (int t = 0; t < nsup; ++t) {
+        int q = J - t * mi;
+        if (q < 0) q += n;
+        if (q <= qmax) {
+          const int u = q * cpb + c, w = u / mju;
+          float4 g = hr[((size_t)t * nwin + w) * ((size_t)mju * bj) + (size_t)(u - w * mju) * bj + jr];
           a.x += g.x; a.y += g.y; a.z += g.z;
         }
       }
+      if (!keep->empty()) {
+        double d = std::max(std::max(fabs((double)a.x - (*keep)[i].x), fabs((double)a.y - (*keep)[i].y)), fabs((double)a.z - (*keep)[i].z));
+        if (!(d == d)) d = 1e30;   // NaN: an entry nobody wrote
+        maxdiff = std::max(maxdiff, d);
+        scale = std::max(scale, (double)fabsf((*keep)[i].x));
+      }
+      maxw += a.w;
     }
-    if (!keep->empty()) {
-      maxdiff = std::max(maxdiff, (double)fabsf(a.x - (*keep)[i].x));
-      maxdiff = std::max(maxdiff, (double)fabsf(a.y - (*keep)[i].y));
-      maxdiff = std::max(maxdiff, (double)fabsf(a.z - (*keep)[i].z));
-      scale = std::max(scale, (double)fabsf((*keep)[i].x));
-    }
-    maxw += a.w;
   }
   double wref = 0.;
   for (int i = 0; i < pb.N && !keep->empty(); ++i) wref += (*keep)[i].w;
-  printf("sym   %-44s regs %3d occ %d grid %4dx%-3d smem %6zu | best %8.4f ms avg %8.4f ms | %7.3f Gpairs/s %6.2f TFLOP/s(alg) "
-         "| maxdiff %.2e/%.2e sum_pe %.6e vs %.6e",
-         tag, fa.numRegs, occ, n, S, smem, best, sum / reps, pairs / (best * 1e-3) / 1e9,
-         pairs * flop / (best * 1e-3) / 1e12, maxdiff, scale, maxw, wref);
+  printf("sym   %-44s regs %3d occ %d grid %4dx%-3d mi %2d mju %2d smem %6zu | best %8.4f ms avg %8.4f ms | %7.3f Gpairs/s %6.2f TFLOP/s(alg) "
+         "| out %.3f GB | maxdiff %.2e/%.2e sum_pe %.6e vs %.6e",
+         tag, fa.numRegs, occ, nsup, nwin, mi, mju, smem, best, sum / reps, pairs / (best * 1e-3) / 1e9,
+         pairs * flop / (best * 1e-3) / 1e12, ((double)nwin * pb.N + (double)rp_elems) * 16 / 1e9, maxdiff, scale, maxw, wref);
   if (RDF) printf(" | rdf total %llu hash %016llx", hsum, hmix);
   printf("\n");
   fflush(stdout);
@@ -330,12 +343,15 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&pb.upos, (size_t)N * 16));
   CK(cudaMalloc(&pb.posf, (size_t)N * 16));
   const size_t smax = std::min<size_t>(8 * sms, std::max(1, N / 8));
-  CK(cudaMalloc(&pb.fpart, smax * N * 16));
+  pb.fpart_elems = std::max<size_t>(smax * (size_t)N, (size_t)3 << 27);   // at least 6 GB: 140 rows at N = 1M
+  pb.fpart_elems = std::min<size_t>(pb.fpart_elems, (size_t)1 << 29);
+  CK(cudaMalloc(&pb.fpart, pb.fpart_elems * 16));
   CK(cudaMalloc(&pb.blockW, smax * (N / 64 + 1) * sizeof(double)));
   CK(cudaMalloc(&pb.rdf, 256 * 8));
   pb.hmax = sym_max_partner_count((N + 511) / 512);
   if (pb.hmax < 1) pb.hmax = 1;
-  CK(cudaMalloc(&pb.rpart, ((size_t)N * N / 256 + 4096) * 16));
+  pb.rpart_elems = std::min<size_t>((size_t)N * N / 256 + 4096, (size_t)1 << 29);
+  CK(cudaMalloc(&pb.rpart, pb.rpart_elems * 16));
   CK(cudaMalloc(&pb.bbox, (size_t)(N / 256 + 2) * 2 * sizeof(uint4)));   // enough for blocks of 256 and up
   CK(cudaMemset(pb.rdf, 0, 256 * 8));
   CK(cudaMemcpy(pb.upos, hu.data(), (size_t)N * 16, cudaMemcpyHostToDevice));
@@ -364,16 +380,36 @@ int main(int argc, char** argv) {
     for (int bj = 256; bj >= 64; bj >>= 1) {
       const int units = (sym_max_partner_count(n) + 1) * (512 / bj);
       int lastS = -1;
-      for (int per = units; per >= 1; --per) {
+      for (int per = std::min(units, 16); per >= 1; --per) {
         const int S = (units + per - 1) / per;
-        if (S == lastS || (size_t)S > smax || (long long)n * S > 24LL * sms * 3) continue;
-        if (per > 4 && per % 2 && S > 4) continue;   // thin out the long tail of large CTAs
+        if (S == lastS || (long long)n * S > 24LL * sms * 3) continue;
         lastS = S;
         char tag[96];
         snprintf(tag, sizeof(tag), "scan bj%d S%d per_cta%d ctas%d", bj, S, per, n * S);
-        run_sym<P2, true, false, 128, 3, 2, 4>(pb, tag, reps, bj, &keepP, true, S);
+        run_sym<P2, true, false, 128, 3, 2, 4>(pb, tag, reps, bj, &keepP, true, per, 1);
       }
     }
+    return 0;
+  }
+  if (argc > 3 && !strcmp(argv[3], "super")) {
+    // super-tile shapes (mi x mju): kernel time and bytes of partial-force + reaction output per launch
+    if (N <= 262144) run_variant<P2, true, false, 128, 4, 2, 4>(pb, "periodic ordered P2 t128 b4 np2 u4", reps, 1024, &keepP);
+    const int mis[] = {1, 2, 4, 8, 16};
+    const int mjus[] = {4, 8, 12, 16};
+    for (int mju : mjus)
+      for (int mi : mis) {
+        char tag[96];
+        snprintf(tag, sizeof(tag), "super periodic mi%d mju%d", mi, mju);
+        run_sym<P2, true, false, 128, 3, 2, 4>(pb, tag, reps, 256, &keepP, true, mju, mi);
+      }
+    if (N <= 262144) run_variant<P2, false, false, 128, 4, 2, 4>(pb, "open ordered P2 t128 b4 np2 u4", reps, 1024, &keepO);
+    for (int mi : mis) {
+      char tag[96];
+      snprintf(tag, sizeof(tag), "super open mi%d mju16", mi);
+      run_sym<P2, false, false, 128, 3, 2, 4>(pb, tag, reps, 256, &keepO, true, 16, mi);
+    }
+    run_sym<P2, true, true, 128, 3, 2, 4>(pb, "super periodic+RDF mi1 mju8", reps, 256, &keepP, true, 8, 1);
+    run_sym<P2, true, true, 128, 3, 2, 4>(pb, "super periodic+RDF mi4 mju16", reps, 256, &keepP, true, 16, 4);
     return 0;
   }
   //                 V   PER    RDF   THR MINB NPAIR UNROLL
