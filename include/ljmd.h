@@ -74,6 +74,19 @@ int ljmd_create(ljmd_system** out, int N, double rho, double T0, int canonical, 
                 float rdf_dr2, int device);
 
 /*
+ * Same on `ndev` GPUs of one node driven by the ONE calling thread ("create(..., device list)").
+ * The i-particles are split in contiguous shards over devices[0..ndev); every call on the returned handle is
+ * forwarded to all devices and returns when the slowest is done.  No launcher, no IPC and no NCCL: the devices
+ * map each other's memory (cudaDeviceEnablePeerAccess) and the per-step exchange — positions after the drift,
+ * Newton-3 reaction forces, energy / virial / kinetic sums — runs inside the library's own kernels over NVLink.
+ * Host arrays keep their full length: every device reads and writes its own shard of them.  ndev == 1 is
+ * ljmd_create.  Fails when the devices cannot map each other's memory or N is too small to give every device a
+ * 512-particle block.  New functionality: the reference is single-device.
+ */
+int ljmd_create_multi(ljmd_system** out, int N, double rho, double T0, int canonical, int bc,
+                      float rdf_dr2, const int* devices, int ndev);
+
+/*
  * Same, as rank `rank` of `world` cooperating processes (one GPU each).  The
  * i-particles are split in contiguous shards; every rank holds all positions.
  * nccl_unique_id: the 128-byte ncclUniqueId produced by ljmd_nccl_unique_id on
@@ -156,6 +169,12 @@ int ljmd_step(ljmd_system* s, double dt, int nsteps, int rdf_every);
  * The drop-in single step with HOST buffers: upload pos/vel, one Integrate(dt),
  * download pos/vel (and forces when force4 != NULL).  This is what
  * MDSystem::Integrate costs a caller that reads h_Pos/h_Vel after every step.
+ * Sharded systems: a device moves ITS shard both ways — up from the caller's
+ * full-length arrays and back into the same places.  Behind ljmd_create_multi the
+ * devices share the arrays, so the caller sees the whole state; with one process
+ * per GPU (ljmd_create_distributed) each process gets its own shard refreshed
+ * (33.5 MB instead of 268 MB of D2H per step at N = 1M on 8 GPUs) and fetches
+ * the rest with ljmd_get_state when it wants it.
  */
 int ljmd_integrate_host(ljmd_system* s, double dt, float* pos4, float* vel4, float* force4);
 
@@ -217,6 +236,14 @@ int ljmd_set_l2_flush(ljmd_system* s, long long bytes);
  * finishes the velocity update): total milliseconds and launches of the last call, and the algorithmic bytes
  * one launch moves. */
 int ljmd_last_gather_timing(ljmd_system* s, double* gather_ms, int* launches, double* bytes_per_launch);
+
+/* Sharded Newton-3 runs: the same for k_reduce_reaction, which sums this rank's reaction blocks into one record per
+ * particle before the exchange (reads every block once: the HBM-bound kernel of the sharded step). */
+int ljmd_last_reduce_timing(ljmd_system* s, double* reduce_ms, int* launches, double* bytes_per_launch);
+
+/* FP32 CUDA-core throughput of `device` measured with a stream of independent packed FMAs (TFLOP/s, best of 5
+ * launches, CUDA events): the measured denominator of the force kernel's roofline. */
+int ljmd_fp32_peak_probe(int device, double* tflops);
 
 /* Static facts for rooflines: out[0]=SM count, out[1]=i-tile size, out[2]=splits per i-tile,
  * out[3]=force CTAs per launch, out[4]=world size, out[5]=local particles, out[6]=1 if the Newton-3 kernel

@@ -9,7 +9,12 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <new>
+#include <string>
+#include <thread>
 #include <vector>
 
 #ifdef LJMD_WITH_NCCL
@@ -69,7 +74,15 @@ constexpr int kSymMaxMJU = 16;                // units per window: 16 x 256 reco
 constexpr int kSymMaxMI = 16;                 // i-tiles per super-tile
 constexpr int kSymMinBlocksN = 8;             // Newton-3 kernel from this many 512-particle blocks on (N = 4 096: 20.2 vs 22.0 us ordered)
 
+struct MultiCtl;   // single-process multi-GPU front handle (end of this file)
+
 struct ljmd_system {
+  // A handle made by ljmd_create_multi is a FRONT: it owns one sub-handle per device (rank r of world G, each
+  // driven by its own worker thread) and forwards every call.  Sub-handles have inproc = 1: no NCCL communicator,
+  // the fabric is wired with plain peer pointers, read-outs return the rank's own contribution and the front
+  // combines them, state downloads write the rank's own shard of the caller's array.
+  MultiCtl* multi = nullptr;
+  int inproc = 0;
   int N = 0, bc = 0, canonical = 0;
   double rho = 0., L = 0., T0 = 0.;
   float dr2 = 0.1f;
@@ -135,8 +148,9 @@ struct ljmd_system {
   double last_force_ms = 0., last_total_ms = 0., last_steps_ms = 0.;
   std::vector<cudaEvent_t> step_ev;   // per-step (begin, end) pairs: step time without the L2-flush write
   std::vector<cudaEvent_t> gath_ev;   // (begin, end) pairs around k_gather: the dominant HBM-bound kernel
-  double last_gather_ms = 0.;
-  int last_gather_launches = 0;
+  std::vector<cudaEvent_t> red_ev;    // (begin, end) pairs around k_reduce_reaction (sharded Newton-3 runs)
+  double last_gather_ms = 0., last_reduce_ms = 0.;
+  int last_gather_launches = 0, last_reduce_launches = 0;
   int last_force_launches = 0;
 #ifdef LJMD_WITH_NCCL
   ncclComm_t comm = nullptr;
@@ -432,9 +446,20 @@ static int evaluate(ljmd_system* s, const StepParams& p, int mode, bool rdf, int
   if (s->use_sym && s->world > 1) {
     // reaction forces land on particles of every rank: column sums of the local rows, then either a barrier
     // (fabric: k_gather pulls the peers' sums for its own particles) or a reduce-scatter (NCCL)
+    cudaEvent_t r0 = nullptr, r1 = nullptr;
+    if (s->timing) {
+      CU(cudaEventCreate(&r0));
+      CU(cudaEventCreate(&r1));
+      CU(cudaEventRecord(r0, s->stream));
+    }
     k_reduce_reaction<<<(s->npad + kStepThreads - 1) / kStepThreads, kStepThreads, 0, s->stream>>>(p);
     CU(cudaGetLastError());
     s->launches += 1;
+    if (s->timing) {
+      CU(cudaEventRecord(r1, s->stream));
+      s->red_ev.push_back(r0);
+      s->red_ev.push_back(r1);
+    }
     if (s->fab.n > 0) {
       if ((rc = fabric_sync(s, 0, 0))) return rc;
     } else {
@@ -541,9 +566,30 @@ static void collect_timing(ljmd_system* s) {
     cudaEventDestroy(s->gath_ev[k + 1]);
   }
   s->gath_ev.clear();
+  s->last_reduce_ms = 0.;
+  s->last_reduce_launches = 0;
+  for (size_t k = 0; k + 1 < s->red_ev.size(); k += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s->red_ev[k], s->red_ev[k + 1]) == cudaSuccess) {
+      s->last_reduce_ms += ms;
+      s->last_reduce_launches += 1;
+    }
+    cudaEventDestroy(s->red_ev[k]);
+    cudaEventDestroy(s->red_ev[k + 1]);
+  }
+  s->red_ev.clear();
   for (cudaEvent_t e : s->step_ev) cudaEventDestroy(e);   // per-step pairs are consumed by ljmd_step before this
   s->step_ev.clear();
 }
+
+// Run f(sub-handle, rank) on every device of a front handle, each on its own worker thread; first error wins.
+static int multi_all(ljmd_system* front, const std::function<int(ljmd_system*, int)>& f);
+static ljmd_system* multi_sub(ljmd_system* front, int r);
+static int multi_count(const ljmd_system* front);
+#define MULTI_ALL(s, expr)                                                                   \
+  do {                                                                                       \
+    if ((s) && (s)->multi) return multi_all((s), [&](ljmd_system* sub, int r_) -> int { (void)r_; return (expr); }); \
+  } while (0)
 
 // ------------------------------------------------------------------------------------ C ABI: A
 extern "C" int ljmd_device_count(void) {
@@ -618,6 +664,7 @@ static int destroy_impl(ljmd_system* s) {
   for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
   for (cudaEvent_t e : s->step_ev) cudaEventDestroy(e);
   for (cudaEvent_t e : s->gath_ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : s->red_ev) cudaEventDestroy(e);
   if (s->ev_begin) cudaEventDestroy(s->ev_begin);
   if (s->ev_end) cudaEventDestroy(s->ev_end);
   if (s->stream) cudaStreamDestroy(s->stream);
@@ -626,7 +673,7 @@ static int destroy_impl(ljmd_system* s) {
 }
 
 static int create_impl(ljmd_system** out, int N, double rho_or_negL, double T0, int canonical, int bc, float rdf_dr2,
-                       int device, int rank, int world, const void* uid) {
+                       int device, int rank, int world, const void* uid, int inproc = 0) {
   if (!out) return set_err(LJMD_ERR_ARG, "out is NULL");
   *out = nullptr;
   if (N < 2) return set_err(LJMD_ERR_ARG, "N must be >= 2 (got %d)", N);
@@ -643,7 +690,7 @@ static int create_impl(ljmd_system** out, int N, double rho_or_negL, double T0, 
   ljmd_system* s = new (std::nothrow) ljmd_system();
   if (!s) return set_err(LJMD_ERR_ARG, "out of host memory");
   s->N = N; s->bc = bc; s->canonical = canonical ? 1 : 0; s->T0 = T0; s->dr2 = rdf_dr2;
-  s->device = device; s->rank = rank; s->world = world;
+  s->device = device; s->rank = rank; s->world = world; s->inproc = inproc;
   if (rho_or_negL > 0.) { s->rho = rho_or_negL; s->L = pow(N / s->rho, 1. / 3.); }   // MDSystem.cpp:70
   else { s->L = -rho_or_negL; s->rho = N / (s->L * s->L * s->L); }
   // (the device properties are needed for the plan; queried again below for the arch check)
@@ -762,7 +809,7 @@ static int create_impl(ljmd_system** out, int N, double rho_or_negL, double T0, 
   CUC(cudaStreamSynchronize(s->stream));
   memset(s->h_sc, 0, sizeof(DevScalars));
 #undef CUC
-  if (world > 1) {
+  if (world > 1 && !inproc) {
 #ifdef LJMD_WITH_NCCL
     if (!uid) { destroy_impl(s); return set_err(LJMD_ERR_ARG, "nccl_unique_id is NULL"); }
     ncclUniqueId id;
@@ -799,10 +846,12 @@ int ljmd_create_with_L(ljmd_system** out, int N, double L, int bc, float rdf_dr2
   return create_impl(out, N, -L, 1.0, 0, bc, rdf_dr2, device, 0, 1, nullptr);
 }
 
-extern "C" int ljmd_destroy(ljmd_system* s) { return destroy_impl(s); }
+static int multi_destroy(ljmd_system* front);
+extern "C" int ljmd_destroy(ljmd_system* s) { return (s && s->multi) ? multi_destroy(s) : destroy_impl(s); }
 
 extern "C" int ljmd_fabric_export(ljmd_system* s, void* out64) {
   if (!s || !out64) return set_err(LJMD_ERR_ARG, "NULL argument");
+  if (s->multi || s->inproc) return set_err(LJMD_ERR_ARG, "a single-process multi-GPU system wires its fabric itself");
   CU(cudaSetDevice(s->device));
   if (s->world == 1 || !s->win) return set_err(LJMD_ERR_ARG, "fabric needs a distributed system (world > 1)");
   cudaIpcMemHandle_t h;
@@ -814,6 +863,7 @@ extern "C" int ljmd_fabric_export(ljmd_system* s, void* out64) {
 
 extern "C" int ljmd_fabric_connect(ljmd_system* s, const void* handles) {
   if (!s || !handles) return set_err(LJMD_ERR_ARG, "NULL argument");
+  if (s->multi || s->inproc) return set_err(LJMD_ERR_ARG, "a single-process multi-GPU system wires its fabric itself");
   CU(cudaSetDevice(s->device));
   if (s->world == 1 || !s->win) return set_err(LJMD_ERR_ARG, "fabric needs a distributed system (world > 1)");
   if (s->world > kMaxPeers) return set_err(LJMD_ERR_ARG, "fabric supports up to %d ranks", kMaxPeers);
@@ -846,17 +896,20 @@ extern "C" int ljmd_fabric_connect(ljmd_system* s, const void* handles) {
   } while (0)
 
 extern "C" int ljmd_set_canonical(ljmd_system* s, int canonical) {
+  MULTI_ALL(s, ljmd_set_canonical(sub, canonical));
   CHECK_S(s);
   s->canonical = canonical ? 1 : 0;
   return LJMD_OK;
 }
 extern "C" int ljmd_set_T0(ljmd_system* s, double T0) {
+  MULTI_ALL(s, ljmd_set_T0(sub, T0));
   CHECK_S(s);
   if (!(T0 > 0.)) return set_err(LJMD_ERR_ARG, "T0 must be positive");
   s->T0 = T0;
   return LJMD_OK;
 }
 extern "C" int ljmd_set_boundary(ljmd_system* s, int bc) {
+  MULTI_ALL(s, ljmd_set_boundary(sub, bc));
   CHECK_S(s);
   if (bc < 0 || bc > 2) return set_err(LJMD_ERR_ARG, "boundary condition must be 0, 1 or 2 (got %d)", bc);
   if (bc != s->bc) {
@@ -893,6 +946,7 @@ static int upload_state(ljmd_system* s, const float* pos4, const float* vel4) {
 }
 
 extern "C" int ljmd_set_state(ljmd_system* s, const float* pos4, const float* vel4) {
+  MULTI_ALL(s, ljmd_set_state(sub, pos4, vel4));
   CHECK_S(s);
   if (!pos4 || !vel4) return set_err(LJMD_ERR_ARG, "pos4/vel4 must not be NULL");
   int rc = check_domain(s, pos4);
@@ -911,6 +965,7 @@ extern "C" int ljmd_set_state(ljmd_system* s, const float* pos4, const float* ve
 }
 
 extern "C" int ljmd_upload(ljmd_system* s, const float* pos4, const float* vel4) {
+  MULTI_ALL(s, ljmd_upload(sub, pos4, vel4));
   CHECK_S(s);
   int rc = upload_state(s, pos4, vel4);
   if (rc) return rc;
@@ -920,6 +975,7 @@ extern "C" int ljmd_upload(ljmd_system* s, const float* pos4, const float* vel4)
 }
 
 extern "C" int ljmd_set_velocities(ljmd_system* s, const float* vel4) {
+  MULTI_ALL(s, ljmd_set_velocities(sub, vel4));
   CHECK_S(s);
   if (!vel4) return set_err(LJMD_ERR_ARG, "vel4 must not be NULL");
   int rc = upload_state(s, nullptr, vel4);
@@ -934,12 +990,14 @@ extern "C" int ljmd_set_velocities(ljmd_system* s, const float* vel4) {
   return sync_scalars(s);
 }
 
-// full-length copy of a sharded array into host memory
+// this rank's shard of a sharded array into its place in a full-length host array
+static int download_shard(ljmd_system* s, const float4* dev_local, float* host4) {
+  CU(cudaMemcpyAsync(host4 + (size_t)s->i_begin * 4, dev_local, (size_t)s->nloc * 16, cudaMemcpyDeviceToHost, s->stream));
+  return LJMD_OK;
+}
+// full-length copy of a sharded array into host memory (one process per GPU: every rank gets everything)
 static int download_sharded(ljmd_system* s, const float4* dev_local, float* host4) {
-  if (s->world == 1) {
-    CU(cudaMemcpyAsync(host4, dev_local, (size_t)s->N * 16, cudaMemcpyDeviceToHost, s->stream));
-    return LJMD_OK;
-  }
+  if (s->world == 1 || s->inproc) return download_shard(s, dev_local, host4);
 #ifdef LJMD_WITH_NCCL
   const size_t bytes = (size_t)s->cnt * 16;
   CU(cudaMemcpyAsync((char*)s->gath + (size_t)s->rank * bytes, dev_local, (size_t)s->nloc * 16,
@@ -953,6 +1011,7 @@ static int download_sharded(ljmd_system* s, const float4* dev_local, float* host
 }
 
 extern "C" int ljmd_get_state(ljmd_system* s, float* pos4, float* vel4, float* force4) {
+  MULTI_ALL(s, ljmd_get_state(sub, pos4, vel4, force4));   // every device fills its own shard of the arrays
   CHECK_S(s);
   int rc;
   if (pos4 && (rc = download_sharded(s, s->pos, pos4))) return rc;
@@ -963,6 +1022,7 @@ extern "C" int ljmd_get_state(ljmd_system* s, float* pos4, float* vel4, float* f
 }
 
 extern "C" int ljmd_step(ljmd_system* s, double dt, int nsteps, int rdf_every) {
+  MULTI_ALL(s, ljmd_step(sub, dt, nsteps, rdf_every));
   CHECK_S(s);
   if (nsteps < 0) return set_err(LJMD_ERR_ARG, "nsteps must be >= 0");
   if (s->trace_on && s->trace_n + nsteps > s->trace_cap)
@@ -1065,21 +1125,26 @@ extern "C" int ljmd_step(ljmd_system* s, double dt, int nsteps, int rdf_every) {
 }
 
 extern "C" int ljmd_integrate_host(ljmd_system* s, double dt, float* pos4, float* vel4, float* force4) {
+  MULTI_ALL(s, ljmd_integrate_host(sub, dt, pos4, vel4, force4));
   CHECK_S(s);
   if (!pos4 || !vel4) return set_err(LJMD_ERR_ARG, "pos4/vel4 must not be NULL");
   int rc = upload_state(s, pos4, vel4);
   if (rc) return rc;
   StepParams p = make_step_params(s, dt);
   if ((rc = one_step(s, p, false))) return rc;
-  if ((rc = download_sharded(s, s->pos, pos4))) return rc;
-  if ((rc = download_sharded(s, s->vel, vel4))) return rc;
-  if (force4 && (rc = download_sharded(s, s->force, force4))) return rc;
+  // a rank moves ITS shard both ways: up from the caller's arrays, back into the same places.  On one GPU (and
+  // behind a multi-GPU front handle, where the devices share the arrays) that is the whole state; one process
+  // per GPU gets the other shards through ljmd_get_state when it wants them.
+  if ((rc = download_shard(s, s->pos, pos4))) return rc;
+  if ((rc = download_shard(s, s->vel, vel4))) return rc;
+  if (force4 && (rc = download_shard(s, s->force, force4))) return rc;
   rc = sync_scalars(s);
   if (s->timing) collect_timing(s);
   return rc;
 }
 
 extern "C" int ljmd_compute_forces(ljmd_system* s, int with_rdf) {
+  MULTI_ALL(s, ljmd_compute_forces(sub, with_rdf));
   CHECK_S(s);
   // positions the caller sees are the wrapped ones: evaluate there (CalculateForces reads h_Pos)
   StepParams p = make_step_params(s, 0.);
@@ -1095,6 +1160,7 @@ extern "C" int ljmd_compute_forces(ljmd_system* s, int with_rdf) {
 }
 
 extern "C" int ljmd_get_scalars(ljmd_system* s, double* out) {
+  if (s && s->multi) return ljmd_get_scalars(multi_sub(s, 0), out);   // identical on every device (fixed-order sums)
   CHECK_S(s);
   if (!out) return set_err(LJMD_ERR_ARG, "out is NULL");
   const DevScalars& h = *s->h_sc;
@@ -1107,6 +1173,7 @@ extern "C" int ljmd_get_scalars(ljmd_system* s, double* out) {
 }
 
 extern "C" int ljmd_reset_averaging(ljmd_system* s) {
+  MULTI_ALL(s, ljmd_reset_averaging(sub));
   CHECK_S(s);
   DevScalars z;
   memset(&z, 0, sizeof(z));
@@ -1121,7 +1188,7 @@ extern "C" int ljmd_reset_averaging(ljmd_system* s) {
 
 static int fetch_rdf(ljmd_system* s, const unsigned long long* dev, unsigned long long* host256) {
 #ifdef LJMD_WITH_NCCL
-  if (s->world > 1) {
+  if (s->world > 1 && !s->inproc) {   // in-process sub-handles return their own counts: the front adds them
     unsigned long long* tmp = reinterpret_cast<unsigned long long*>(s->gath);
     CU(cudaMemcpyAsync(tmp, dev, kRdfBins * 8, cudaMemcpyDeviceToDevice, s->stream));
     NC(ncclAllReduce(tmp, tmp, kRdfBins, ncclUint64, ncclSum, s->comm, s->stream));
@@ -1134,6 +1201,19 @@ static int fetch_rdf(ljmd_system* s, const unsigned long long* dev, unsigned lon
 }
 
 extern "C" int ljmd_get_rdf(ljmd_system* s, int* out256) {
+  if (s && s->multi) {
+    if (!out256) return set_err(LJMD_ERR_ARG, "out256 is NULL");
+    const int G = multi_count(s);
+    std::vector<int> part((size_t)G * kRdfBins);
+    const int rc = multi_all(s, [&](ljmd_system* sub, int r) { return ljmd_get_rdf(sub, part.data() + (size_t)r * kRdfBins); });
+    if (rc) return rc;
+    for (int k = 0; k < kRdfBins; ++k) {
+      long long t = 0;
+      for (int r = 0; r < G; ++r) t += part[(size_t)r * kRdfBins + k];
+      out256[k] = (int)t;
+    }
+    return LJMD_OK;
+  }
   CHECK_S(s);
   if (!out256) return set_err(LJMD_ERR_ARG, "out256 is NULL");
   int rc;
@@ -1148,6 +1228,22 @@ extern "C" int ljmd_get_rdf(ljmd_system* s, int* out256) {
 }
 
 extern "C" int ljmd_get_rdf_accum(ljmd_system* s, long long* out256, int* nsamples, int reset) {
+  if (s && s->multi) {
+    if (!out256) return set_err(LJMD_ERR_ARG, "out256 is NULL");
+    const int G = multi_count(s);
+    std::vector<long long> part((size_t)G * kRdfBins);
+    std::vector<int> ns(G, 0);
+    const int rc = multi_all(s, [&](ljmd_system* sub, int r) {
+      return ljmd_get_rdf_accum(sub, part.data() + (size_t)r * kRdfBins, &ns[r], reset);
+    });
+    if (rc) return rc;
+    for (int k = 0; k < kRdfBins; ++k) {
+      out256[k] = 0;
+      for (int r = 0; r < G; ++r) out256[k] += part[(size_t)r * kRdfBins + k];
+    }
+    if (nsamples) *nsamples = ns[0];
+    return LJMD_OK;
+  }
   CHECK_S(s);
   if (!out256) return set_err(LJMD_ERR_ARG, "out256 is NULL");
   int rc = fetch_rdf(s, s->rdf_acc, s->h_rdf);
@@ -1163,6 +1259,20 @@ extern "C" int ljmd_get_rdf_accum(ljmd_system* s, long long* out256, int* nsampl
 }
 
 extern "C" int ljmd_velocity_histogram(ljmd_system* s, double step, int nbins, int* out) {
+  if (s && s->multi) {
+    if (!out || nbins < 1 || nbins > 65536 / 2) return set_err(LJMD_ERR_ARG, "bad histogram arguments");
+    const int G = multi_count(s);
+    std::vector<int> part((size_t)G * nbins);
+    const int rc = multi_all(s, [&](ljmd_system* sub, int r) {
+      return ljmd_velocity_histogram(sub, step, nbins, part.data() + (size_t)r * nbins);
+    });
+    if (rc) return rc;
+    for (int k = 0; k < nbins; ++k) {
+      out[k] = 0;
+      for (int r = 0; r < G; ++r) out[k] += part[(size_t)r * nbins + k];
+    }
+    return LJMD_OK;
+  }
   CHECK_S(s);
   if (!out || nbins < 1 || nbins > 65536 / 2 || !(step > 0.)) return set_err(LJMD_ERR_ARG, "bad histogram arguments");
   CU(cudaMemsetAsync(s->velh, 0, (size_t)nbins * 4, s->stream));
@@ -1174,7 +1284,7 @@ extern "C" int ljmd_velocity_histogram(ljmd_system* s, double step, int nbins, i
   CU(cudaGetLastError());
   s->launches += 1;
 #ifdef LJMD_WITH_NCCL
-  if (s->world > 1) NC(ncclAllReduce(s->velh, s->velh, nbins, ncclUint32, ncclSum, s->comm, s->stream));
+  if (s->world > 1 && !s->inproc) NC(ncclAllReduce(s->velh, s->velh, nbins, ncclUint32, ncclSum, s->comm, s->stream));
 #endif
   std::vector<unsigned int> h((size_t)nbins);
   CU(cudaMemcpyAsync(h.data(), s->velh, (size_t)nbins * 4, cudaMemcpyDeviceToHost, s->stream));
@@ -1184,6 +1294,7 @@ extern "C" int ljmd_velocity_histogram(ljmd_system* s, double step, int nbins, i
 }
 
 extern "C" int ljmd_set_l2_flush(ljmd_system* s, long long bytes) {
+  MULTI_ALL(s, ljmd_set_l2_flush(sub, bytes));
   CHECK_S(s);
   if (bytes < 0) return set_err(LJMD_ERR_ARG, "bytes must be >= 0");
   if ((size_t)bytes != s->flush_bytes) {
@@ -1225,6 +1336,21 @@ static int build_subvol_spec(ljmd_system* s, int type, double alpha_step, double
 }
 
 static int subvolume_impl(ljmd_system* s, int type, double alpha_step, double vcut_max, int* out, int cap, int* nout) {
+  if (s && s->multi) {
+    if (!out || !nout || cap < 0) return set_err(LJMD_ERR_ARG, "bad sub-volume arguments");
+    const int G = multi_count(s);
+    std::vector<int> part((size_t)G * std::max(cap, 1), 0), n(G, 0);
+    const int rc = multi_all(s, [&](ljmd_system* sub, int r) {
+      return subvolume_impl(sub, type, alpha_step, vcut_max, part.data() + (size_t)r * std::max(cap, 1), cap, &n[r]);
+    });
+    if (rc) return rc;
+    *nout = n[0];
+    for (int k = 0; k < n[0]; ++k) {   // cumulative counts of disjoint shards add up
+      out[k] = 0;
+      for (int r = 0; r < G; ++r) out[k] += part[(size_t)r * std::max(cap, 1) + k];
+    }
+    return LJMD_OK;
+  }
   CHECK_S(s);
   if (!out || !nout) return set_err(LJMD_ERR_ARG, "bad sub-volume arguments");
   SubvolParams q;
@@ -1242,7 +1368,7 @@ static int subvolume_impl(ljmd_system* s, int type, double alpha_step, double vc
   CU(cudaGetLastError());
   s->launches += 1;
 #ifdef LJMD_WITH_NCCL
-  if (s->world > 1) NC(ncclAllReduce(s->velh, s->velh, nb, ncclUint32, ncclSum, s->comm, s->stream));
+  if (s->world > 1 && !s->inproc) NC(ncclAllReduce(s->velh, s->velh, nb, ncclUint32, ncclSum, s->comm, s->stream));
 #endif
   unsigned int h[kMaxSubBins];
   CU(cudaMemcpyAsync(h, s->velh, (size_t)nb * 4, cudaMemcpyDeviceToHost, s->stream));
@@ -1262,6 +1388,7 @@ static void trace_free(ljmd_system* s) {
 
 extern "C" int ljmd_trace_begin(ljmd_system* s, int ncounters, const int* kinds, const double* alpha_steps,
                                 const double* vcut_max, int capacity_steps) {
+  MULTI_ALL(s, ljmd_trace_begin(sub, ncounters, kinds, alpha_steps, vcut_max, capacity_steps));
   CHECK_S(s);
   if (ncounters < 0 || ncounters > kMaxTraceCounters) return set_err(LJMD_ERR_ARG, "0..%d counters", kMaxTraceCounters);
   if (capacity_steps < 1) return set_err(LJMD_ERR_ARG, "capacity_steps must be >= 1");
@@ -1289,6 +1416,7 @@ extern "C" int ljmd_trace_begin(ljmd_system* s, int ncounters, const int* kinds,
 }
 
 extern "C" int ljmd_trace_row_length(ljmd_system* s, int* counts_per_step) {
+  if (s && s->multi) return ljmd_trace_row_length(multi_sub(s, 0), counts_per_step);
   CHECK_S(s);
   if (!counts_per_step) return set_err(LJMD_ERR_ARG, "counts_per_step must not be NULL");
   if (!s->trace_on) return set_err(LJMD_ERR_ARG, "no trace is active");
@@ -1314,8 +1442,9 @@ static int trace_record(ljmd_system* s) {
   return LJMD_OK;
 }
 
-extern "C" int ljmd_trace_read(ljmd_system* s, int max_steps, int* nsteps, double* scalars, long long* counts,
-                               double* mean_velocity) {
+// vel_int: [nsteps][3] integer velocity sums in 2^-32 fixed point (this rank's particles when in-process)
+static int trace_read_impl(ljmd_system* s, int max_steps, int* nsteps, double* scalars, long long* counts,
+                           long long* vel_int) {
   CHECK_S(s);
   if (!nsteps) return set_err(LJMD_ERR_ARG, "nsteps must not be NULL");
   if (!s->trace_on) return set_err(LJMD_ERR_ARG, "no trace is active");
@@ -1324,7 +1453,7 @@ extern "C" int ljmd_trace_read(ljmd_system* s, int max_steps, int* nsteps, doubl
   *nsteps = n;
   if (n == 0) return LJMD_OK;
 #ifdef LJMD_WITH_NCCL
-  if (s->world > 1)
+  if (s->world > 1 && !s->inproc)
     NC(ncclAllReduce(s->trace_counts, s->trace_counts, (size_t)n * row, ncclUint64, ncclSum, s->comm, s->stream));
 #endif
   std::vector<unsigned long long> h((size_t)n * row);
@@ -1344,15 +1473,58 @@ extern "C" int ljmd_trace_read(ljmd_system* s, int max_steps, int* nsteps, doubl
         off += s->trace_nbins[c];
       }
     }
-    if (mean_velocity)
-      for (int a = 0; a < 3; ++a)
-        mean_velocity[3 * k + a] = (double)(long long)r[nb + a] / 4294967296.0 / (double)s->N;
+    if (vel_int)
+      for (int a = 0; a < 3; ++a) vel_int[3 * k + a] = (long long)r[nb + a];
   }
   s->trace_n = 0;
   return LJMD_OK;
 }
 
+extern "C" int ljmd_trace_read(ljmd_system* s, int max_steps, int* nsteps, double* scalars, long long* counts,
+                               double* mean_velocity) {
+  if (!s) return set_err(LJMD_ERR_ARG, "system is NULL");
+  if (!nsteps || max_steps < 0) return set_err(LJMD_ERR_ARG, "nsteps must not be NULL");
+  std::vector<long long> vint(mean_velocity ? (size_t)3 * std::max(max_steps, 1) : 0, 0);
+  int rc;
+  if (s->multi) {
+    // every device returns the rows of its own particles: integer counts and integer velocity sums add up exactly
+    const int G = multi_count(s);
+    int nb = 0;
+    if ((rc = ljmd_trace_row_length(multi_sub(s, 0), &nb))) return rc;
+    const size_t cstride = (size_t)std::max(max_steps, 1) * std::max(nb, 1), vstride = (size_t)3 * std::max(max_steps, 1);
+    std::vector<long long> cpart(counts ? cstride * G : 0, 0), vpart(mean_velocity ? vstride * G : 0, 0);
+    std::vector<int> ns(G, 0);
+    rc = multi_all(s, [&](ljmd_system* sub, int r) {
+      return trace_read_impl(sub, max_steps, &ns[r], r == 0 ? scalars : nullptr, counts ? cpart.data() + cstride * r : nullptr,
+                             mean_velocity ? vpart.data() + vstride * r : nullptr);
+    });
+    if (rc) return rc;
+    *nsteps = ns[0];
+    for (int k = 0; k < ns[0]; ++k) {
+      if (counts)
+        for (int b = 0; b < nb; ++b) {
+          long long t = 0;
+          for (int r = 0; r < G; ++r) t += cpart[cstride * r + (size_t)k * nb + b];
+          counts[(size_t)k * nb + b] = t;
+        }
+      if (mean_velocity)
+        for (int a = 0; a < 3; ++a) {
+          long long t = 0;
+          for (int r = 0; r < G; ++r) t += vpart[vstride * r + 3 * k + a];
+          vint[3 * k + a] = t;
+        }
+    }
+  } else {
+    if ((rc = trace_read_impl(s, max_steps, nsteps, scalars, counts, mean_velocity ? vint.data() : nullptr))) return rc;
+  }
+  if (mean_velocity)
+    for (int k = 0; k < *nsteps; ++k)
+      for (int a = 0; a < 3; ++a) mean_velocity[3 * k + a] = (double)vint[3 * k + a] / 4294967296.0 / (double)s->N;
+  return LJMD_OK;
+}
+
 extern "C" int ljmd_trace_end(ljmd_system* s) {
+  MULTI_ALL(s, ljmd_trace_end(sub));
   CHECK_S(s);
   trace_free(s);
   return LJMD_OK;
@@ -1368,14 +1540,34 @@ extern "C" int ljmd_velocity_subvolume_counts(ljmd_system* s, int type, double v
   return subvolume_impl(s, 4 + type, alpha_step, vcut_max, out, cap, nout);
 }
 
-extern "C" long long ljmd_launch_count(ljmd_system* s) { return s ? s->launches : 0; }
+extern "C" long long ljmd_launch_count(ljmd_system* s) {
+  if (s && s->multi) {
+    long long t = 0;
+    for (int r = 0; r < multi_count(s); ++r) t += multi_sub(s, r)->launches;
+    return t;
+  }
+  return s ? s->launches : 0;
+}
 
 extern "C" int ljmd_set_event_timing(ljmd_system* s, int on) {
+  MULTI_ALL(s, ljmd_set_event_timing(sub, on));
   CHECK_S(s);
   s->timing = on ? 1 : 0;
   return LJMD_OK;
 }
 extern "C" int ljmd_last_step_timing(ljmd_system* s, double* force_ms, double* total_ms, int* force_launches) {
+  if (s && s->multi) {   // the slowest device defines the step
+    double f = 0., t = 0.;
+    for (int r = 0; r < multi_count(s); ++r) {
+      double fr = 0., tr = 0.;
+      const int rc = ljmd_last_step_timing(multi_sub(s, r), &fr, &tr, force_launches);
+      if (rc) return rc;
+      f = std::max(f, fr); t = std::max(t, tr);
+    }
+    if (force_ms) *force_ms = f;
+    if (total_ms) *total_ms = t;
+    return LJMD_OK;
+  }
   CHECK_S(s);
   if (force_ms) *force_ms = s->last_force_ms;
   // the steps themselves (sum of per-step intervals); the L2-flush writes between them are not step work
@@ -1383,24 +1575,64 @@ extern "C" int ljmd_last_step_timing(ljmd_system* s, double* force_ms, double* t
   if (force_launches) *force_launches = s->last_force_launches;
   return LJMD_OK;
 }
+// bytes of all reaction blocks of this rank (what one pass over every band reads)
+static double reaction_band_bytes(const ljmd_system* s) {
+  if (!s->use_sym) return 0.;
+  const int hmax = sym_max_partner_count(s->nblk);
+  int qmax = s->sym_mi - 1 + hmax;
+  if (qmax > s->nblk - 1) qmax = s->nblk - 1;
+  return 16. * (double)s->n_super * (qmax + 1) * kITile;
+}
+
+// k_reduce_reaction (sharded Newton-3 runs): column sums of this rank's reaction blocks for all N particles —
+// reads every band once, writes one record per particle.  The HBM-bound kernel of the sharded step.
+extern "C" int ljmd_last_reduce_timing(ljmd_system* s, double* reduce_ms, int* launches, double* bytes_per_launch) {
+  if (s && s->multi) {
+    double g = 0.;
+    for (int r = 0; r < multi_count(s); ++r) {
+      double gr = 0.;
+      const int rc = ljmd_last_reduce_timing(multi_sub(s, r), &gr, launches, bytes_per_launch);
+      if (rc) return rc;
+      g = std::max(g, gr);
+    }
+    if (reduce_ms) *reduce_ms = g;
+    return LJMD_OK;
+  }
+  CHECK_S(s);
+  if (reduce_ms) *reduce_ms = s->last_reduce_ms;
+  if (launches) *launches = s->last_reduce_launches;
+  if (bytes_per_launch) *bytes_per_launch = reaction_band_bytes(s) + 16. * (double)s->npad;
+  return LJMD_OK;
+}
+
 extern "C" int ljmd_last_gather_timing(ljmd_system* s, double* gather_ms, int* launches, double* bytes_per_launch) {
+  if (s && s->multi) {
+    double g = 0.;
+    for (int r = 0; r < multi_count(s); ++r) {
+      double gr = 0.;
+      const int rc = ljmd_last_gather_timing(multi_sub(s, r), &gr, launches, bytes_per_launch);   // bytes: per device
+      if (rc) return rc;
+      g = std::max(g, gr);
+    }
+    if (gather_ms) *gather_ms = g;
+    return LJMD_OK;
+  }
   CHECK_S(s);
   if (gather_ms) *gather_ms = s->last_gather_ms;
   if (launches) *launches = s->last_gather_launches;
   if (bytes_per_launch) {
-    // algorithmic bytes of one k_gather launch: per local particle it reads the S direct
-    // partial rows, the reaction rows that target it (one per partner block, or one pre-reduced record per
-    // rank when sharded), velocity and old force, and writes force plus t_Force (TVN) or velocity and position
-    // reaction blocks that cover a particle: the super-tiles whose band reaches its block
-    const double covering = std::min<double>(s->n_super, (double)(s->sym_mi + sym_max_partner_count(s->nblk)) / s->sym_mi);
-    const double per_particle_reads =
-        16. * s->nsplit + (s->use_sym ? 16. * (s->world == 1 ? covering : s->world) : 0.) + 32.;
-    *bytes_per_launch = (per_particle_reads + 48.) * (double)s->nloc;
+    // algorithmic bytes of one k_gather launch: per local particle the nsplit partial-force rows,
+    // velocity and old force in; force plus t_Force (TVN) or velocity and position out; plus the reaction
+    // records: on one GPU every super-tile's band (each entry is read exactly once), sharded one pre-reduced
+    // record per rank (pulled from the peers' windows over NVLink: not HBM traffic of this device)
+    *bytes_per_launch = (16. * s->nsplit + 32. + 48.) * (double)s->nloc + reaction_band_bytes(s) * (s->world == 1 ? 1. : 0.) +
+                        (s->use_sym && s->world > 1 ? 16. * s->world * (double)s->nloc : 0.);
   }
   return LJMD_OK;
 }
 
 extern "C" int ljmd_get_launch_info(ljmd_system* s, int* out8) {
+  if (s && s->multi) return ljmd_get_launch_info(multi_sub(s, 0), out8);
   CHECK_S(s);
   if (!out8) return set_err(LJMD_ERR_ARG, "out8 is NULL");
   out8[0] = s->num_sms; out8[1] = kITile; out8[2] = s->nsplit; out8[3] = (s->use_sym ? s->n_super : s->n_itiles) * s->nsplit;
@@ -1411,6 +1643,7 @@ extern "C" int ljmd_get_launch_info(ljmd_system* s, int* out8) {
 // ------------------------------------------------------------------------------------ C ABI: B
 // Worker for the legacy seam (ljmd_legacy.cu): forces on caller-owned device arrays.
 int ljmd_legacy_forces(ljmd_system* s, const float* d_pos, float* d_force, float* pressure, int* rdf256) {
+  if (s && s->multi) return set_err(LJMD_ERR_ARG, "the legacy seam is single-device");
   CHECK_S(s);
   // The caller's copyArrayToDevice (a pageable-memory cudaMemcpy on the legacy default stream) may return before
   // its DMA has landed, and this handle's stream is non-blocking: order explicitly after the legacy stream.
@@ -1429,5 +1662,212 @@ int ljmd_legacy_forces(ljmd_system* s, const float* d_pos, float* d_force, float
     if ((rc = fetch_rdf(s, s->rdf_cur, s->h_rdf))) return rc;
     for (int k = 0; k < kRdfBins; ++k) rdf256[k] = (int)s->h_rdf[k];
   }
+  return LJMD_OK;
+}
+
+// ------------------------------------------------------------------- FP32 peak probe (roofline denominator)
+// A stream of independent packed FMAs (FFMA2, 8 chains per thread, 16 warps per SM sub-partition): the FP32
+// CUDA-core rate this device sustains, measured with CUDA events.  bench.py reports the force kernel against this
+// figure next to the nominal SMs x 128 lanes x 2 x clock (MEASURED_PEAKS.json carries no FP32 CUDA-core number).
+__global__ void __launch_bounds__(256) k_fp32_probe(float* out, int iters, float seed) {
+  u64 v[8], ca, cb;
+  asm volatile("mov.b64 %0, {%1,%1};" : "=l"(ca) : "f"(seed * 1.0001f));
+  asm volatile("mov.b64 %0, {%1,%1};" : "=l"(cb) : "f"(seed * 0.0001f));
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float lo = seed + c + threadIdx.x, hi = seed - c;
+    asm volatile("mov.b64 %0, {%1,%2};" : "=l"(v[c]) : "f"(lo), "f"(hi));
+  }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(v[c]) : "l"(ca), "l"(cb));
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float lo, hi;
+    asm volatile("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v[c]));
+    s += lo + hi;
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" int ljmd_fp32_peak_probe(int device, double* tflops) {
+  if (!tflops) return set_err(LJMD_ERR_ARG, "tflops is NULL");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return set_err(LJMD_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  }
+  if (device < 0 || device >= ndev) return set_err(LJMD_ERR_ARG, "device %d out of range (%d visible)", device, ndev);
+  CU(cudaSetDevice(device));
+  int sms = 0;
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const int blocks = sms * 8, threads = 256, iters = 8192;
+  float* d = nullptr;
+  CU(cudaMalloc(&d, (size_t)blocks * threads * sizeof(float)));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  k_fp32_probe<<<blocks, threads>>>(d, 64, 1.0f);   // warm-up
+  double best = 0.;
+  for (int rep = 0; rep < 5; ++rep) {
+    CU(cudaEventRecord(e0));
+    k_fp32_probe<<<blocks, threads>>>(d, iters, 1.0f);
+    CU(cudaEventRecord(e1));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = (double)blocks * threads * iters * 8 /*chains*/ * 2 /*lanes*/ * 2 /*fma*/;
+    best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops = best;
+  return LJMD_OK;
+}
+
+// ------------------------------------------------------------------- single-process multi-GPU (front handle)
+// ljmd_create_multi: the caller keeps ONE handle and ONE thread; the library drives G devices of the node.
+// Each device gets a sub-handle (rank r of world G) and a persistent worker thread that owns every CUDA call on
+// it; a call on the front handle is forwarded to all workers and returns when the slowest is done.  The per-step
+// exchange is the fabric of ljmd_step.cuh over plain peer pointers (cudaDeviceEnablePeerAccess: no IPC, no NCCL,
+// no launcher); read-outs are combined on the host from the devices' own integer counts.
+struct MultiCtl {
+  int n = 0;
+  std::vector<ljmd_system*> sub;
+  std::vector<int> dev;
+  std::vector<std::thread> workers;
+  std::mutex m;
+  std::condition_variable cv_go, cv_done;
+  const std::function<int(ljmd_system*, int)>* job = nullptr;
+  unsigned long long gen = 0;
+  int pending = 0;
+  bool stop = false;
+  std::vector<int> rc;
+  std::vector<std::string> err;
+};
+
+static void multi_worker(MultiCtl* c, int r) {
+  cudaSetDevice(c->dev[r]);
+  unsigned long long seen = 0;
+  for (;;) {
+    const std::function<int(ljmd_system*, int)>* job;
+    {
+      std::unique_lock<std::mutex> lk(c->m);
+      c->cv_go.wait(lk, [&] { return c->stop || c->gen != seen; });
+      if (c->stop) return;
+      seen = c->gen;
+      job = c->job;
+    }
+    g_err[0] = 0;
+    const int rc = (*job)(c->sub[r], r);
+    {
+      std::lock_guard<std::mutex> lk(c->m);
+      c->rc[r] = rc;
+      c->err[r] = rc ? g_err : "";
+      if (--c->pending == 0) c->cv_done.notify_all();
+    }
+  }
+}
+
+static int multi_run(MultiCtl* c, const std::function<int(ljmd_system*, int)>& f) {
+  {
+    std::unique_lock<std::mutex> lk(c->m);
+    c->job = &f;
+    c->pending = c->n;
+    c->gen += 1;
+    c->cv_go.notify_all();
+    c->cv_done.wait(lk, [&] { return c->pending == 0; });
+    c->job = nullptr;
+  }
+  for (int r = 0; r < c->n; ++r)
+    if (c->rc[r]) return set_err(c->rc[r], "device %d (rank %d of %d): %s", c->dev[r], r, c->n, c->err[r].c_str());
+  return LJMD_OK;
+}
+
+static int multi_all(ljmd_system* front, const std::function<int(ljmd_system*, int)>& f) { return multi_run(front->multi, f); }
+static ljmd_system* multi_sub(ljmd_system* front, int r) { return front->multi->sub[r]; }
+static int multi_count(const ljmd_system* front) { return front->multi->n; }
+
+static int multi_destroy(ljmd_system* front) {
+  MultiCtl* c = front->multi;
+  multi_run(c, [&](ljmd_system* sub, int r) {
+    const int rc = destroy_impl(sub);
+    c->sub[r] = nullptr;
+    return rc;
+  });
+  {
+    std::lock_guard<std::mutex> lk(c->m);
+    c->stop = true;
+    c->cv_go.notify_all();
+  }
+  for (std::thread& t : c->workers) t.join();
+  delete c;
+  delete front;
+  return LJMD_OK;
+}
+
+extern "C" int ljmd_create_multi(ljmd_system** out, int N, double rho, double T0, int canonical, int bc, float rdf_dr2,
+                                 const int* devices, int ndev) {
+  if (!out) return set_err(LJMD_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (!(rho > 0.)) return set_err(LJMD_ERR_ARG, "rho must be positive");
+  if (!devices || ndev < 1 || ndev > kMaxPeers) return set_err(LJMD_ERR_ARG, "1..%d devices", kMaxPeers);
+  if (ndev == 1) return create_impl(out, N, rho, T0, canonical, bc, rdf_dr2, devices[0], 0, 1, nullptr);
+  int visible = 0;
+  if (cudaGetDeviceCount(&visible) != cudaSuccess || visible == 0) {
+    cudaGetLastError();
+    return set_err(LJMD_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  }
+  for (int a = 0; a < ndev; ++a) {
+    if (devices[a] < 0 || devices[a] >= visible) return set_err(LJMD_ERR_ARG, "device %d out of range (%d visible)", devices[a], visible);
+    for (int b = 0; b < a; ++b)
+      if (devices[a] == devices[b]) return set_err(LJMD_ERR_ARG, "device %d listed twice", devices[a]);
+  }
+  for (int a = 0; a < ndev; ++a)
+    for (int b = 0; b < ndev; ++b) {
+      int ok = 1;
+      if (a != b) CU(cudaDeviceCanAccessPeer(&ok, devices[a], devices[b]));
+      if (!ok) return set_err(LJMD_ERR_CUDA, "device %d cannot map the memory of device %d (no NVLink / PCIe peer access)", devices[a], devices[b]);
+    }
+  MultiCtl* c = new (std::nothrow) MultiCtl();
+  ljmd_system* front = new (std::nothrow) ljmd_system();
+  if (!c || !front) { delete c; delete front; return set_err(LJMD_ERR_ARG, "out of host memory"); }
+  c->n = ndev;
+  c->sub.assign(ndev, nullptr);
+  c->dev.assign(devices, devices + ndev);
+  c->rc.assign(ndev, 0);
+  c->err.assign(ndev, "");
+  for (int r = 0; r < ndev; ++r) c->workers.emplace_back(multi_worker, c, r);
+  front->multi = c;
+  front->N = N; front->bc = bc; front->canonical = canonical ? 1 : 0; front->T0 = T0; front->rho = rho;
+  front->L = pow(N / rho, 1. / 3.); front->dr2 = rdf_dr2; front->world = ndev; front->device = devices[0];
+  int rc = multi_run(c, [&](ljmd_system*, int r) {
+    return create_impl(&c->sub[r], N, rho, T0, canonical, bc, rdf_dr2, c->dev[r], r, ndev, nullptr, /*inproc=*/1);
+  });
+  if (rc == LJMD_OK) {
+    // wire the fabric: every device maps every peer, the windows are plain pointers in this address space
+    rc = multi_run(c, [&](ljmd_system* sub, int r) {
+      for (int q = 0; q < ndev; ++q) {
+        if (q == r) continue;
+        const cudaError_t e = cudaDeviceEnablePeerAccess(c->dev[q], 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+          return set_err(LJMD_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", c->dev[q], cudaGetErrorString(e));
+        cudaGetLastError();
+      }
+      for (int q = 0; q < ndev; ++q) sub->fab.base[q] = c->sub[q]->win;
+      sub->fab.me = r;
+      sub->fab.n = ndev;
+      return (int)LJMD_OK;
+    });
+  }
+  if (rc != LJMD_OK) {
+    std::string keep = g_err;
+    multi_destroy(front);
+    return set_err(rc, "%s", keep.c_str());
+  }
+  *out = front;
   return LJMD_OK;
 }

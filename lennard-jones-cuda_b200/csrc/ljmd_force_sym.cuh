@@ -26,6 +26,10 @@
 // met all 32 lanes x 2*NPAIR i-particles; the warps' packets go to per-warp shared-memory slices, are summed in
 // warp order and added to the window's accumulator in tile order; the gather kernel adds the blocks of the
 // super-tiles in a fixed order.  No floating-point atomics anywhere: runs are bit-reproducible.
+// The CTA's (tile, unit) work list is built once in shared memory and the main loop just walks it: with the
+// enumeration inlined in the loop (round-2 first attempt) ptxas kept ~12 more live scalars, stopped coalescing
+// the accumulator registers across the back-edge of the pair loop and re-built the packed i-coordinate pairs
+// inside it: +6 % instructions in the periodic loop, +27 % in the open one (5 % / 12 % of the kernel time).
 // Measured alternatives at N = 65 536 periodic (profiles/r01_tune_force_sym_*.log): ordered kernel 2.82 ms;
 // rotating positions and accumulators by shuffle (6 SHFL per step) 1.92 ms; broadcast j + 5-level butterfly
 // sum of the reaction (15 SHFL + 15 FADD per j) 2.37 ms.
@@ -255,6 +259,10 @@ __device__ __forceinline__ void pair_sym(const uint4& uj, const PairI<V>& pi, Pa
     }                                                                                                            \
   }
 
+// Work items of a CTA, built once in shared memory: (first record, record count, tile, window slot, diagonal?)
+// packed in an int2: x = j0, y = nj | slot << 10 | tile << 16 | diag << 24 | first-of-tile << 25.
+constexpr int kSymMaxItems = 256;   // mi * mju <= 16 * 16
+
 template <typename V, bool PERIODIC, bool RDF, int THREADS, int MINB, int NPAIR, int UNROLLK = 4>
 __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp) {
   pdl_trigger();
@@ -266,81 +274,64 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int BJ = sp.bj;
-  const int MJU = sp.mju;
   uint4* tile_u = reinterpret_cast<uint4*>(smem_raw);  // [2][BJ]
   unsigned char* after_tiles = smem_raw + (size_t)2 * BJ * 16;
   uint4* stage = reinterpret_cast<uint4*>(after_tiles);                          // [NW][64]
   float* slices = reinterpret_cast<float*>(after_tiles + (size_t)NW * 64 * 16);  // [NW][BJ][3]
-  float* racc = slices + (size_t)NW * BJ * 3;                                    // [MJU][BJ][3] window accumulator
-  unsigned char* tail = reinterpret_cast<unsigned char*>(racc + (size_t)MJU * BJ * 3);
-  tail += (16 - (reinterpret_cast<uintptr_t>(tail) & 15)) & 15;
+  float* racc = slices + (size_t)NW * BJ * 3;                                    // [mju][BJ][3] window accumulator
+  unsigned char* tail = reinterpret_cast<unsigned char*>(racc + (size_t)sp.mju * BJ * 3);
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);          // [2]
   double* red = reinterpret_cast<double*>(tail + 16);          // [NW]
-  unsigned int* hist = reinterpret_cast<unsigned int*>(tail + 16 + 8 * NW);         // [NW][256] (RDF)
-  uint2* queues = reinterpret_cast<uint2*>(tail + 16 + 8 * NW + NW * kRdfBins * 4);  // [NW][cap] (RDF)
+  int2* items = reinterpret_cast<int2*>(tail + 16 + 8 * NW);   // [kSymMaxItems]
+  int* nitems_s = reinterpret_cast<int*>(tail + 16 + 8 * NW + kSymMaxItems * 8);   // [4]: item count
+  unsigned int* hist = reinterpret_cast<unsigned int*>(tail + 32 + 8 * NW + kSymMaxItems * 8);         // [NW][256] (RDF)
+  uint2* queues = reinterpret_cast<uint2*>(tail + 32 + 8 * NW + kSymMaxItems * 8 + NW * kRdfBins * 4);  // [NW][cap] (RDF)
 
-  const int n = sp.nblk;
-  const int cpb = B / BJ;
   const int ibase0 = p.i_begin + blockIdx.x * sp.mi * B;   // first particle of the super-tile
-  const int I0 = ibase0 / B;                               // its global block (i_begin is a multiple of B)
   const int ntiles = min(sp.mi, (p.i_end - ibase0 + B - 1) / B);   // the rank's last super-tile may be short
   int win = (int)blockIdx.y + sp.win_shift;
   if (win >= sp.nwin) win -= sp.nwin;
-  const int u0 = win * MJU, u1 = u0 + MJU;                 // this CTA's window of the band, in units
 
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     mbar_fence_init();
+    // the CTA's work list: tile-major, empty units (beyond N: ragged last block) skipped
+    const int n = sp.nblk, cpb = B / BJ, I0 = ibase0 / B;   // i_begin is a multiple of B
+    const int u0 = win * sp.mju, u1 = u0 + sp.mju;
+    int cnt = 0;
+    for (int t = 0; t < ntiles; ++t) {
+      int g = I0 + t;
+      if (g >= n) g -= n;
+      const int ub = max(u0, t * cpb), ue = min(u1, (t + sym_partner_count(g, n) + 1) * cpb);   // blocks q in [t, t + h_t]
+      bool first = true;
+      for (int u = ub; u < ue; ++u) {
+        const int q = u / cpb;
+        int J = I0 + q;
+        if (J >= n) J -= n;
+        const int j0 = J * B + (u - q * cpb) * BJ;
+        const int nj = min(BJ, min(p.N, (J + 1) * B) - j0);
+        if (nj <= 0) continue;
+        items[cnt++] = make_int2(j0, nj | ((u - u0) << 10) | (t << 16) | ((q == t) ? (1 << 24) : 0) | (first ? (1 << 25) : 0));
+        first = false;
+      }
+    }
+    nitems_s[0] = cnt;
   }
   if (RDF) {
     for (int k = tid; k < NW * kRdfBins; k += THREADS) hist[k] = 0u;
   }
-  for (int k = tid; k < MJU * BJ * 3; k += THREADS) racc[k] = 0.f;
+  for (int k = tid; k < sp.mju * BJ * 3; k += THREADS) racc[k] = 0.f;
   __syncthreads();
+  const int nitems = nitems_s[0];
 
-  // first record and record count of band unit u (0 when the unit lies beyond N: ragged last block)
-  auto unit_j0 = [&](int u) {
-    const int q = u / cpb;
-    int J = I0 + q;
-    if (J >= n) J -= n;
-    return J * B + (u - q * cpb) * BJ;
-  };
-  auto unit_nj = [&](int j0) {
-    const int blk_end = min(p.N, (j0 / B + 1) * B);
-    return min(BJ, blk_end - j0);
-  };
-  // units of the window that tile t owns: blocks q in [t, t + partner_count(I0 + t)]
-  auto tile_ub = [&](int t) { return max(u0, t * cpb); };
-  auto tile_ue = [&](int t) {
-    int g = I0 + t;
-    if (g >= n) g -= n;
-    return min(u1, (t + sym_partner_count(g, n) + 1) * cpb);
-  };
-  // the CTA's work list: (tile, unit) in tile-major order, empty units skipped
-  auto advance = [&](int& t, int& u) {   // step to the next non-empty item at or after (t, u)
-    while (t < ntiles) {
-      const int ue = tile_ue(t);
-      while (u < ue && unit_nj(unit_j0(u)) <= 0) ++u;
-      if (u < ue) return;
-      ++t;
-      if (t < ntiles) u = tile_ub(t);
-    }
-  };
-  auto issue = [&](int u, int st) {
-    const int j0 = unit_j0(u);
-    const uint32_t bytes = (uint32_t)unit_nj(j0) * 16u;
+  auto issue = [&](int it, int st) {
+    const int2 d = items[it];
+    const uint32_t bytes = (uint32_t)(d.y & 1023) * 16u;
     mbar_expect_tx(&bars[st], bytes);
-    bulk_g2s(tile_u + (size_t)st * BJ, p.jrec + j0, bytes, &bars[st]);
+    bulk_g2s(tile_u + (size_t)st * BJ, p.jrec + d.x, bytes, &bars[st]);
   };
-
-  int ct = 0, cu = tile_ub(0);
-  advance(ct, cu);
-  int nload = 0, ncons = 0;
-  if (ct < ntiles) {
-    if (tid == 0) issue(cu, 0);
-    nload = 1;
-  }
+  if (nitems > 0 && tid == 0) issue(0, 0);
 
   PairI<V> pi[NPAIR];
   PairAcc<V> acc[NPAIR];
@@ -350,6 +341,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
   for (int q = 0; q < NPAIR; ++q) {
     acc[q].fx = acc[q].fy = acc[q].fz = acc[q].s6 = acc[q].w = zero2;
     s6run[q] = wrun[q] = fxrun[q] = fyrun[q] = fzrun[q] = zero2;
+    pi[q].ax = pi[q].ay = pi[q].az = pi[q].bx = pi[q].by = pi[q].bz = 0;
+    pi[q].x2 = pi[q].y2 = pi[q].z2 = zero2;
+    pi[q].i_lo = pi[q].i_hi = 0u;
+    pi[q].v_lo = pi[q].v_hi = false;
   }
   RdfCtx R;
   R.q = queues + warp * kRdfQueueCap;
@@ -359,118 +354,124 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
   uint4* mystage = stage + warp * 64;
   double wsum = 0.;
   float4* out = p.fpart + (size_t)blockIdx.y * p.ilocal_cap;
+  unsigned int stored = 0u;      // tiles whose row segment has been written
+  int ibase = ibase0;            // first particle of the tile in registers
+  int cur_tile = -1;
+  bool warp_all_valid = false;
+  uint4 my_lo = make_uint4(0u, 0u, 0u, 0u), my_hi = my_lo;   // bounding box of my own block (RDF pruning)
 
-  for (int t = 0; t < ntiles; ++t) {
-    // ---- tile t: its i-particles into registers
-    const int ibase = ibase0 + t * B;
-    int gI = I0 + t;
-    if (gI >= n) gI -= n;
-    const bool all_valid = load_i_particles<V, PERIODIC, THREADS, NPAIR>(p, ibase, pi);
-    // is every lane of this warp holding real particles? (warp-uniform choice of the unmasked fast path)
-    const bool warp_all_valid = __all_sync(0xffffffffu, all_valid);
-    uint4 my_lo = make_uint4(0u, 0u, 0u, 0u), my_hi = my_lo;   // bounding box of my own block (RDF pruning)
-    if (RDF && sp.bbox != nullptr) { my_lo = sp.bbox[2 * gI]; my_hi = sp.bbox[2 * gI + 1]; }
-
-    while (ct == t) {
-      const int cur = cu;
-      int nt = ct, nu = cu + 1;
-      advance(nt, nu);
-      if (nt < ntiles) {
-        if (tid == 0) issue(nu, nload & 1);
-        ++nload;
-      }
-      const int st = ncons & 1;
-      mbar_wait(&bars[st], (uint32_t)((ncons >> 1) & 1));
-      ++ncons;
-      const int j0 = unit_j0(cur);
-      const int nj = unit_nj(j0);
-      const bool diag = (cur / cpb == t);
-      const uint4* tu = tile_u + (size_t)st * BJ;
-      float wgt;
-      if (diag) {
-        // ---- diagonal block: ordered loop over its own particles, self pair excluded ----
-        wgt = 1.f;
-        const int jrel0 = j0 - ibase - tid;
-#pragma unroll 2
-        for (int j = 0; j < nj; ++j) {
-          const uint4 uj = tu[j];
-          const int jr = jrel0 + j;
+  // the tile in registers is done for this window: its partial forces leave the CTA
+  auto store_tile = [&]() {
+    const float fs = p.fscale;
 #pragma unroll
-          for (int q = 0; q < NPAIR; ++q)
-            pair_body<V, PERIODIC, true, RDF>(uj, pi[q], acc[q], jr == (2 * q) * THREADS, jr == (2 * q + 1) * THREADS,
-                                              p, (unsigned)(j0 + j), R);
-        }
-      } else {
-        // ---- partner block: each unordered pair once, reaction accumulators travel with the rotating j ----
-        wgt = 2.f;
-        if (RDF) {
-          // bounding boxes of the two blocks farther apart than the histogram range: no pair of this unit can
-          // count, run the plain loop (uniform: every thread of the CTA sees the same two boxes)
-          bool near = true;
-          if (sp.bbox != nullptr) {
-            const int J = j0 / B;
-            near = boxes_in_range<PERIODIC>(my_lo, my_hi, sp.bbox[2 * J], sp.bbox[2 * J + 1], p.L, sp.bbox_cut2);
-          }
-          if (near) { LJMD_SYM_PARTNER_CHUNKS(true) } else { LJMD_SYM_PARTNER_CHUNKS(false) }
-        } else {
-          LJMD_SYM_PARTNER_CHUNKS(false)
-        }
+    for (int q = 0; q < NPAIR; ++q) {
+      const float2 fx = upk(fxrun[q]), fy = upk(fyrun[q]), fz = upk(fzrun[q]);
+      const float2 s6 = upk(s6run[q]), w = upk(wrun[q]);
+      const int il = (ibase - p.i_begin) + (2 * q) * THREADS + tid;
+      // r^-12 - r^-6 = u/12 - r^-6/2
+      if (pi[q].v_lo) {
+        out[il] = make_float4(fx.x * fs, fy.x * fs, fz.x * fs, w.x * (1.f / 12.f) - 0.5f * s6.x);
+        wsum += (double)w.x;
       }
-      // fold the unit's tile-level accumulators into the run-level ones (two-level float summation);
-      // an unordered pair of a partner block stands for two ordered pairs in the potential / virial sums
-      const V w2 = bc2<V>(wgt);
-#pragma unroll
-      for (int q = 0; q < NPAIR; ++q) {
-        s6run[q] = fma2(acc[q].s6, w2, s6run[q]);
-        wrun[q] = fma2(acc[q].w, w2, wrun[q]);
-        fxrun[q] = add2(fxrun[q], acc[q].fx);
-        fyrun[q] = add2(fyrun[q], acc[q].fy);
-        fzrun[q] = add2(fzrun[q], acc[q].fz);
-        acc[q].s6 = acc[q].w = acc[q].fx = acc[q].fy = acc[q].fz = zero2;
+      if (pi[q].v_hi) {
+        out[il + THREADS] = make_float4(fx.y * fs, fy.y * fs, fz.y * fs, w.y * (1.f / 12.f) - 0.5f * s6.y);
+        wsum += (double)w.y;
       }
-      __syncthreads();  // slices complete; stage st free for the load after next
-      if (!diag) {
-        // reaction of this unit: sum the warps' slices in warp order, add to the window accumulator
-        float* ra = racc + (size_t)(cur - u0) * BJ * 3;
-        for (int k = tid; k < nj * 3; k += THREADS) {
-          float a = slices[k];
-#pragma unroll
-          for (int w = 1; w < NW; ++w) a += slices[(size_t)w * BJ * 3 + k];
-          ra[k] += a;
-        }
-        __syncthreads();  // slices are rewritten by the next partner unit
-      }
-      ct = nt;
-      cu = nu;
+      s6run[q] = wrun[q] = fxrun[q] = fyrun[q] = fzrun[q] = zero2;
     }
-    // ---- tile t done for this window: its partial forces leave the CTA (zeros when it owned no unit here)
-    {
-      const float fs = p.fscale;
+    stored |= 1u << cur_tile;
+  };
+
+  for (int it = 0; it < nitems; ++it) {
+    if (it + 1 < nitems && tid == 0) issue(it + 1, (it + 1) & 1);
+    const int2 d = items[it];
+    const int j0 = d.x, nj = d.y & 1023;
+    const bool diag = (d.y >> 24) & 1;
+    if ((d.y >> 25) & 1) {
+      // ---- next tile: the finished one leaves, its successor's i-particles come into the registers
+      if (cur_tile >= 0) store_tile();
+      cur_tile = (d.y >> 16) & 255;
+      ibase = ibase0 + cur_tile * B;
+      const bool all_valid = load_i_particles<V, PERIODIC, THREADS, NPAIR>(p, ibase, pi);
+      // is every lane of this warp holding real particles? (warp-uniform choice of the unmasked fast path)
+      warp_all_valid = __all_sync(0xffffffffu, all_valid);
+      if (RDF && sp.bbox != nullptr) { const int gI = ibase / B; my_lo = sp.bbox[2 * gI]; my_hi = sp.bbox[2 * gI + 1]; }
+    }
+    const int st = it & 1;
+    mbar_wait(&bars[st], (uint32_t)((it >> 1) & 1));
+    const uint4* tu = tile_u + (size_t)st * BJ;
+    float wgt;
+    if (diag) {
+      // ---- diagonal block: ordered loop over its own particles, self pair excluded ----
+      wgt = 1.f;
+      const int jrel0 = j0 - ibase - tid;
+#pragma unroll 2
+      for (int j = 0; j < nj; ++j) {
+        const uint4 uj = tu[j];
+        const int jr = jrel0 + j;
 #pragma unroll
-      for (int q = 0; q < NPAIR; ++q) {
-        const float2 fx = upk(fxrun[q]), fy = upk(fyrun[q]), fz = upk(fzrun[q]);
-        const float2 s6 = upk(s6run[q]), w = upk(wrun[q]);
-        const int il = (ibase - p.i_begin) + (2 * q) * THREADS + tid;
-        // r^-12 - r^-6 = u/12 - r^-6/2
-        if (pi[q].v_lo) {
-          out[il] = make_float4(fx.x * fs, fy.x * fs, fz.x * fs, w.x * (1.f / 12.f) - 0.5f * s6.x);
-          wsum += (double)w.x;
-        }
-        if (pi[q].v_hi) {
-          out[il + THREADS] = make_float4(fx.y * fs, fy.y * fs, fz.y * fs, w.y * (1.f / 12.f) - 0.5f * s6.y);
-          wsum += (double)w.y;
-        }
-        s6run[q] = wrun[q] = fxrun[q] = fyrun[q] = fzrun[q] = zero2;
+        for (int q = 0; q < NPAIR; ++q)
+          pair_body<V, PERIODIC, true, RDF>(uj, pi[q], acc[q], jr == (2 * q) * THREADS, jr == (2 * q + 1) * THREADS,
+                                            p, (unsigned)(j0 + j), R);
       }
+    } else {
+      // ---- partner block: each unordered pair once, reaction accumulators travel with the rotating j ----
+      wgt = 2.f;
+      if (RDF) {
+        // bounding boxes of the two blocks farther apart than the histogram range: no pair of this unit can
+        // count, run the plain loop (uniform: every thread of the CTA sees the same two boxes)
+        bool near = true;
+        if (sp.bbox != nullptr) {
+          const int J = j0 / B;
+          near = boxes_in_range<PERIODIC>(my_lo, my_hi, sp.bbox[2 * J], sp.bbox[2 * J + 1], p.L, sp.bbox_cut2);
+        }
+        if (near) { LJMD_SYM_PARTNER_CHUNKS(true) } else { LJMD_SYM_PARTNER_CHUNKS(false) }
+      } else {
+        LJMD_SYM_PARTNER_CHUNKS(false)
+      }
+    }
+    // fold the unit's tile-level accumulators into the run-level ones (two-level float summation);
+    // an unordered pair of a partner block stands for two ordered pairs in the potential / virial sums
+    const V w2 = bc2<V>(wgt);
+#pragma unroll
+    for (int q = 0; q < NPAIR; ++q) {
+      s6run[q] = fma2(acc[q].s6, w2, s6run[q]);
+      wrun[q] = fma2(acc[q].w, w2, wrun[q]);
+      fxrun[q] = add2(fxrun[q], acc[q].fx);
+      fyrun[q] = add2(fyrun[q], acc[q].fy);
+      fzrun[q] = add2(fzrun[q], acc[q].fz);
+      acc[q].s6 = acc[q].w = acc[q].fx = acc[q].fy = acc[q].fz = zero2;
+    }
+    __syncthreads();  // slices complete; stage st free for the load after next
+    if (!diag) {
+      // reaction of this unit: sum the warps' slices in warp order, add to the window accumulator
+      float* ra = racc + (size_t)((d.y >> 10) & 63) * BJ * 3;
+      for (int k = tid; k < nj * 3; k += THREADS) {
+        float a = slices[k];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) a += slices[(size_t)w * BJ * 3 + k];
+        ra[k] += a;
+      }
+      __syncthreads();  // slices are rewritten by the next partner unit
+    }
+  }
+  if (cur_tile >= 0) store_tile();
+  // tiles that own no unit of this window (triangles at the ends of the band) still owe their zero rows
+  for (int t = 0; t < ntiles; ++t) {
+    if ((stored >> t) & 1u) continue;
+#pragma unroll
+    for (int m = 0; m < IPT; ++m) {
+      const int i = ibase0 + t * B + m * THREADS + tid;
+      if (i < p.i_end) out[i - p.i_begin] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
 
   // ---- the window's reaction sums leave the CTA: one block of rpart, every entry written (zeros included),
   // so the gather kernels never read stale data and nothing has to be cleared between steps
   {
-    float4* dst = sp.rpart + ((size_t)blockIdx.x * sp.nwin + win) * ((size_t)MJU * BJ);
+    float4* dst = sp.rpart + ((size_t)blockIdx.x * sp.nwin + win) * ((size_t)sp.mju * BJ);
     const float fs = p.fscale;
-    for (int k = tid; k < MJU * BJ; k += THREADS)
+    for (int k = tid; k < sp.mju * BJ; k += THREADS)
       dst[k] = make_float4(racc[3 * k] * fs, racc[3 * k + 1] * fs, racc[3 * k + 2] * fs, 0.f);
   }
   const double wtot = block_sum<THREADS>(wsum, red);
@@ -491,9 +492,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
 inline size_t force_sym_smem_bytes(bool rdf, int bj, int threads, int mju) {
   const int nw = threads / 32;
   // j-chunk double buffer, per-warp rotation stages, per-warp reaction slices (12 B), window accumulator (12 B),
-  // alignment slack, barriers, block-sum scratch, RDF scratch
-  return (size_t)2 * bj * 16 + (size_t)nw * 64 * 16 + (size_t)nw * bj * 12 + (size_t)mju * bj * 12 + 16 + 16 + 8 * nw +
-         (rdf ? rdf_smem_bytes(threads) : 0);
+  // barriers, block-sum scratch, work list + its length, RDF scratch
+  return (size_t)2 * bj * 16 + (size_t)nw * 64 * 16 + (size_t)nw * bj * 12 + (size_t)mju * bj * 12 + 16 + 8 * nw +
+         kSymMaxItems * 8 + 16 + (rdf ? rdf_smem_bytes(threads) : 0);
 }
 
 }  // namespace ljmd

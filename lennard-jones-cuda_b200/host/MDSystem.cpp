@@ -87,11 +87,34 @@ void MDSystem::Reinitialize(const MDSystem::MDSystemConfiguration& config) {   /
 void MDSystem::ReallocateMemory() {   // MDSystem.cpp:116-144: device buffers follow N
   if (m_sys) ljmd_destroy(m_sys);
   m_sys = 0;
-  int dev = 0;
-  if (const char* e = std::getenv("LJMD_DEVICE")) dev = std::atoi(e);
-  check(ljmd_create(&m_sys, m_config.N, m_config.rho, m_config.T0, m_config.canonical ? 1 : 0,
-                    m_config.boundaryConditions, rdf_dr2, dev),
-        "ljmd_create");
+  // device list: m_config.numGPUs > 1 -> devices 0..numGPUs-1; LJMD_DEVICES="0,1,.." (numGPUs == 0 only, so a
+  // caller that asks for one device gets one); else the single device LJMD_DEVICE (default 0)
+  std::vector<int> devs;
+  if (m_config.numGPUs > 1) {
+    for (int d = 0; d < m_config.numGPUs; ++d) devs.push_back(d);
+  } else if (m_config.numGPUs == 0) {
+    if (const char* e = std::getenv("LJMD_DEVICES")) {
+      for (const char* p = e; *p;) {
+        char* end = 0;
+        const long d = std::strtol(p, &end, 10);
+        if (end == p) break;
+        devs.push_back((int)d);
+        p = (*end == ',') ? end + 1 : end;
+      }
+    }
+  }
+  if (devs.size() > 1) {
+    check(ljmd_create_multi(&m_sys, m_config.N, m_config.rho, m_config.T0, m_config.canonical ? 1 : 0,
+                            m_config.boundaryConditions, rdf_dr2, devs.data(), (int)devs.size()),
+          "ljmd_create_multi");
+  } else {
+    int dev = devs.empty() ? 0 : devs[0];
+    if (devs.empty())
+      if (const char* e = std::getenv("LJMD_DEVICE")) dev = std::atoi(e);
+    check(ljmd_create(&m_sys, m_config.N, m_config.rho, m_config.T0, m_config.canonical ? 1 : 0,
+                      m_config.boundaryConditions, rdf_dr2, dev),
+          "ljmd_create");
+  }
   CUDAInit = true;
   m_host_vel_dirty = false;
 }

@@ -34,8 +34,13 @@ class MDSystem {
     int boundaryConditions;  // 0 periodic, 1 hard wall, 2 none (expansion)
     bool useCUDA;            // accepted for compatibility; the GPU is always used
     int CUDABlockSize;       // accepted for compatibility; launch shapes are chosen by the library
+    // New, defaulted, at the end so that existing aggregate-style code keeps compiling: GPUs of this
+    // node the system is sharded over.  1: one device (LJMD_DEVICE, default 0).  > 1: devices 0..numGPUs-1.
+    // 0: take the list from the environment variable LJMD_DEVICES ("0,1,2,3"), one device when it is unset.
+    int numGPUs;
     MDSystemConfiguration()
-        : N(128), T0(1.5), rho(0.2), canonical(false), boundaryConditions(0), useCUDA(false), CUDABlockSize(256) {}
+        : N(128), T0(1.5), rho(0.2), canonical(false), boundaryConditions(0), useCUDA(false), CUDABlockSize(256),
+          numGPUs(0) {}
   };
 
   MDSystemConfiguration m_config;

@@ -20,13 +20,13 @@ S_COUNT = 16
 
 # every symbol include/ljmd.h declares (tests check the library exports all of them)
 API_SYMBOLS = [
-    "ljmd_last_error", "ljmd_device_count", "ljmd_create", "ljmd_create_distributed", "ljmd_nccl_unique_id",
+    "ljmd_last_error", "ljmd_device_count", "ljmd_create", "ljmd_create_multi", "ljmd_create_distributed", "ljmd_nccl_unique_id",
     "ljmd_fabric_export", "ljmd_fabric_connect", "ljmd_destroy", "ljmd_rdf_dr2", "ljmd_set_canonical", "ljmd_set_boundary", "ljmd_set_T0", "ljmd_set_state",
     "ljmd_set_velocities", "ljmd_upload", "ljmd_get_state", "ljmd_step", "ljmd_integrate_host", "ljmd_compute_forces",
     "ljmd_get_scalars", "ljmd_reset_averaging", "ljmd_get_rdf", "ljmd_get_rdf_accum", "ljmd_velocity_histogram", "ljmd_subvolume_counts", "ljmd_velocity_subvolume_counts",
     "ljmd_trace_begin", "ljmd_trace_row_length", "ljmd_trace_read", "ljmd_trace_end",
-    "ljmd_launch_count", "ljmd_set_event_timing", "ljmd_last_step_timing", "ljmd_last_gather_timing", "ljmd_get_launch_info",
-    "ljmd_image_threshold", "ljmd_plan", "ljmd_plan_newton3", "ljmd_set_l2_flush",
+    "ljmd_launch_count", "ljmd_set_event_timing", "ljmd_last_step_timing", "ljmd_last_gather_timing", "ljmd_last_reduce_timing", "ljmd_get_launch_info",
+    "ljmd_image_threshold", "ljmd_plan", "ljmd_plan_newton3", "ljmd_set_l2_flush", "ljmd_fp32_peak_probe",
     # legacy seam (MDSystem.cpp:9-25)
     "allocateArray", "deleteArray", "copyArrayToDevice", "copyArrayFromDevice", "calculateNForces", "threadExit",
     "allocateNBodyArrays", "deleteNBodyArrays", "registerGLBufferObject", "unregisterGLBufferObject", "threadSync",
@@ -74,6 +74,7 @@ def load_library(path=None):
     lib.ljmd_launch_count.argtypes = [vp]
     lib.ljmd_create.argtypes = [C.POINTER(vp), C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_float, C.c_int]
     lib.ljmd_create_distributed.argtypes = lib.ljmd_create.argtypes + [C.c_int, C.c_int, vp]
+    lib.ljmd_create_multi.argtypes = [C.POINTER(vp), C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_float, ip, C.c_int]
     lib.ljmd_nccl_unique_id.argtypes = [vp]
     lib.ljmd_destroy.argtypes = [vp]
     lib.ljmd_fabric_export.argtypes = [vp, vp]
@@ -103,10 +104,12 @@ def load_library(path=None):
     lib.ljmd_last_step_timing.argtypes = [vp, dp, dp, ip]
     lib.ljmd_get_launch_info.argtypes = [vp, ip]
     lib.ljmd_last_gather_timing.argtypes = [vp, dp, ip, dp]
+    lib.ljmd_last_reduce_timing.argtypes = [vp, dp, ip, dp]
     lib.ljmd_set_l2_flush.argtypes = [vp, C.c_longlong]
     lib.ljmd_image_threshold.restype = C.c_float
     lib.ljmd_image_threshold.argtypes = [C.c_double, C.c_int]
     lib.ljmd_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, ip]
+    lib.ljmd_plan_newton3.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, ip]
     lib.calculateNForces.argtypes = [vp, vp, fp, C.c_int, C.c_float, C.c_int, ip, C.c_float, C.c_int, C.c_int]
     lib.calculateNForces.restype = None
     lib.allocateArray.argtypes = [C.POINTER(vp), C.c_int]
@@ -143,14 +146,24 @@ class LJSystem:
     """
 
     def __init__(self, N, T0=1.5, rho=0.2, canonical=False, bc=BC_PERIODIC, device=0, rank=0, world=1,
-                 nccl_unique_id=None, rdf_dr2=None):
+                 nccl_unique_id=None, rdf_dr2=None, devices=None):
+        """devices=[d0, d1, ...]: ONE handle in ONE process drives all listed GPUs (ljmd_create_multi: i-shards
+        over the devices, exchange over NVLink peer memory, no NCCL and no launcher).  rank/world/nccl_unique_id:
+        one process per GPU (ljmd_create_distributed)."""
         self._lib = load_library()
         self._h = C.c_void_p()
         self.N, self.T0, self.rho, self.bc, self.canonical = int(N), float(T0), float(rho), int(bc), bool(canonical)
         self.rank, self.world = rank, world
         dr2 = self._lib.ljmd_rdf_dr2(self.N) if rdf_dr2 is None else rdf_dr2
         self.rdf_dr2 = float(dr2)
-        if world == 1:
+        self.devices = list(devices) if devices is not None else None
+        if self.devices is not None:
+            if world != 1:
+                raise ValueError("devices=[...] (one process, many GPUs) excludes rank/world (one process per GPU)")
+            arr = (C.c_int * len(self.devices))(*self.devices)
+            rc = self._lib.ljmd_create_multi(C.byref(self._h), self.N, self.rho, self.T0, int(self.canonical), self.bc,
+                                             C.c_float(dr2), arr, len(self.devices))
+        elif world == 1:
             rc = self._lib.ljmd_create(C.byref(self._h), self.N, self.rho, self.T0, int(self.canonical), self.bc,
                                        C.c_float(dr2), device)
         else:
@@ -352,6 +365,11 @@ class LJSystem:
         self._check(self._lib.ljmd_last_gather_timing(self._h, C.byref(ms), C.byref(n), C.byref(b)))
         return dict(gather_ms=ms.value, launches=n.value, bytes_per_launch=b.value)
 
+    def last_reduce_timing(self):
+        ms, n, b = C.c_double(0), C.c_int(0), C.c_double(0)
+        self._check(self._lib.ljmd_last_reduce_timing(self._h, C.byref(ms), C.byref(n), C.byref(b)))
+        return dict(reduce_ms=ms.value, launches=n.value, bytes_per_launch=b.value)
+
     def launch_info(self):
         buf = (C.c_int * 8)()
         self._check(self._lib.ljmd_get_launch_info(self._h, buf))
@@ -372,6 +390,17 @@ def plan(N, rank=0, world=1, num_sms=148):
         raise LJMDError(lib.ljmd_last_error().decode())
     return dict(i_begin=buf[0], i_end=buf[1], i_tiles=buf[2], j_splits=buf[3], force_ctas=buf[4], i_tile=buf[5],
                 newton3=bool(buf[6]), partner_blocks=buf[7])
+
+
+def fp32_peak_probe(device=0):
+    """Measured FP32 CUDA-core throughput (TFLOP/s) of `device`: a stream of independent packed FMAs."""
+    lib = load_library()
+    out = C.c_double(0.0)
+    lib.ljmd_fp32_peak_probe.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    rc = lib.ljmd_fp32_peak_probe(int(device), C.byref(out))
+    if rc != 0:
+        raise LJMDError(lib.ljmd_last_error().decode())
+    return float(out.value)
 
 
 def plan_newton3(N, rank=0, world=1, num_sms=148):

@@ -394,8 +394,9 @@ int main(int argc, char** argv) {
   if (argc > 3 && !strcmp(argv[3], "super")) {
     // super-tile shapes (mi x mju): kernel time and bytes of partial-force + reaction output per launch
     if (N <= 262144) run_variant<P2, true, false, 128, 4, 2, 4>(pb, "periodic ordered P2 t128 b4 np2 u4", reps, 1024, &keepP);
-    const int mis[] = {1, 2, 4, 8, 16};
-    const int mjus[] = {4, 8, 12, 16};
+    const bool quick = argc > 4 && !strcmp(argv[4], "quick");
+    const std::vector<int> mis = quick ? std::vector<int>{1, 4, 16} : std::vector<int>{1, 2, 4, 8, 16};
+    const std::vector<int> mjus = quick ? std::vector<int>{8, 16} : std::vector<int>{4, 8, 12, 16};
     for (int mju : mjus)
       for (int mi : mis) {
         char tag[96];
