@@ -40,6 +40,15 @@ except Exception:
     pass
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def measured_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -235,7 +244,7 @@ def main_reference(args, pkg):
         "e2e": {"value": r["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -481,12 +490,19 @@ def main_ours(args, pkg):
                           f"cost is N(N-1) pair evaluations per step); {host_description()}"}
             # the reference's own CUDA kernel on this GPU (the bar row a-3' of SURVEY.md 8 names)
             line["reference_gpu"] = reference_gpu_leg()
-        print(json.dumps(line))
+        emit(line)
     D.finalize()
     return 0
 
 
 def main():
+    # The contract is ONE JSON line on stdout.  Libraries loaded below write there too (NCCL prints its version
+    # banner on stdout at communicator creation), so file descriptor 1 is pointed at stderr for the run and the
+    # JSON line goes to the saved descriptor.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -185,6 +185,23 @@ int ljmd_compute_forces(ljmd_system* s, int with_rdf);
 /* out[LJMD_S_COUNT] doubles, see the enum above. */
 int ljmd_get_scalars(ljmd_system* s, double* out);
 
+/*
+ * Shear stress P_xy, the one observable the reference computes on its CPU path only (MDSystem.cpp:299,309,335,353;
+ * its GPU path leaves the member stale): (2 * sum_{i, j != i} (-r_x,ij f_y,ij / 4) + sum_i (-v_x v_y)) / (N / rho) for
+ * the positions of the latest force evaluation and the current velocities.  Evaluated ON DEMAND by a separate
+ * all-pairs pass (about the cost of one ordered force evaluation), so the step's hot loop does not pay for an
+ * observable nothing in the reference reads.
+ */
+int ljmd_get_pshear(ljmd_system* s, double* pshear);
+
+/*
+ * Device-resident state of a single-device handle: float4 arrays of N entries (pos.w = L/150 as in h_Pos) and the
+ * CUDA stream (cudaStream_t) the library orders its work on.  For renderers and downstream CUDA code that would
+ * otherwise pay a D2H copy per frame (the reference's registerGLBufferObject hooks are stubs, MDSystem.cu:199-226).
+ * Any pointer may be NULL.  Read-only for the caller; valid until ljmd_destroy.
+ */
+int ljmd_device_arrays(ljmd_system* s, const void** pos4, const void** vel4, const void** force4, void** stream);
+
 /* MDSystem::resetAveraging (MDSystem.cpp:701-705). */
 int ljmd_reset_averaging(ljmd_system* s);
 

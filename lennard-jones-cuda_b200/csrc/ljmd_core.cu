@@ -1665,6 +1665,132 @@ int ljmd_legacy_forces(ljmd_system* s, const float* d_pos, float* d_force, float
   return LJMD_OK;
 }
 
+// ------------------------------------------------------------------- shear stress, on demand
+// Pshear = (4/2 * sum_i sum_{j != i} (-r_x,ij * f_y,ij / 4) + sum_i (-v_x v_y)) / (N / rho), MDSystem.cpp:299,309,335,353.
+// The reference computes it on its CPU path only and nothing reads it (its GPU path leaves the member stale), so
+// it is kept OUT of the force kernels' hot loop: one more accumulator there costs ~4 % of every step.  This kernel
+// is a plain ordered all-pairs pass over the saved evaluation positions: one i per thread, j-records staged in
+// shared memory, float products, double accumulation per thread.
+template <bool PERIODIC>
+__global__ void __launch_bounds__(256) k_shear(const uint4* __restrict__ jrec, const float4* __restrict__ vel, int N,
+                                               int i_begin, int i_end, float c2, double kunit, double* __restrict__ out2) {
+  __shared__ uint4 tile[256];
+  __shared__ double red[2][8];
+  const int i = i_begin + blockIdx.x * 256 + threadIdx.x;
+  const bool live = i < i_end;
+  const uint4 me = jrec[live ? i : i_begin];
+  double acc = 0.;
+  for (int j0 = 0; j0 < N; j0 += 256) {
+    __syncthreads();
+    tile[threadIdx.x] = jrec[min(j0 + (int)threadIdx.x, N - 1)];
+    __syncthreads();
+    const int nj = min(256, N - j0);
+    float part = 0.f;
+    for (int j = 0; j < nj; ++j) {
+      const uint4 u = tile[j];
+      float dx, dy, dz;
+      if (PERIODIC) {
+        dx = __int2float_rn((int)me.x - (int)u.x); dy = __int2float_rn((int)me.y - (int)u.y); dz = __int2float_rn((int)me.z - (int)u.z);
+      } else {
+        dx = __uint_as_float(me.x) - __uint_as_float(u.x); dy = __uint_as_float(me.y) - __uint_as_float(u.y);
+        dz = __uint_as_float(me.z) - __uint_as_float(u.z);
+      }
+      const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+      float x = (j0 + j == i) ? 0.f : rcp_approx(r2);
+      if (PERIODIC) x *= c2;
+      const float r6 = x * x * x;
+      const float sfac = r6 * fmaf(r6, 12.f, -6.f) * x;   // r^-2 (12 r^-12 - 6 r^-6)
+      part = fmaf(-dx * dy, sfac, part);                   // -r_x * f_y / 4 (coordinates in k-units when periodic)
+    }
+    acc += (double)part;
+  }
+  if (!live) acc = 0.;
+  acc *= kunit * kunit;                                    // k-units^2 -> sigma^2 (1 for open boxes)
+  double kin = 0.;
+  if (live) { const float4 v = vel[i - i_begin]; kin = (double)(-v.x * v.y); }   // :335 float product, double sum
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { acc += __shfl_xor_sync(0xffffffffu, acc, o); kin += __shfl_xor_sync(0xffffffffu, kin, o); }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = acc; red[1][threadIdx.x >> 5] = kin; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0., k = 0.;
+    for (int w = 0; w < 8; ++w) { a += red[0][w]; k += red[1][w]; }
+    out2[2 * blockIdx.x] = a;
+    out2[2 * blockIdx.x + 1] = k;
+  }
+}
+
+// conf: sum_i sum_{j != i} (-r_x f_y) * 4/2 over this handle's i-particles; kin: sum_i (-v_x v_y)
+static int shear_parts(ljmd_system* s, double* conf, double* kin) {
+  CHECK_S(s);
+  const bool periodic = (s->bc == LJMD_BC_PERIODIC);
+  const int nb = (s->nloc + 255) / 256;
+  double* d = nullptr;
+  CU(cudaMalloc(&d, (size_t)2 * nb * sizeof(double)));
+  const double k2 = 4294967296.0 / s->L;
+  const uint4* jrec = periodic ? s->upos : reinterpret_cast<const uint4*>(s->posA);
+  if (periodic) k_shear<true><<<nb, 256, 0, s->stream>>>(jrec, s->vel, s->N, s->i_begin, s->i_end, (float)(k2 * k2), 1. / k2, d);
+  else k_shear<false><<<nb, 256, 0, s->stream>>>(jrec, s->vel, s->N, s->i_begin, s->i_end, 1.f, 1., d);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { cudaFree(d); return set_err(LJMD_ERR_CUDA, "k_shear launch: %s", cudaGetErrorString(e)); }
+  s->launches += 1;
+  std::vector<double> h((size_t)2 * nb);
+  e = cudaMemcpyAsync(h.data(), d, h.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return set_err(LJMD_ERR_CUDA, "k_shear: %s", cudaGetErrorString(e));
+  double a = 0., k = 0.;
+  for (int b = 0; b < nb; ++b) { a += h[2 * b]; k += h[2 * b + 1]; }   // fixed order: deterministic
+  *conf = a * (4. / 2.);                                                // :309
+  *kin = k;
+  return LJMD_OK;
+}
+
+extern "C" int ljmd_get_pshear(ljmd_system* s, double* pshear) {
+  if (!s || !pshear) return set_err(LJMD_ERR_ARG, "NULL argument");
+  double conf = 0., kin = 0.;
+  if (s->multi) {
+    const int G = multi_count(s);
+    std::vector<double> c(G, 0.), k(G, 0.);
+    const int rc = multi_all(s, [&](ljmd_system* sub, int r) { return shear_parts(sub, &c[r], &k[r]); });
+    if (rc) return rc;
+    for (int r = 0; r < G; ++r) { conf += c[r]; kin += k[r]; }
+  } else {
+    int rc = shear_parts(s, &conf, &kin);
+    if (rc) return rc;
+#ifdef LJMD_WITH_NCCL
+    if (s->world > 1) {   // rare read-out: host-staged all-reduce of two doubles through the scratch buffer
+      double two[2] = {conf, kin};
+      CU(cudaMemcpyAsync(s->gath, two, sizeof(two), cudaMemcpyHostToDevice, s->stream));
+      NC(ncclAllReduce(s->gath, s->gath, 2, ncclDouble, ncclSum, s->comm, s->stream));
+      CU(cudaMemcpyAsync(two, s->gath, sizeof(two), cudaMemcpyDeviceToHost, s->stream));
+      CU(cudaStreamSynchronize(s->stream));
+      conf = two[0]; kin = two[1];
+    }
+#endif
+  }
+  *pshear = (conf + kin) / ((double)s->N / s->rho);   // :353
+  return LJMD_OK;
+}
+
+// ------------------------------------------------------------------- device pointers
+// The arrays a renderer or a downstream CUDA consumer reads every frame, without the D2H copy the reference's GUI
+// pays (MDSystemGL.cpp:150-151 hands h_Pos to glVertexPointer; its registerGLBufferObject hooks are stubs,
+// MDSystem.cu:199-226).  A GL client maps its own buffer with cudaGraphicsGLRegisterBuffer and copies device to
+// device from these pointers on the stream returned here, or reads them in its own kernels.  Single-device
+// handles only (a sharded system has no one device holding the velocities).  Valid until ljmd_destroy; positions
+// are float4 (x,y,z,w = L/150), exactly what h_Pos holds after Integrate.
+extern "C" int ljmd_device_arrays(ljmd_system* s, const void** pos4, const void** vel4, const void** force4, void** stream) {
+  if (s && s->multi) return set_err(LJMD_ERR_ARG, "device arrays are exported by single-device handles only");
+  CHECK_S(s);
+  if (s->world > 1) return set_err(LJMD_ERR_ARG, "device arrays are exported by single-device handles only");
+  if (pos4) *pos4 = s->pos;
+  if (vel4) *vel4 = s->vel;
+  if (force4) *force4 = s->force;
+  if (stream) *stream = (void*)s->stream;
+  return LJMD_OK;
+}
+
 // ------------------------------------------------------------------- FP32 peak probe (roofline denominator)
 // A stream of independent packed FMAs (FFMA2, 8 chains per thread, 16 warps per SM sub-partition): the FP32
 // CUDA-core rate this device sustains, measured with CUDA events.  bench.py reports the force kernel against this

@@ -156,10 +156,11 @@ void MDSystem::CorrectTotalMomentum() {   // MDSystem.cpp:183-216
   const int N = m_config.N;
   double px = 0., py = 0., pz = 0.;
   for (int i = 0; i < 4 * N; i += 4) { px += h_Vel[i]; py += h_Vel[i + 1]; pz += h_Vel[i + 2]; }
-  for (int i = 0; i < 4 * N; i += 4) {
-    h_Vel[i] += (float)(-px / N);
-    h_Vel[i + 1] += (float)(-py / N);
-    h_Vel[i + 2] += (float)(-pz / N);
+  const double totmass = N;   // the reference counts unit masses in a double (:186-192)
+  for (int i = 0; i < 4 * N; i += 4) {   // float += double: the sum is formed in double and rounded once (:199-201)
+    h_Vel[i] += -px / totmass;
+    h_Vel[i + 1] += -py / totmass;
+    h_Vel[i + 2] += -pz / totmass;
   }
   m_host_vel_dirty = true;
 }
@@ -175,6 +176,10 @@ void MDSystem::pullScalars(bool accumulate) {
   double s[LJMD_S_COUNT];
   check(ljmd_get_scalars(m_sys, s), "ljmd_get_scalars");
   U = s[LJMD_S_U]; T = s[LJMD_S_T]; K = s[LJMD_S_K]; V = s[LJMD_S_V]; P = s[LJMD_S_P];
+  // P_xy: the reference computes it on its CPU path only and nothing reads it; an extra all-pairs pass per step,
+  // so it is filled only on request (LJMD_PSHEAR=1), and is 0 otherwise — what DESIGN.md documents
+  static const bool want_shear = std::getenv("LJMD_PSHEAR") && std::getenv("LJMD_PSHEAR")[0] == '1';
+  if (want_shear) check(ljmd_get_pshear(m_sys, &Pshear), "ljmd_get_pshear");
   if (accumulate) {   // MDSystem.cpp:355-358
     av_iters++;
     av_U_tot += U;
@@ -325,7 +330,10 @@ void MDSystem::updatevelo() {   // MDSystem.cpp:676-694
   const int maxind = (int)curvelo.vals.size();
   const double shag = curvelo.vals[1].first - curvelo.vals[0].first;
   std::vector<int> dens(maxind, 0);
-  if (m_host_vel_dirty) check(ljmd_upload(m_sys, 0, h_Vel), "ljmd_upload");
+  // h_Vel is a public member the reference reads here (:684): a caller may have edited it in place since the last
+  // call, so it always goes up (16 B per particle, once per GUI frame)
+  check(ljmd_upload(m_sys, 0, h_Vel), "ljmd_upload");
+  m_host_vel_dirty = false;
   check(ljmd_velocity_histogram(m_sys, shag, maxind, dens.data()), "ljmd_velocity_histogram");
   for (int i = 0; i < maxind; ++i)
     curvelo.vals[i].second = (curvelo.vals[i].second * veloIters + dens[i] / shag / N) / (veloIters + 1);

@@ -23,7 +23,7 @@ API_SYMBOLS = [
     "ljmd_last_error", "ljmd_device_count", "ljmd_create", "ljmd_create_multi", "ljmd_create_distributed", "ljmd_nccl_unique_id",
     "ljmd_fabric_export", "ljmd_fabric_connect", "ljmd_destroy", "ljmd_rdf_dr2", "ljmd_set_canonical", "ljmd_set_boundary", "ljmd_set_T0", "ljmd_set_state",
     "ljmd_set_velocities", "ljmd_upload", "ljmd_get_state", "ljmd_step", "ljmd_integrate_host", "ljmd_compute_forces",
-    "ljmd_get_scalars", "ljmd_reset_averaging", "ljmd_get_rdf", "ljmd_get_rdf_accum", "ljmd_velocity_histogram", "ljmd_subvolume_counts", "ljmd_velocity_subvolume_counts",
+    "ljmd_get_scalars", "ljmd_get_pshear", "ljmd_device_arrays", "ljmd_reset_averaging", "ljmd_get_rdf", "ljmd_get_rdf_accum", "ljmd_velocity_histogram", "ljmd_subvolume_counts", "ljmd_velocity_subvolume_counts",
     "ljmd_trace_begin", "ljmd_trace_row_length", "ljmd_trace_read", "ljmd_trace_end",
     "ljmd_launch_count", "ljmd_set_event_timing", "ljmd_last_step_timing", "ljmd_last_gather_timing", "ljmd_last_reduce_timing", "ljmd_get_launch_info",
     "ljmd_image_threshold", "ljmd_plan", "ljmd_plan_newton3", "ljmd_set_l2_flush", "ljmd_fp32_peak_probe",
@@ -91,6 +91,8 @@ def load_library(path=None):
     lib.ljmd_compute_forces.argtypes = [vp, C.c_int]
     lib.ljmd_get_scalars.argtypes = [vp, dp]
     lib.ljmd_reset_averaging.argtypes = [vp]
+    lib.ljmd_get_pshear.argtypes = [vp, dp]
+    lib.ljmd_device_arrays.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.ljmd_get_rdf.argtypes = [vp, ip]
     lib.ljmd_get_rdf_accum.argtypes = [vp, C.POINTER(C.c_longlong), ip, C.c_int]
     lib.ljmd_velocity_histogram.argtypes = [vp, C.c_double, C.c_int, ip]
@@ -279,6 +281,18 @@ class LJSystem:
         names = ["U", "T", "K", "V", "P", "Pvirial", "t", "L", "av_U_tot", "av_T_tot", "av_p_tot", "av_iters", "chi",
                  "Tkin_trial"]
         return {n: buf[i] for i, n in enumerate(names)}
+
+    def pshear(self):
+        """Shear stress P_xy (MDSystem.cpp:299,309,335,353), evaluated on demand."""
+        out = C.c_double(0.0)
+        self._check(self._lib.ljmd_get_pshear(self._h, C.byref(out)))
+        return float(out.value)
+
+    def device_arrays(self):
+        """Device pointers (ints) of pos / vel / force (float4[N]) and the library's CUDA stream."""
+        p, v, f, st = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(self._lib.ljmd_device_arrays(self._h, C.byref(p), C.byref(v), C.byref(f), C.byref(st)))
+        return dict(pos=p.value, vel=v.value, force=f.value, stream=st.value or 0)
 
     def reset_averaging(self):
         self._check(self._lib.ljmd_reset_averaging(self._h))

@@ -17,6 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_LIB = os.path.join(HERE, "libljmd_oracle.so")
 REF_LIB = os.path.join(HERE, "_ref", "libljmd_ref.so")
 REF_LEGACY_LIB = os.path.join(HERE, "_ref", "libljmd_ref_legacy.so")
+HOST_SHIM_LIB = os.path.join(HERE, "libljmd_host_shim.so")   # the same shim over the PRODUCT's MDSystem class
 RDF_BINS = 256
 
 
@@ -154,8 +155,10 @@ class Reference:
 
     @classmethod
     def lib(cls, legacy=False):
+        """legacy: False = reference CPU path, True = reference host layer on the product's legacy seam,
+        "product" = the product's own MDSystem class (libljmd_host.so) behind the same shim."""
         if legacy not in cls._libs:
-            path = REF_LEGACY_LIB if legacy else REF_LIB
+            path = HOST_SHIM_LIB if legacy == "product" else (REF_LEGACY_LIB if legacy else REF_LIB)
             if not os.path.exists(path):
                 raise RuntimeError(f"{path} missing: run `make -C oracle ref ref_legacy` where /root/reference exists")
             lib = C.CDLL(path)
@@ -181,6 +184,9 @@ class Reference:
             lib.ljref_renormalize_velocities.argtypes = [vp, C.c_int]
             lib.ljref_kinetic_temperature.restype = C.c_double
             lib.ljref_kinetic_temperature.argtypes = [vp]
+            if hasattr(lib, "ljref_correct_total_momentum"):
+                lib.ljref_correct_total_momentum.argtypes = [vp]
+                lib.ljref_poke_velocities.argtypes = [vp, vp]
             if hasattr(lib, "ljref_subsystem_batch"):
                 lib.ljref_subsystem_batch.argtypes = [vp, C.c_double, C.c_int, vp, C.c_int]
                 lib.ljref_velocity_batch.argtypes = [vp, C.c_double, C.c_double, C.c_int, vp, C.c_int]
@@ -256,6 +262,12 @@ class Reference:
     def updatevelo(self):
         self._l.ljref_updatevelo(self._h)
 
+    def _getvelo(self):
+        v = np.zeros(4096)
+        d = np.zeros(4096)
+        n = self._l.ljref_getvelo(self._h, _p(v), _p(d), 4096)
+        return v[:n], d[:n]
+
     def subsystem_batch(self, alpha_step=0.05, type=3):
         """The reference task helper GetNSubsystemBatch on this system's h_Pos."""
         out = np.zeros(256, dtype=np.int32)
@@ -270,6 +282,16 @@ class Reference:
 
     def renormalize_to_energy(self, ust):
         self._l.ljref_renormalize_to_energy(self._h, ust)
+
+    def renormalize_velocities(self, recalculate=True):
+        self._l.ljref_renormalize_velocities(self._h, int(recalculate))
+
+    def correct_total_momentum(self):
+        self._l.ljref_correct_total_momentum(self._h)
+
+    def poke_velocities(self, vel):
+        vel = _f4(vel)
+        self._l.ljref_poke_velocities(self._h, _p(vel))
 
     def kinetic_temperature(self):
         return float(self._l.ljref_kinetic_temperature(self._h))

@@ -108,6 +108,13 @@ int ljref_getvelo(void* h, double* v, double* dens, int cap)
 
 void ljref_renormalize_to_energy(void* h, double ust) { static_cast<MDSystem*>(h)->RenormalizeVelocitiesToEnergy(ust); }
 void ljref_renormalize_velocities(void* h, int recalc) { static_cast<MDSystem*>(h)->RenormalizeVelocities(recalc != 0); }
+void ljref_correct_total_momentum(void* h) { static_cast<MDSystem*>(h)->CorrectTotalMomentum(); }
+// Overwrite h_Vel only (no re-evaluation): the state the velocity helpers act on.
+void ljref_poke_velocities(void* h, const float* vel)
+{
+  MDSystem* s = static_cast<MDSystem*>(h);
+  std::memcpy(s->h_Vel, vel, 4 * (size_t)s->m_config.N * sizeof(float));
+}
 double ljref_kinetic_temperature(void* h) { MDSystem* s = static_cast<MDSystem*>(h); return s->KineticTemperature(s->h_Vel); }
 
 }  // extern "C"

@@ -608,3 +608,49 @@ def test_full_size_hardwall_c4_slice(pkg, gpu_lib):
         assert np.array_equal(s.rdf_counts().astype(np.int64), rdf_numpy(pos, s.L, 1, s.rdf_dr2))
         vh = s.velocity_histogram(0.12, 101)
         assert vh.sum() == N
+
+
+# ------------------------------------------------------------------ rows f-3 / f-4: shear stress on demand, device arrays
+@pytest.mark.parametrize("name", golden_names())
+def test_pshear_on_demand_matches_reference_cpu_path(pkg, oracle, gpu_lib, kernel, name):
+    """P_xy (MDSystem.cpp:299,309,335,353) is computed by the reference's CPU path only; ljmd_get_pshear evaluates
+    it on demand from the saved evaluation positions.  Against the golden reference value and the oracle."""
+    g = load_golden(name)
+    N, vol = g["N"], g["N"] / g["rho"]
+    with make_system(pkg, g) as s:
+        s.set_state(g["pos0"], g["vel0"])
+        ps0 = s.pshear()
+        _, sc_ref, _ = oracle.forces(g["pos0"], s.L, g["bc"], g["dr2"])
+        want = oracle.parameters(N, g["rho"], g["vel0"], sc_ref["V"], sc_ref["Pvirial"], sc_ref["Pshear_conf"])["Pshear"]
+        _, _, sc64 = oracle.forces_f64(g["pos0"], s.L, g["bc"])
+        scale = (3.0 * sc64["Pabs"] + N * g["s0"]["T"]) / vol      # sum of |pair virial terms| + kinetic part
+        assert abs(ps0 - want) <= SCALAR_TOL * scale, (ps0, want)
+        assert abs(ps0 - g["s0"]["Pshear"]) <= SCALAR_TOL * scale, (ps0, g["s0"]["Pshear"])
+        # after the golden's steps: the value belongs to the state the handle holds now
+        s.step(g["dt"], g["steps"])
+        ps1 = s.pshear()
+        assert abs(ps1 - g["s1"]["Pshear"]) <= 20 * SCALAR_TOL * scale, (ps1, g["s1"]["Pshear"])
+        assert s.pshear() == ps1                                    # deterministic
+
+
+def test_device_arrays_expose_the_resident_state(pkg, gpu_lib):
+    """ljmd_device_arrays: the float4 device arrays a renderer reads instead of paying a D2H per frame (the
+    reference's GL hooks are stubs, MDSystem.cu:199-226).  Read them back with the CUDA runtime directly."""
+    N, rho = 3000, 0.6
+    pos = pkg.snapshots.lattice(N, rho, jitter=0.05, seed=8)
+    vel = pkg.snapshots.velocities(N, 1.0, seed=8)
+    rt = C.CDLL("libcudart.so")
+    rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    rt.cudaStreamSynchronize.argtypes = [C.c_void_p]
+    with pkg.ljmd.LJSystem(N, T0=1.0, rho=rho, canonical=True, bc=0) as s:
+        s.set_state(pos, vel)
+        s.step(0.004, 4)
+        d = s.device_arrays()
+        assert d["pos"] and d["vel"] and d["force"]
+        assert rt.cudaStreamSynchronize(d["stream"]) == 0
+        want = s.get_state()
+        for key, ref in zip(("pos", "vel", "force"), want):
+            buf = np.empty((N, 4), dtype=np.float32)
+            assert rt.cudaMemcpy(buf.ctypes.data_as(C.c_void_p), d[key], buf.nbytes, 2) == 0
+            assert np.array_equal(buf, ref), key
+        assert np.all(want[0][:, 3] == np.float32(s.L / np.float32(150.0)))     # the GL homogeneous w travels along
