@@ -226,6 +226,10 @@ static void choose_sym_plan(int n_itiles, int nblk, int num_sms, Plan* pl) {
   // CTAs of 8+ units amortise their prologue and partial-force row: go on to ~60 CTAs per slot, which keeps the
   // tail (about half a CTA duration at low residency) under 1 % of the launch
   if (per_cta >= 8) per_cta = (int)std::max<long long>(8, (total + 60 * slots - 1) / (60 * slots));
+  // Between the two regimes (about 10 CTAs of 3-8 units per slot) the launch is a handful of "waves" and an
+  // unlucky count leaves most slots idle for a whole CTA duration: the 1/8 shard of C4 (32 896 units) ran 9.3 waves
+  // of 8-unit CTAs in 3.02 ms where 2.77 ms is a perfect split.  Halve the CTAs until ~16 per slot are in flight.
+  while (per_cta > 2 && total / per_cta < 16 * slots) per_cta = (per_cta + 1) / 2;
   int mju = std::min(per_cta, kSymMaxMJU);
   int mi = 1;
   if (per_cta > mju) {

@@ -130,6 +130,7 @@ static int pick_split(int n_it, int N, int sms, int minb) {
 }
 
 static int g_force_split = 0;   // scan_ordered: overrides the split of run_variant
+static int g_shard = 1;         // emulate rank 0 of a g_shard-way sharded run: i-particles [0, N / g_shard)
 template <typename V, bool PERIODIC, bool RDF, int THREADS, int MINB, int NPAIR, int UNROLL>
 static void run_variant(const Problem& pb, const char* tag, int reps, int tile_j, std::vector<float4>* keep) {
   auto kern = k_force<V, PERIODIC, RDF, THREADS, MINB, NPAIR, UNROLL>;
@@ -214,7 +215,8 @@ static void run_sym(const Problem& pb, const char* tag, int reps, int bj, std::v
   mi = std::max(1, std::min(mi, n / 2));
   const int band = sym_band_units(mi, hmax, n, cpb);
   const int nwin = (band + mju - 1) / mju;
-  const int nsup = (n + mi - 1) / mi;
+  const int n_loc = (n + g_shard - 1) / g_shard;   // i-tiles of the emulated rank
+  const int nsup = (n_loc + mi - 1) / mi;
   const size_t smem = force_sym_smem_bytes(RDF, bj, THREADS, mju);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaFuncAttributes fa;
@@ -226,7 +228,7 @@ static void run_sym(const Problem& pb, const char* tag, int reps, int bj, std::v
   ForceParams& fp = sp.f;
   fp.jrec = PERIODIC ? pb.upos : reinterpret_cast<const uint4*>(pb.posf);
   fp.posf = pb.posf; fp.fpart = pb.fpart; fp.blockW = pb.blockW; fp.rdf = pb.rdf;
-  fp.N = pb.N; fp.i_begin = 0; fp.i_end = pb.N; fp.ilocal_cap = pb.N; fp.tile_j = bj;
+  fp.N = pb.N; fp.i_begin = 0; fp.i_end = std::min(pb.N, n_loc * B); fp.ilocal_cap = pb.N; fp.tile_j = bj;
   const double k2 = 4294967296.0 / pb.L;
   fp.c2 = PERIODIC ? (float)(k2 * k2) : 1.f;
   fp.fscale = PERIODIC ? (float)(4.0 * pb.L / 4294967296.0) : 4.f;
@@ -270,10 +272,10 @@ static void run_sym(const Problem& pb, const char* tag, int reps, int bj, std::v
     best = std::min(best, ms);
     sum += ms;
   }
-  const double pairs = (double)pb.N * (pb.N - 1);
+  const double pairs = (double)pb.N * (pb.N - 1) / g_shard;
   const double flop = PERIODIC ? 37. : 25.;
   double maxdiff = 0., scale = 0., maxw = 0.;
-  if (pb.N <= 262144) {   // host-side gather of the partial rows and reaction blocks (the library's index rule)
+  if (pb.N <= 262144 && g_shard == 1) {   // host-side gather of the partial rows and reaction blocks (the library's index rule)
     std::vector<float4> h((size_t)nwin * pb.N), hr(rp_elems);
     CK(cudaMemcpy(h.data(), pb.fpart, h.size() * 16, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(hr.data(), pb.rpart, hr.size() * 16, cudaMemcpyDeviceToHost));
@@ -388,6 +390,19 @@ int main(int argc, char** argv) {
         snprintf(tag, sizeof(tag), "scan bj%d S%d per_cta%d ctas%d", bj, S, per, n * S);
         run_sym<P2, true, false, 128, 3, 2, 4>(pb, tag, reps, bj, &keepP, true, per, 1);
       }
+    }
+    return 0;
+  }
+  if (argc > 4 && !strcmp(argv[3], "shardscan")) {
+    // the force kernel of rank 0 of an argv[4]-way sharded run, every window size: what the planner should pick
+    g_shard = atoi(argv[4]);
+    for (int mju = 16; mju >= 1; --mju) {
+      if (mju > 8 && (mju & 1)) continue;
+      char tag[96];
+      snprintf(tag, sizeof(tag), "shard%d periodic mi1 mju%d", g_shard, mju);
+      run_sym<P2, true, false, 128, 3, 2, 4>(pb, tag, reps, 256, &keepP, true, mju, 1);
+      snprintf(tag, sizeof(tag), "shard%d open     mi1 mju%d", g_shard, mju);
+      run_sym<P2, false, false, 128, 3, 2, 4>(pb, tag, reps, 256, &keepO, true, mju, 1);
     }
     return 0;
   }
