@@ -133,6 +133,17 @@ int ljmd_set_T0(ljmd_system* s, double T0);
  */
 int ljmd_set_state(ljmd_system* s, const float* pos4, const float* vel4);
 
+/*
+ * MDSystem::SampleInitialConditions on the device (MDSystem.cpp:147-181), then the evaluation ljmd_set_state does:
+ * the reference's simple-cubic start lattice (bit-identical positions, w = L/150), Gaussian velocity components
+ * N(0, T0) from a counter-based Philox4x32-10 generator keyed by `seed` and counted by the global particle index,
+ * total momentum removed (CorrectTotalMomentum, :183-216) and velocities rescaled to T0 exactly
+ * (RenormalizeVelocities(true), :375-389).  The same seed gives the same state bit for bit on any number of GPUs
+ * (the two global sums are integer).  The reference's own generator is time-seeded, so there is nothing to be
+ * bit-compatible with; the distribution is the same (Maxwell speeds, isotropic directions).
+ */
+int ljmd_init_state(ljmd_system* s, unsigned long long seed);
+
 /* Plain upload of host arrays (either may be NULL) without any evaluation: what the reference does when
  * a caller edits h_Pos / h_Vel in place (copyArrayToDevice, MDSystem.cu:212-216). */
 int ljmd_upload(ljmd_system* s, const float* pos4, const float* vel4);

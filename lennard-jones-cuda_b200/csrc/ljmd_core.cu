@@ -1669,6 +1669,80 @@ int ljmd_legacy_forces(ljmd_system* s, const float* d_pos, float* d_force, float
   return LJMD_OK;
 }
 
+// ------------------------------------------------------------------- device-side initial conditions (§8 f-4)
+// Three phases with two global integer sums in between (total momentum, then kinetic temperature); `sums` are this
+// handle's particles only — sharded systems add them up (NCCL when one process per GPU, on the host behind a front).
+static int init_phase(ljmd_system* s, int phase, unsigned long long seed, const long long* total4, long long* own4) {
+  CHECK_S(s);
+  InitParams q;
+  memset(&q, 0, sizeof(q));
+  q.pos = s->pos; q.vel = s->vel; q.nloc = s->nloc; q.i_begin = s->i_begin; q.N = s->N; q.L = s->L; q.T0 = s->T0; q.seed = seed;
+  q.Ns = (int)ceil(pow((double)s->N, 1. / 3.));   // MDSystem.cpp:150
+  q.dL = s->L / q.Ns;                             // :151
+  long long* dsum = reinterpret_cast<long long*>(s->velh);   // scratch: 4 x int64
+  q.sums = dsum;
+  const int g = step_grid(s);
+  if (phase == 1) {
+    CU(cudaMemsetAsync(dsum, 0, 4 * sizeof(long long), s->stream));
+    k_init_sample<<<g, kStepThreads, 0, s->stream>>>(q);
+  } else if (phase == 2) {
+    for (int a = 0; a < 3; ++a) q.mean[a] = (double)total4[a] / 4294967296.0 / (double)s->N;
+    k_init_center<<<g, kStepThreads, 0, s->stream>>>(q);
+  } else {
+    const double Tkin = (double)total4[3] / 4294967296.0 * (1. / 3. / (double)s->N);   // MDSystem.cpp:370
+    q.factor = sqrt(s->T0 / Tkin);                                                      // :382
+    k_init_scale<<<g, kStepThreads, 0, s->stream>>>(q);
+  }
+  CU(cudaGetLastError());
+  s->launches += 1;
+  if (own4) {
+#ifdef LJMD_WITH_NCCL
+    if (s->world > 1 && !s->inproc) NC(ncclAllReduce(dsum, dsum, 4, ncclInt64, ncclSum, s->comm, s->stream));
+#endif
+    CU(cudaMemcpyAsync(own4, dsum, 4 * sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+  }
+  return LJMD_OK;
+}
+
+// after the three phases: what ljmd_set_state does once the arrays are on the device
+static int init_finish(ljmd_system* s) {
+  CHECK_S(s);
+  StepParams p = make_step_params(s, 0.);
+  k_prepare<<<step_grid(s), kStepThreads, 0, s->stream>>>(p);
+  CU(cudaGetLastError());
+  s->launches += 1;
+  int rc = allgather_positions(s);
+  if (rc) return rc;
+  CU(cudaMemsetAsync(s->sc, 0, sizeof(DevScalars), s->stream));
+  if ((rc = evaluate(s, p, GATHER_EVAL, false, 0))) return rc;
+  s->rdf_nacc = 0;
+  CU(cudaMemsetAsync(s->rdf_acc, 0, kRdfBins * sizeof(unsigned long long), s->stream));
+  return sync_scalars(s);
+}
+
+extern "C" int ljmd_init_state(ljmd_system* s, unsigned long long seed) {
+  if (!s) return set_err(LJMD_ERR_ARG, "system is NULL");
+  long long tot[4] = {0, 0, 0, 0};
+  if (s->multi) {
+    const int G = multi_count(s);
+    std::vector<long long> part((size_t)4 * G, 0);
+    auto add_up = [&]() { for (int k = 0; k < 4; ++k) { tot[k] = 0; for (int r = 0; r < G; ++r) tot[k] += part[4 * r + k]; } };
+    int rc = multi_all(s, [&](ljmd_system* sub, int r) { return init_phase(sub, 1, seed, nullptr, &part[4 * r]); });
+    if (rc) return rc;
+    add_up();
+    if ((rc = multi_all(s, [&](ljmd_system* sub, int r) { return init_phase(sub, 2, seed, tot, &part[4 * r]); }))) return rc;
+    add_up();
+    if ((rc = multi_all(s, [&](ljmd_system* sub, int) { return init_phase(sub, 3, seed, tot, nullptr); }))) return rc;
+    return multi_all(s, [&](ljmd_system* sub, int) { return init_finish(sub); });
+  }
+  int rc = init_phase(s, 1, seed, nullptr, tot);
+  if (rc) return rc;
+  if ((rc = init_phase(s, 2, seed, tot, tot))) return rc;
+  if ((rc = init_phase(s, 3, seed, tot, nullptr))) return rc;
+  return init_finish(s);
+}
+
 // ------------------------------------------------------------------- shear stress, on demand
 // Pshear = (4/2 * sum_i sum_{j != i} (-r_x,ij * f_y,ij / 4) + sum_i (-v_x v_y)) / (N / rho), MDSystem.cpp:299,309,335,353.
 // The reference computes it on its CPU path only and nothing reads it (its GPU path leaves the member stale), so

@@ -658,6 +658,107 @@ __global__ void __launch_bounds__(kStepThreads) k_trace(const TraceParams q) {
   }
 }
 
+// ---- device-side seeded initial conditions (MDSystem::SampleInitialConditions, MDSystem.cpp:147-181)
+// Positions: the reference's simple-cubic start lattice, same double arithmetic rounded to float.  Velocities: the
+// reference draws a Maxwell speed and an isotropic direction from a time-seeded Mersenne twister (not
+// reproducible); here three N(0, T) components per particle from Philox4x32-10 keyed by the seed and COUNTED by the
+// global particle index, so a particle gets the same draw on any grid shape and any number of GPUs.  The total-
+// momentum correction and the rescale to T0 (:179-180) need two global sums; they are accumulated as 2^-32
+// fixed-point integers (associative: bit-identical for any launch shape or GPU count).
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+struct InitParams {
+  float4* pos;        // [nloc]
+  float4* vel;        // [nloc]
+  int nloc, i_begin, N;
+  int Ns;             // lattice sites per edge = ceil(N^(1/3)) (:150)
+  double dL;          // L / Ns (:151)
+  double L, T0;
+  unsigned long long seed;
+  long long* sums;    // [4]: sum vx, vy, vz (2^-32 fixed point), then sum v^2 (2^-32 fixed point)
+  double mean[3];     // phase 2: total momentum / N
+  double factor;      // phase 3: sqrt(T0 / Tkin)
+};
+
+// phase 1: lattice + raw velocities + momentum sums
+__global__ void __launch_bounds__(kStepThreads) k_init_sample(const InitParams q) {
+  const int il = blockIdx.x * kStepThreads + threadIdx.x;
+  long long sx = 0, sy = 0, sz = 0;
+  if (il < q.nloc) {
+    const int iN = q.i_begin + il;
+    const int Ns = q.Ns;                                                    // :150, evaluated on the host (libm's pow)
+    const double dL = q.dL;                                                 // :151
+    float4 x;
+    x.x = (float)__dmul_rn(__dadd_rn((double)(iN % Ns), 0.5), dL);          // :161-167
+    x.y = (float)__dmul_rn(__dadd_rn((double)((iN / Ns) % Ns), 0.5), dL);
+    x.z = (float)__dmul_rn(__dadd_rn((double)(iN / (Ns * Ns)), 0.5), dL);
+    x.w = (float)__ddiv_rn(q.L, 150.);                                      // :168 `L / 150.f`: a double division
+    q.pos[il] = x;
+    uint32_t r[4];
+    philox4x32_10((uint32_t)iN, 0u, 0u, 0u, (uint32_t)q.seed, (uint32_t)(q.seed >> 32), r);
+    // Box-Muller on uniforms in (0, 1): three of the four normals
+    const double u1 = ((double)r[0] + 0.5) * (1.0 / 4294967296.0), u2 = ((double)r[1] + 0.5) * (1.0 / 4294967296.0);
+    const double u3 = ((double)r[2] + 0.5) * (1.0 / 4294967296.0), u4 = ((double)r[3] + 0.5) * (1.0 / 4294967296.0);
+    const double ra = sqrt(-2. * log(u1)), rb = sqrt(-2. * log(u3));
+    const double sT = sqrt(q.T0);
+    float4 v;
+    v.x = (float)(sT * ra * cospi(2. * u2));
+    v.y = (float)(sT * ra * sinpi(2. * u2));
+    v.z = (float)(sT * rb * cospi(2. * u4));
+    v.w = 0.f;
+    q.vel[il] = v;
+    sx = __double2ll_rn((double)v.x * 4294967296.0);
+    sy = __double2ll_rn((double)v.y * 4294967296.0);
+    sz = __double2ll_rn((double)v.z * 4294967296.0);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o); sz += __shfl_xor_sync(0xffffffffu, sz, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(q.sums), (unsigned long long)sx);
+    atomicAdd(reinterpret_cast<unsigned long long*>(q.sums) + 1, (unsigned long long)sy);
+    atomicAdd(reinterpret_cast<unsigned long long*>(q.sums) + 2, (unsigned long long)sz);
+  }
+}
+// phase 2: CorrectTotalMomentum (:183-216) + sum of v^2
+__global__ void __launch_bounds__(kStepThreads) k_init_center(const InitParams q) {
+  const int il = blockIdx.x * kStepThreads + threadIdx.x;
+  long long s2 = 0;
+  if (il < q.nloc) {
+    float4 v = q.vel[il];
+    v.x = (float)__dadd_rn((double)v.x, -q.mean[0]);     // float += double: formed in double, rounded once (:199-201)
+    v.y = (float)__dadd_rn((double)v.y, -q.mean[1]);
+    v.z = (float)__dadd_rn((double)v.z, -q.mean[2]);
+    q.vel[il] = v;
+    s2 = __double2ll_rn((double)sq3(v.x, v.y, v.z) * 4294967296.0);   // :367 float expression
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(reinterpret_cast<unsigned long long*>(q.sums) + 3, (unsigned long long)s2);
+}
+// phase 3: RenormalizeVelocities(true) (:375-389)
+__global__ void __launch_bounds__(kStepThreads) k_init_scale(const InitParams q) {
+  const int il = blockIdx.x * kStepThreads + threadIdx.x;
+  if (il >= q.nloc) return;
+  float4 v = q.vel[il];
+  v.x = (float)__dmul_rn((double)v.x, q.factor);
+  v.y = (float)__dmul_rn((double)v.y, q.factor);
+  v.z = (float)__dmul_rn((double)v.z, q.factor);
+  q.vel[il] = v;
+}
+
 __global__ void k_rdf_accum(const unsigned long long* cur, unsigned long long* acc) {
   acc[threadIdx.x] += cur[threadIdx.x];
 }

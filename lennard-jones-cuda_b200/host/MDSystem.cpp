@@ -44,7 +44,7 @@ MDSystem::MDSystem(const MDSystem::MDSystemConfiguration& config)   // MDSystem.
     : U(0), T(0), K(0), V(0), P(0), Pshear(0), CUDAInit(false), h_Pos(0), h_Vel(0), h_Force(0), d_Pos(0), d_Vel(0),
       d_Force(0), t(0), L(0), veloIters(0), rdf_dr2(0.1f), momN(0), momN2(0), momN3(0), momN4(0), momiters(0),
       av_U_tot(0), av_T_tot(0), av_p_tot(0), av_iters(0), m_sys(0), m_velo_bins(101), m_velo_step(0.12),
-      m_host_vel_dirty(false) {
+      m_host_vel_dirty(false), m_device_sampled(false) {
   Reinitialize(config);
 }
 
@@ -69,12 +69,15 @@ void MDSystem::Reinitialize(const MDSystem::MDSystemConfiguration& config) {   /
   h_Force = new float[4 * (size_t)N];
   std::memset(h_Vel, 0, sizeof(float) * 4 * (size_t)N);
   std::memset(h_Force, 0, sizeof(float) * 4 * (size_t)N);
-  SampleInitialConditions();                 // :90
   rdf_dr2 = ljmd_rdf_dr2(N);                 // :93-95
   NdNdr2 = std::vector<int>(LJMD_RDF_BINS, 0);   // :97
-  ReallocateMemory();                        // :99 — (re)creates the device handle
-  check(ljmd_set_state(m_sys, h_Pos, h_Vel), "ljmd_set_state");   // :101-103 forces + parameters
-  check(ljmd_get_state(m_sys, 0, 0, h_Force), "ljmd_get_state");
+  ReallocateMemory();                        // :99 — (re)creates the device handle (before the sampling: it runs there)
+  m_device_sampled = false;
+  SampleInitialConditions();                 // :90 — on the device: lattice, seeded velocities, forces, parameters
+  if (!m_device_sampled) {                   // host sampling (LJMD_HOST_INIT=1): upload and evaluate, :101-103
+    check(ljmd_set_state(m_sys, h_Pos, h_Vel), "ljmd_set_state");
+    check(ljmd_get_state(m_sys, 0, 0, h_Force), "ljmd_get_state");
+  }
   pullScalars(false);
   veloIters = 0;
   initvelo();                                // :107
@@ -120,6 +123,19 @@ void MDSystem::ReallocateMemory() {   // MDSystem.cpp:116-144: device buffers fo
 }
 
 void MDSystem::SampleInitialConditions() {   // MDSystem.cpp:147-181
+  // Device path (default): ljmd_init_state samples on the GPU(s) — the reference's lattice bit for bit, Philox
+  // velocities keyed by LJMD_SEED (time-seeded like the reference when unset), momentum removed, T = T0 — and
+  // evaluates forces and parameters; the host mirrors follow.  LJMD_HOST_INIT=1 keeps the serial host loop below.
+  const char* hostinit = std::getenv("LJMD_HOST_INIT");
+  if (m_sys && !(hostinit && hostinit[0] == '1')) {
+    check(ljmd_set_T0(m_sys, m_config.T0), "ljmd_set_T0");
+    check(ljmd_init_state(m_sys, initial_seed()), "ljmd_init_state");
+    check(ljmd_get_state(m_sys, h_Pos, h_Vel, h_Force), "ljmd_get_state");
+    pullScalars(false);
+    m_host_vel_dirty = false;
+    m_device_sampled = true;
+    return;
+  }
   const int N = m_config.N;
   const int Nsingle = (int)std::ceil(std::pow((double)N, 1. / 3.));
   const double dL = L / Nsingle;

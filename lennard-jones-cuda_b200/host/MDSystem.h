@@ -123,7 +123,8 @@ class MDSystem {
   ljmd_system* m_sys;
   int m_velo_bins;
   double m_velo_step;
-  bool m_host_vel_dirty;  // h_Vel was edited on the host since the last upload
+  bool m_host_vel_dirty;
+  bool m_device_sampled;   // SampleInitialConditions ran on the device (state already evaluated there)  // h_Vel was edited on the host since the last upload
   void syncConfig();
   void pullScalars(bool accumulate);
   void check(int rc, const char* what);

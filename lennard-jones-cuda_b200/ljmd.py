@@ -22,7 +22,7 @@ S_COUNT = 16
 API_SYMBOLS = [
     "ljmd_last_error", "ljmd_device_count", "ljmd_create", "ljmd_create_multi", "ljmd_create_distributed", "ljmd_nccl_unique_id",
     "ljmd_fabric_export", "ljmd_fabric_connect", "ljmd_destroy", "ljmd_rdf_dr2", "ljmd_set_canonical", "ljmd_set_boundary", "ljmd_set_T0", "ljmd_set_state",
-    "ljmd_set_velocities", "ljmd_upload", "ljmd_get_state", "ljmd_step", "ljmd_integrate_host", "ljmd_compute_forces",
+    "ljmd_set_velocities", "ljmd_upload", "ljmd_init_state", "ljmd_get_state", "ljmd_step", "ljmd_integrate_host", "ljmd_compute_forces",
     "ljmd_get_scalars", "ljmd_get_pshear", "ljmd_device_arrays", "ljmd_reset_averaging", "ljmd_get_rdf", "ljmd_get_rdf_accum", "ljmd_velocity_histogram", "ljmd_subvolume_counts", "ljmd_velocity_subvolume_counts",
     "ljmd_trace_begin", "ljmd_trace_row_length", "ljmd_trace_read", "ljmd_trace_end",
     "ljmd_launch_count", "ljmd_set_event_timing", "ljmd_last_step_timing", "ljmd_last_gather_timing", "ljmd_last_reduce_timing", "ljmd_get_launch_info",
@@ -84,6 +84,7 @@ def load_library(path=None):
     lib.ljmd_set_T0.argtypes = [vp, C.c_double]
     lib.ljmd_set_state.argtypes = [vp, vp, vp]
     lib.ljmd_set_velocities.argtypes = [vp, vp]
+    lib.ljmd_init_state.argtypes = [vp, C.c_ulonglong]
     lib.ljmd_upload.argtypes = [vp, vp, vp]
     lib.ljmd_get_state.argtypes = [vp, vp, vp, vp]
     lib.ljmd_step.argtypes = [vp, C.c_double, C.c_int, C.c_int]
@@ -223,6 +224,10 @@ class LJSystem:
     def set_state(self, pos, vel):
         pos, vel = _f4(pos, self.N, "pos"), _f4(vel, self.N, "vel")
         self._check(self._lib.ljmd_set_state(self._h, _ptr(pos), _ptr(vel)))
+
+    def init_state(self, seed):
+        """Device-side SampleInitialConditions (start lattice + seeded Philox velocities at T0) and evaluation."""
+        self._check(self._lib.ljmd_init_state(self._h, int(seed)))
 
     def upload(self, pos=None, vel=None):
         pos = _f4(pos, self.N, "pos") if pos is not None else None

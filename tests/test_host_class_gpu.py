@@ -122,3 +122,31 @@ def test_velocity_histogram_running_mean(pkg, gpu_lib, N, T0, rho, canonical, bc
         assert np.array_equal(dr, do), f"running mean differs after update {k + 1}"
     for s in (ref, our):
         s.close()
+
+
+@pytest.mark.parametrize("N,T0,rho", [(400, 1.4, 0.05), (4096, 1.0, 0.85), (100003, 0.7, 0.3)])
+def test_device_side_initial_conditions(pkg, oracle, gpu_lib, N, T0, rho):
+    """ljmd_init_state: the reference's start lattice bit for bit, Philox velocities with zero total
+    momentum, T = T0 and Maxwell statistics; the seed fixes the state; the state is evaluated (forces, V, K)."""
+    from scipy import stats
+    with pkg.ljmd.LJSystem(N, T0=T0, rho=rho, canonical=True, bc=0) as s:
+        s.init_state(2024)
+        pos, vel, frc = s.get_state()
+        assert np.array_equal(pos, oracle.lattice(N, s.L)), "start lattice differs from MDSystem.cpp:150-168"
+        v3 = vel[:, :3].astype(np.float64)
+        assert np.abs(v3.sum(axis=0)).max() <= 2e-5 * np.sqrt(N * T0)
+        assert abs((v3 * v3).sum() / (3 * N) - T0) <= 2e-6 * T0
+        assert stats.kstest(np.sqrt((v3 * v3).sum(axis=1)), stats.maxwell(scale=np.sqrt(T0)).cdf).pvalue > 1e-3
+        for a in range(3):
+            assert stats.kstest(v3[:, a], stats.norm(scale=np.sqrt(T0)).cdf).pvalue > 1e-3
+        assert abs(np.corrcoef(v3[:, 0], v3[:, 1])[0, 1]) < 5.0 / np.sqrt(N)          # components are independent
+        sc = s.scalars()
+        assert abs(sc["T"] - T0) <= 2e-6 * T0 and sc["t"] == 0.0 and sc["av_iters"] == 0
+        assert abs(2.0 * frc[:, 3].astype(np.float64).sum() - sc["V"]) <= 1e-6 * max(1.0, abs(sc["V"]))
+        s.init_state(2024)
+        p2, v2, _ = s.get_state()
+        assert np.array_equal(p2, pos) and np.array_equal(v2, vel)
+        s.init_state(2025)
+        assert not np.array_equal(s.get_state()[1], vel)
+        s.step(0.004, 3)                                      # and the state steps
+        assert abs(s.scalars()["T"] - T0) <= 2e-2 * T0

@@ -115,6 +115,26 @@ def test_multi_handle_matches_single_gpu(pkg, gpu_lib, world, case):
     compare_with_single_gpu(pkg, got, canonical, bc, N, rho)
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_device_init_is_identical_on_any_gpu_count(pkg, gpu_lib, world):
+    """ljmd_init_state: Philox draws are counted by the global particle index and the two global sums are integer,
+    so the sampled state is bit-identical on 1 and on `world` GPUs; P_xy on demand agrees too."""
+    if gpu_lib.ljmd_device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    N, T0, rho = 20011, 1.2, 0.4
+    with pkg.ljmd.LJSystem(N, T0=T0, rho=rho, canonical=True, bc=0) as one:
+        one.init_state(77)
+        p1, v1, f1 = one.get_state()
+        ps1 = one.pshear()
+    with pkg.ljmd.LJSystem(N, T0=T0, rho=rho, canonical=True, bc=0, devices=list(range(world))) as many:
+        many.init_state(77)
+        p2, v2, f2 = many.get_state()
+        ps2 = many.pshear()
+    assert np.array_equal(p1, p2) and np.array_equal(v1, v2)
+    assert np.abs(f1[:, :3] - f2[:, :3]).max() <= 2e-6 * np.abs(f1[:, :3]).max()
+    assert abs(ps1 - ps2) <= 1e-9 * max(1.0, abs(ps1))
+
+
 def test_multi_handle_argument_errors(pkg, gpu_lib):
     with pytest.raises(pkg.ljmd.LJMDError):
         pkg.ljmd.LJSystem(4096, devices=[0, 0])                       # a device listed twice
