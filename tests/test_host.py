@@ -91,7 +91,7 @@ def test_launch_plan_tiles_the_problem(pkg, N, world):
         else:
             assert p["force_ctas"] == p["i_tiles"] * p["j_splits"]
         if p["newton3"]:
-            # many small CTAs (measured optimum, profiles/r01_tune_force_sym_split_scan.log): at least ~4.5 per
+            # many small CTAs (measured optimum, profiles/r02_tune_force_sym_split_scan.log): at least ~4.5 per
             # resident slot so the hardware scheduler can balance the SMs, at most ~60 so the partial-force rows
             # k_gather reads back stay a small fraction of the step
             slots = 148 * 3
@@ -282,7 +282,7 @@ def test_launch_plan_is_near_the_measured_optimum(pkg):
     """The Newton-3 launch planner against the split scan it was calibrated on (profiles/, measured on a B200):
     at every scanned size the number of splits it picks is one of the measured configurations, and that
     configuration ran within 4 % of the best one found for the size."""
-    path = os.path.join(ROOT, "profiles", "r01_tune_force_sym_split_scan.log")
+    path = os.path.join(ROOT, "profiles", "r02_tune_force_sym_split_scan.log")
     table, N = {}, None
     for ln in open(path):
         m = re.match(r"== N=(\d+)", ln)

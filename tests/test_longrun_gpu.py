@@ -4,7 +4,9 @@ Error model = the reference's own (src/tasks/auxiliary/time-average-aux.h:27-67)
 mean times sqrt(s), s = 2 / ln(Var / C1) the statistical inefficiency from the lag-1 autocorrelation
 (Allen & Tildesley pp. 194-195).  The two trajectories decorrelate through FP32 chaos, so the time averages
 must agree within a few of those sigmas; the EVN energy drift must be of the same order."""
+import json
 import math
+import os
 
 import numpy as np
 import pytest
@@ -73,3 +75,62 @@ def test_time_averages_match_reference(pkg, gpu_lib, name, canonical):
         drift_g = abs(np.polyfit(np.arange(nsteps) * dt, u_g, 1)[0])
         assert drift_g <= 3.0 * drift_r + 2e-4, (drift_r, drift_g)            # |dU/dt| per particle
         assert np.std(u_g) <= 2.0 * np.std(u_r) + 1e-4                          # same energy fluctuation
+
+
+# ------------------------------------------------------------------ C1 at production length
+C1_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "stats", "c1_longrun_reference.json")
+
+
+@pytest.mark.skipif(not os.path.exists(C1_GOLDEN), reason="run oracle/make_golden_longrun.py where the reference builds")
+def test_c1_production_run_matches_reference_statistics(pkg, gpu_lib):
+    """BASELINE config C1 (N = 400, T* = 1.4, rho* = 0.05, periodic, TVN, dt* = 0.004), the reference's own sample
+    input: teq = 50 then 40 000 production steps per replica, 8 replicas, on the GPU through the observation trace
+    (one read-out per 1 000 steps), against the reference CPU path's <u*>, <T*>, <Z> for the same protocol
+    (tests/golden/stats/c1_longrun_reference.json, 4 replicas, made by oracle/make_golden_longrun.py).
+
+    Acceptance: |difference of the means| <= 3 sigma, no absolute floor.  sigma combines both sides and is, per
+    side, the LARGER of the reference's own error model (TimeAverage::GetMeanError: naive error x sqrt of the lag-one
+    statistical inefficiency, time-average-aux.h:38-66) and the model-free standard error over independent replicas
+    (the lag-one estimate undershoots for observables that decorrelate over thousands of steps in a dilute gas)."""
+    ref = json.load(open(C1_GOLDEN))
+    c = ref["config"]
+    N, T0, rho, dt = c["N"], c["T0"], c["rho"], c["dt"]
+    neq, nprod = c["neq"], c["nprod"]
+    seeds = [101, 102, 103, 104, 105, 106, 107, 108]
+    per = {k: [] for k in ("u", "T", "Z")}
+    with pkg.ljmd.LJSystem(N, T0=T0, rho=rho, canonical=True, bc=0) as s:
+        for seed in seeds:
+            s.set_state(pkg.snapshots.lattice(N, rho, jitter=0.05, seed=seed), pkg.snapshots.velocities(N, T0, seed=seed))
+            s.step(dt, neq)
+            s.reset_averaging()
+            s.trace_begin([], 1000)
+            rows = []
+            for _ in range(nprod // 1000):
+                s.step(dt, 1000)
+                rows.append(s.trace_read()["scalars"])
+            s.trace_end()
+            sc = np.concatenate(rows)                       # t, U, T, P, K, V, Pvirial, 0
+            assert sc.shape == (nprod, 8)
+            tot = s.scalars()
+            assert tot["av_iters"] == nprod                 # the device's running sums cover the same steps
+            assert abs(tot["av_U_tot"] - sc[:, 1].sum()) <= 1e-9 * abs(sc[:, 1].sum())
+            for name, x in (("u", sc[:, 1] / N), ("T", sc[:, 2]), ("Z", sc[:, 3] / (rho * sc[:, 2]))):
+                per[name].append(time_average(x))
+    report = {}
+    for name in ("u", "T", "Z"):
+        means = np.array([m for m, _ in per[name]])
+        gpu_mean = means.mean()
+        gpu_err = max(math.sqrt(sum(e * e for _, e in per[name])) / len(seeds), means.std(ddof=1) / math.sqrt(len(seeds)))
+        rc = ref["combined"][name]
+        ref_err = max(rc["error_model"], rc["error_replicas"])
+        sigma = math.hypot(gpu_err, ref_err)
+        report[name] = (gpu_mean, rc["mean"], sigma)
+        if name == "T":
+            # TVN pins the kinetic temperature: both sides sit on T0 to O(dt^2), the statistical error is ~0
+            assert abs(gpu_mean - T0) <= 2e-4 and abs(rc["mean"] - T0) <= 2e-4, report
+            assert abs(gpu_mean - rc["mean"]) <= 3.0 * sigma + 2e-5, report
+        else:
+            assert abs(gpu_mean - rc["mean"]) <= 3.0 * sigma, report
+    # the cross-ensemble number the reference repository states for this state: u* ~ 1.71 at T* = 1.4
+    # (input/N400.ust1.708.rhost0.05:12)
+    assert abs(report["u"][0] - 1.708) < 0.03, report
