@@ -14,6 +14,16 @@ from conftest import ROOT
 
 pytestmark = pytest.mark.gpu
 
+# LJMD_TEST_WORLDS="4,8" restricts the world sizes (an 8-GPU box is charged 8x: run what the 2-GPU box cannot)
+_ONLY = [int(w) for w in os.environ.get("LJMD_TEST_WORLDS", "").split(",") if w.strip()]
+
+
+def need(gpu_lib, world):
+    if _ONLY and world not in _ONLY:
+        pytest.skip(f"LJMD_TEST_WORLDS excludes world {world}")
+    if gpu_lib.ljmd_device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+
 
 CASES = [("tvn_periodic", 1, 0, 6000, 0.8), ("evn_hardwall", 0, 1, 5003, 0.05), ("tvn_periodic_sym", 1, 0, 20000, 0.5)]
 # (world, comm, case): every transport and kernel on 2 GPUs; the Newton-3 and hard-wall cases again on 4 and 8
@@ -25,8 +35,7 @@ SHARDED = [(2, c, k) for c in ("p2p", "nccl") for k in CASES] + \
 def test_sharded_step_matches_single_gpu(pkg, gpu_lib, tmp_path, world, comm, case):
     """One process per GPU.  comm = p2p: per-step exchange over the CUDA-IPC peer windows (fabric); nccl: NCCL."""
     name, canonical, bc, N, rho = case
-    if gpu_lib.ljmd_device_count() < world:
-        pytest.skip(f"needs {world} GPUs")
+    need(gpu_lib, world)
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", LJMD_COMM=comm)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
            "127.0.0.1", "--master-port", "29544", os.path.join(ROOT, "tests", "dist_worker.py"), "gpu", str(tmp_path),
@@ -96,8 +105,7 @@ def test_multi_handle_matches_single_gpu(pkg, gpu_lib, world, case):
     """ljmd_create_multi: the same observation sequence through ONE handle that drives `world` devices from the
     calling thread (worker threads inside the library, peer pointers over NVLink, no NCCL, no launcher)."""
     name, canonical, bc, N, rho = case
-    if gpu_lib.ljmd_device_count() < world:
-        pytest.skip(f"needs {world} GPUs")
+    need(gpu_lib, world)
     if -(-N // 512) < world:
         pytest.skip("fewer 512-particle blocks than devices")
     pos = pkg.snapshots.lattice(N, rho, jitter=0.05, seed=21)
@@ -119,8 +127,7 @@ def test_multi_handle_matches_single_gpu(pkg, gpu_lib, world, case):
 def test_device_init_is_identical_on_any_gpu_count(pkg, gpu_lib, world):
     """ljmd_init_state: Philox draws are counted by the global particle index and the two global sums are integer,
     so the sampled state is bit-identical on 1 and on `world` GPUs; P_xy on demand agrees too."""
-    if gpu_lib.ljmd_device_count() < world:
-        pytest.skip(f"needs {world} GPUs")
+    need(gpu_lib, world)
     N, T0, rho = 20011, 1.2, 0.4
     with pkg.ljmd.LJSystem(N, T0=T0, rho=rho, canonical=True, bc=0) as one:
         one.init_state(77)
