@@ -408,10 +408,10 @@ static int launch_force(ljmd_system* s, bool rdf) {
 // ---- collectives (no-ops for world == 1) -------------------------------------------------------
 // Two transports: the fabric (peer windows over NVLink, ljmd_fabric_connect) and NCCL (always available,
 // and still used for the rare read-out collectives).
-static int fabric_sync(ljmd_system* s, int first, int count) {
+static int fabric_sync(ljmd_system* s, int first, int count, int fin = 0, double dt = 0.) {
   NvtxRange nvtx_("ljmd:exchange(fabric barrier)");
   s->epoch += 1;
-  k_fabric_sync<<<1, 32, 0, s->stream>>>(s->fab, s->epoch, first, count, s->sc);
+  k_fabric_sync<<<1, 32, 0, s->stream>>>(s->fab, s->epoch, first, count, s->sc, fin, s->N, s->rho, dt);
   CU(cudaGetLastError());
   s->launches += 1;
   return LJMD_OK;
@@ -492,17 +492,28 @@ static int evaluate(ljmd_system* s, const StepParams& p, int mode, bool rdf, int
     s->gath_ev.push_back(g0);
     s->gath_ev.push_back(g1);
   }
+  // Fabric: the step's LAST barrier all-reduces the remaining sums, evaluates CalculateParameters in the same
+  // one-warp kernel (no k_params launch) and — every rank having pushed its next evaluation positions in the
+  // finishing kernel just before — is also the barrier those positions need (no separate one below).
+  const bool fab = s->world > 1 && s->fab.n > 0;
+  bool positions_synced = false;
   if (mode == GATHER_TVN) {
     if ((rc = allreduce_sums(s, SUM_PE, 3))) return rc;  // PE, W, TV2
     if (fuse_next) CU(launch_k(pdl, k_finish_tvn<true>, dim3(g), gb, 0, s->stream, p, fin));
     else CU(launch_k(pdl, k_finish_tvn<false>, dim3(g), gb, 0, s->stream, p, fin));
     s->launches += 1;
-    if (s->world > 1) {
+    if (fab) {
+      if ((rc = fabric_sync(s, SUM_K, 1, accumulate ? 2 : 1, p.dt))) return rc;
+      positions_synced = true;
+    } else if (s->world > 1) {
       if ((rc = allreduce_sums(s, SUM_K, 1))) return rc;
       k_params<<<1, 32, 0, s->stream>>>(p, accumulate);
       CU(cudaGetLastError());
       s->launches += 1;
     }
+  } else if (fab) {
+    if ((rc = fabric_sync(s, SUM_PE, SUM_COUNT, accumulate ? 2 : 1, p.dt))) return rc;
+    positions_synced = true;
   } else if (s->world > 1) {
     if ((rc = allreduce_sums(s, SUM_PE, SUM_COUNT))) return rc;
     k_params<<<1, 32, 0, s->stream>>>(p, accumulate);
@@ -516,7 +527,7 @@ static int evaluate(ljmd_system* s, const StepParams& p, int mode, bool rdf, int
     s->rdf_nacc += 1;
   }
   // the fused kernel published the next step's evaluation positions: make them visible on every rank
-  if (fuse_next && (rc = allgather_positions(s))) return rc;
+  if (fuse_next && !positions_synced && (rc = allgather_positions(s))) return rc;
   return LJMD_OK;
 }
 

@@ -181,14 +181,13 @@ __device__ __forceinline__ void apply_bc(float4& p, float4& v, double L, int bc)
 
 // MDSystem::CalculateParameters (MDSystem.cpp:348-358) + t += dt (:582) from the reduced sums.
 // accumulate: 1 inside Integrate, 0 for a bare evaluation (set_state resets av_* anyway).
-__device__ __forceinline__ void finalize_params(const StepParams& p, int accumulate) {
-  DevScalars* sc = p.sc;
+__device__ __forceinline__ void finalize_values(DevScalars* sc, int N, double rho, double dt, int accumulate) {
   const double K = sc->sums[SUM_K];
   const double V = sc->sums[SUM_PE] * (4. / 2.);            // :308
   const double Pvir = sc->sums[SUM_W] * (4. / 3. / 2.);     // :307
-  const double T = 2. * K / 3. / p.N;                        // :348
-  double P = Pvir + p.N * T;                                 // :349
-  P /= (p.N / p.rho);                                        // :350
+  const double T = 2. * K / 3. / N;                          // :348
+  double P = Pvir + N * T;                                   // :349
+  P /= (N / rho);                                            // :350
   sc->K = K; sc->V = V; sc->T = T; sc->P = P; sc->Pvirial = Pvir;
   sc->U = K + V;                                             // :351
   if (accumulate) {
@@ -196,8 +195,11 @@ __device__ __forceinline__ void finalize_params(const StepParams& p, int accumul
     sc->av_U_tot += sc->U;
     sc->av_p_tot += P;
     sc->av_T_tot += T;
-    sc->t += p.dt;                                           // :582
+    sc->t += dt;                                             // :582
   }
+}
+__device__ __forceinline__ void finalize_params(const StepParams& p, int accumulate) {
+  finalize_values(p.sc, p.N, p.rho, p.dt, accumulate);
 }
 
 template <bool CANON>
@@ -476,7 +478,10 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 }
 constexpr unsigned long long kFabricTimeoutNs = 10ull * 1000ull * 1000ull * 1000ull;   // 10 s of wall time
 
-__global__ void k_fabric_sync(const Fabric f, unsigned long long epoch, int first, int count, DevScalars* sc) {
+// fin: 0 barrier / all-reduce only; 1 also CalculateParameters from the reduced sums (the step's last barrier:
+// saves the separate k_params launch); 2 the same with the av_* accumulation and t += dt of an Integrate.
+__global__ void k_fabric_sync(const Fabric f, unsigned long long epoch, int first, int count, DevScalars* sc, int fin,
+                              int N, double rho, double dt) {
   const int lane = threadIdx.x;
   const int par = (int)(epoch & 1ull);
   if (lane < f.n) {
@@ -511,6 +516,7 @@ __global__ void k_fabric_sync(const Fabric f, unsigned long long epoch, int firs
       for (int r = 0; r < f.n; ++r) t += __ldcv(src + (size_t)r * kSlotDoubles + k);
       sc->sums[first + k] = t;
     }
+    if (fin) finalize_values(sc, N, rho, dt, fin == 2);
   }
   // the kernels that follow in the stream read peer-written data with plain loads: make this kernel's acquires
   // cover them (kernel boundary orders; the fence makes the visibility explicit for every lane)

@@ -106,8 +106,9 @@ def test_multi_handle_matches_single_gpu(pkg, gpu_lib, world, case):
     calling thread (worker threads inside the library, peer pointers over NVLink, no NCCL, no launcher)."""
     name, canonical, bc, N, rho = case
     need(gpu_lib, world)
-    if -(-N // 512) < world:
-        pytest.skip("fewer 512-particle blocks than devices")
+    nblk = -(-N // 512)
+    if (world - 1) * -(-nblk // world) >= nblk:
+        pytest.skip("shards are whole 512-particle blocks: the last device would get none")
     pos = pkg.snapshots.lattice(N, rho, jitter=0.05, seed=21)
     vel = pkg.snapshots.velocities(N, 1.0, seed=21)
     with pkg.ljmd.LJSystem(N, T0=1.0, rho=rho, canonical=canonical, bc=bc, devices=list(range(world))) as s:
