@@ -23,6 +23,7 @@
 #include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges around force / gather / exchange / step
 
 #include "ljmd_force_sym.cuh"
+#include "ljmd_sort.cuh"
 #include "ljmd_step.cuh"
 
 using namespace ljmd;
@@ -73,6 +74,7 @@ constexpr int kSymBJ = 256;                   // largest j-chunk (work unit) of 
 constexpr int kSymMaxMJU = 16;                // units per window: 16 x 256 records x 12 B = 48 KB of shared memory, 3 CTAs/SM
 constexpr int kSymMaxMI = 16;                 // i-tiles per super-tile
 constexpr int kSymMinBlocksN = 8;             // Newton-3 kernel from this many 512-particle blocks on (N = 4 096: 20.2 vs 22.0 us ordered)
+constexpr double kFrameRfar = 2.5;            // warp frames: a chunk takes the float path from this gap (sigma) on
 
 struct MultiCtl;   // single-process multi-GPU front handle (end of this file)
 
@@ -103,6 +105,16 @@ struct ljmd_system {
   float4* rsum = nullptr;    // [npad] rank-local column sums of the reaction rows (world > 1)
   float4* rshard = nullptr;  // [cnt]  reaction totals of this rank's particles after the reduce-scatter
   uint4* bbox = nullptr;     // [nblk][2] block bounding boxes (RDF pruning in the Newton-3 kernel)
+  // record order (Newton-3 kernel): slot[il] = record of local particle il; periodic boxes keep the records sorted
+  // along a Hilbert curve (ljmd_sort.cuh) and run the FRAMES kernel (ljmd_force_sym.cuh, "Warp frames")
+  int frames = 0;            // sorting + FRAMES kernel enabled (Newton-3 kernel; LJMD_FRAMES=0 turns it off)
+  int sorted = 0;            // slot[] currently holds a Hilbert order (not the identity)
+  int sort_interval = 128;   // steps between re-sorts
+  int sort_bits = 1, sort_ncell = 8;
+  long long steps_since_sort = 0;
+  int* slot = nullptr;       // [cnt]
+  int* sort_order = nullptr; // [cnt]
+  unsigned int *sort_key = nullptr, *sort_count = nullptr, *sort_offs = nullptr, *sort_bsum = nullptr;
   // CUDA graph of `graph_period` steady-state steps of a batched ljmd_step (single GPU, no instrumentation)
   cudaGraphExec_t graph_exec = nullptr;
   int graph_period = 0, graph_rdf_every = -1, graph_canonical = -1, graph_bc = -1;
@@ -293,6 +305,8 @@ static StepParams make_step_params(ljmd_system* s, double dt) {
   p.rp_stride = s->sym_mju * s->sym_bj; p.sym_bj = s->sym_bj; p.sym_mi = s->sym_mi; p.sym_mju = s->sym_mju;
   p.sym_nwin = s->sym_nwin; p.n_super = s->n_super; p.rpart = s->rpart; p.rsum = s->rsum; p.rshard = s->rshard; p.npad = s->npad;
   p.fab = s->fab;
+  p.slot = s->slot;
+  p.order = s->sort_order;   // identity until the first sort (nullptr with LJMD_FRAMES=0)
   return p;
 }
 
@@ -331,20 +345,20 @@ static cudaError_t launch_force_t(ljmd_system* s, const ForceParams& fp) {
   return launch_k(s->pdl != 0, kern, grid, dim3(kForceThreads), smem, s->stream, fp);
 }
 
-template <bool PERIODIC, bool RDF>
+template <bool PERIODIC, bool RDF, bool FRAMES = false>
 static cudaError_t launch_force_sym_t(ljmd_system* s, const SymParams& sp) {
   constexpr int MINB = RDF ? kMinBlocksRdf : kSymMinBlocks;
-  auto kern = k_force_sym<P2, PERIODIC, RDF, kForceThreads, MINB, kNPair>;
+  auto kern = k_force_sym<P2, PERIODIC, RDF, kForceThreads, MINB, kNPair, kUnroll, FRAMES>;
   const size_t smem = force_sym_smem_bytes(RDF, s->sym_bj, kForceThreads, s->sym_mju);
   dim3 grid(s->n_super, s->sym_nwin);
   return launch_k(s->pdl != 0, kern, grid, dim3(kForceThreads), smem, s->stream, sp);
 }
 // The window accumulator takes the Newton-3 kernel past the 48 KB default of dynamic shared memory: opt in once
 // per device, for the largest window the planner can choose.
-template <bool PERIODIC, bool RDF>
+template <bool PERIODIC, bool RDF, bool FRAMES = false>
 static cudaError_t sym_smem_opt_in() {
   constexpr int MINB = RDF ? kMinBlocksRdf : kSymMinBlocks;
-  auto kern = k_force_sym<P2, PERIODIC, RDF, kForceThreads, MINB, kNPair>;
+  auto kern = k_force_sym<P2, PERIODIC, RDF, kForceThreads, MINB, kNPair, kUnroll, FRAMES>;
   return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)force_sym_smem_bytes(RDF, kSymBJ, kForceThreads, kSymMaxMJU));
 }
@@ -390,7 +404,16 @@ static int launch_force(ljmd_system* s, bool rdf) {
     sp.rpart = s->rpart; sp.ncols = 0; sp.nblk = s->nblk; sp.bj = s->sym_bj;
     sp.mi = s->sym_mi; sp.mju = s->sym_mju; sp.nwin = s->sym_nwin; sp.win_shift = s->sym_win_shift;
     sp.bbox = bbox; sp.bbox_cut2 = (float)(cut * 1.002 + 1e-3);
-    if (periodic) e = rdf ? launch_force_sym_t<true, true>(s, sp) : launch_force_sym_t<true, false>(s, sp);
+    // warp frames: only worth testing for when the records are spatially sorted
+    sp.frames = (periodic && s->frames && s->sorted) ? 1 : 0;
+    sp.kunit = (float)(s->L / 4294967296.0);
+    sp.far2 = (float)((kFrameRfar * k2) * (kFrameRfar * k2));
+    // (the RDF build of the FRAMES kernel measured 8-15 % slower than the plain RDF kernel — 166 registers and a
+    // third inner loop beside the queue code — so RDF evaluations, one step in rdf_every, stay fixed-point)
+    if (rdf && s->sorted) sp.win_shift = 0;   // sorted records: the in-range pairs sit in the windows next to the
+                                              // diagonal, the longest CTAs of an RDF launch — start them first
+    if (periodic && s->frames && !rdf) e = launch_force_sym_t<true, false, true>(s, sp);
+    else if (periodic) e = rdf ? launch_force_sym_t<true, true>(s, sp) : launch_force_sym_t<true, false>(s, sp);
     else e = rdf ? launch_force_sym_t<false, true>(s, sp) : launch_force_sym_t<false, false>(s, sp);
   } else if (periodic) e = rdf ? launch_force_t<true, true>(s, fp) : launch_force_t<true, false>(s, fp);
   else e = rdf ? launch_force_t<false, true>(s, fp) : launch_force_t<false, false>(s, fp);
@@ -437,6 +460,34 @@ static int allreduce_sums(ljmd_system* s, int first, int count) {
   double* ptr = s->sc->sums + first;
   NC(ncclAllReduce(ptr, ptr, count, ncclDouble, ncclSum, s->comm, s->stream));
 #endif
+  return LJMD_OK;
+}
+
+// Re-sort this rank's records along the Hilbert curve (periodic Newton-3 runs).  Call only where every record is
+// rewritten before it is read again: right before k_drift / k_prepare.  `force`: sort even if not yet due.
+static int maybe_sort_records(ljmd_system* s, bool force) {
+  if (!s->frames || !s->slot) return LJMD_OK;
+  if (s->bc != LJMD_BC_PERIODIC) return LJMD_OK;   // open boxes have no image to save; keep whatever order there is
+  if (!force && s->sorted && s->steps_since_sort < s->sort_interval) return LJMD_OK;
+  NvtxRange nvtx_("ljmd:sort records");
+  SortParams q;
+  q.pos = s->pos; q.nloc = s->nloc; q.i_begin = s->i_begin; q.bits = s->sort_bits; q.ncell = s->sort_ncell;
+  q.fix_scale = 4294967296.0 / s->L;
+  q.key = s->sort_key; q.count = s->sort_count; q.offs = s->sort_offs; q.bsum = s->sort_bsum;
+  q.order = s->sort_order; q.slot = s->slot;
+  const int gp = (s->nloc + kSortThreads - 1) / kSortThreads;
+  const int gc = (s->sort_ncell + kSortThreads - 1) / kSortThreads;
+  const int nb = (s->sort_ncell + kScanBlock - 1) / kScanBlock;
+  k_sort_keys<<<gp, kSortThreads, 0, s->stream>>>(q);
+  k_scan_local<<<nb, kSortThreads, 0, s->stream>>>(q.count, q.offs, q.bsum, q.ncell);
+  k_scan_top<<<1, kSortThreads, 0, s->stream>>>(q.bsum, nb);
+  k_scan_add<<<gc, kSortThreads, 0, s->stream>>>(q.offs, q.bsum, q.ncell, (unsigned int)s->nloc);
+  k_sort_scatter<<<gp, kSortThreads, 0, s->stream>>>(q);
+  k_sort_slots<<<gc, kSortThreads, 0, s->stream>>>(q);
+  CU(cudaGetLastError());
+  s->launches += 6;
+  s->sorted = 1;
+  s->steps_since_sort = 0;
   return LJMD_OK;
 }
 
@@ -674,6 +725,8 @@ static int destroy_impl(ljmd_system* s) {
   cudaFree(s->counter); cudaFree(s->velh); cudaFree(s->sc); cudaFree(s->rdf_cur); cudaFree(s->rdf_acc);
   cudaFree(s->flush_buf);
   cudaFree(s->rpart); cudaFree(s->rshard); cudaFree(s->bbox);
+  cudaFree(s->slot); cudaFree(s->sort_order); cudaFree(s->sort_key); cudaFree(s->sort_count); cudaFree(s->sort_offs);
+  cudaFree(s->sort_bsum);
   trace_free(s);   // also destroys the cached graph
   cudaFreeHost(s->h_sc); cudaFreeHost(s->h_rdf);
   for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
@@ -788,6 +841,32 @@ static int create_impl(ljmd_system** out, int N, double rho_or_negL, double T0, 
     CUC((sym_smem_opt_in<true, true>()));
     CUC((sym_smem_opt_in<false, false>()));
     CUC((sym_smem_opt_in<false, true>()));
+    CUC((sym_smem_opt_in<true, false, true>()));
+    // record order: identity until the first sort (LJMD_FRAMES=0: stays the identity, fixed-point kernel only)
+    {
+      const char* e = getenv("LJMD_FRAMES");
+      s->frames = (e && e[0] == '0') ? 0 : 1;
+      // a sort is six small launches (~20-100 us): every 128 steps where the step itself takes ~0.1 ms, more
+      // often where a step takes milliseconds and the clouds should stay tight
+      s->sort_interval = s->N >= 262144 ? 16 : (s->N >= 65536 ? 32 : 128);
+      if (const char* iv = getenv("LJMD_SORT_INTERVAL")) s->sort_interval = std::max(1, atoi(iv));
+    }
+    s->sort_bits = 1;
+    while (s->sort_bits < 8 && (1LL << (3 * s->sort_bits)) < 2LL * s->nloc) s->sort_bits += 1;
+    s->sort_ncell = 1 << (3 * s->sort_bits);
+    CUC(cudaMalloc(&s->slot, (size_t)s->cnt * sizeof(int)));
+    k_slot_identity<<<(s->nloc + kSortThreads - 1) / kSortThreads, kSortThreads, 0, s->stream>>>(s->slot, s->nloc, s->i_begin);
+    CUC(cudaGetLastError());
+    if (s->frames) {
+      CUC(cudaMalloc(&s->sort_order, (size_t)s->cnt * sizeof(int)));
+      k_slot_identity<<<(s->nloc + kSortThreads - 1) / kSortThreads, kSortThreads, 0, s->stream>>>(s->sort_order, s->nloc, 0);
+      CUC(cudaGetLastError());
+      CUC(cudaMalloc(&s->sort_key, (size_t)s->cnt * sizeof(unsigned int)));
+      CUC(cudaMalloc(&s->sort_count, (size_t)s->sort_ncell * sizeof(unsigned int)));
+      CUC(cudaMalloc(&s->sort_offs, ((size_t)s->sort_ncell + 1) * sizeof(unsigned int)));
+      CUC(cudaMalloc(&s->sort_bsum, ((size_t)(s->sort_ncell + kScanBlock - 1) / kScanBlock + 1) * sizeof(unsigned int)));
+      CUC(cudaMemsetAsync(s->sort_count, 0, (size_t)s->sort_ncell * sizeof(unsigned int), s->stream));
+    }
   }
   // lanes per particle in k_gather: enough threads to keep ~2 CTAs of 256 on every SM, never more lanes than
   // half the rows they share
@@ -932,12 +1011,13 @@ extern "C" int ljmd_set_boundary(ljmd_system* s, int bc) {
     s->rdf_valid = 0;
     // Re-anchor the evaluation positions on what the caller sees (the wrapped positions) and,
     // for a periodic box, rebuild the fixed-point records the other modes do not maintain.
+    int rc = maybe_sort_records(s, true);   // a box that just became periodic wants its records sorted
+    if (rc) return rc;
     StepParams p = make_step_params(s, 0.);
     k_prepare<<<step_grid(s), kStepThreads, 0, s->stream>>>(p);
     CU(cudaGetLastError());
     s->launches += 1;
-    int rc = allgather_positions(s);
-    if (rc) return rc;
+    if ((rc = allgather_positions(s))) return rc;
     CU(cudaStreamSynchronize(s->stream));
   }
   return LJMD_OK;
@@ -967,6 +1047,7 @@ extern "C" int ljmd_set_state(ljmd_system* s, const float* pos4, const float* ve
   int rc = check_domain(s, pos4);
   if (rc) return rc;
   if ((rc = upload_state(s, pos4, vel4))) return rc;
+  if ((rc = maybe_sort_records(s, true))) return rc;
   StepParams p = make_step_params(s, 0.);
   k_prepare<<<step_grid(s), kStepThreads, 0, s->stream>>>(p);
   CU(cudaGetLastError());
@@ -1044,6 +1125,21 @@ extern "C" int ljmd_step(ljmd_system* s, double dt, int nsteps, int rdf_every) {
     return set_err(LJMD_ERR_ARG, "trace holds %d of %d steps: read it before %d more", s->trace_n, s->trace_cap, nsteps);
   StepParams p = make_step_params(s, dt);
   if (s->timing) CU(cudaEventRecord(s->ev_begin, s->stream));
+  // Periodic Newton-3 runs re-sort their records every sort_interval steps (handle-wide count, so a batch and the
+  // same steps one by one sort at the same steps and stay bit-identical).  A sort needs a step that starts with a
+  // plain drift, so the batch is cut there into segments, each run by the loop below.
+  const int total_steps = nsteps;
+  int seg_done = 0;
+  do {
+  nsteps = total_steps - seg_done;
+  {
+    int rc = maybe_sort_records(s, false);
+    if (rc) return rc;
+    if (s->frames && s->slot && s->bc == LJMD_BC_PERIODIC) {
+      const long long room = std::max<long long>(1, s->sort_interval - s->steps_since_sort);
+      if (room < nsteps) nsteps = (int)room;
+    }
+  }
   bool drifted = false;
   // Steady-state steps of a batch (previous step fused this one's drift, this one fuses the next) are the same
   // launches with the same arguments, RDF cadence included: capture `period` of them once in a CUDA graph and
@@ -1052,8 +1148,10 @@ extern "C" int ljmd_step(ljmd_system* s, double dt, int nsteps, int rdf_every) {
   // timing, L2 flush, trace), on more than one GPU, and with LJMD_GRAPH=0.
   const int period = rdf_every > 0 ? rdf_every : 16;
   const char* genv = getenv("LJMD_GRAPH");
+  // (the captured RDF cadence counts from the segment's first step: only segments that start on it replay)
   const bool use_graph = s->world == 1 && !s->timing && s->flush_bytes == 0 && period <= 64 &&
-                         nsteps - 2 >= 2 * period && !(genv && genv[0] == '0');
+                         nsteps - 2 >= 2 * period && !(genv && genv[0] == '0') &&
+                         (rdf_every <= 0 || seg_done % rdf_every == 0);
   // Kick-drift-wrap fusion inside a batch.  With the fabric an EVN step of the ordered kernel has no barrier
   // between a peer's force kernel and this rank's finishing kernel, so its position pushes must not be fused.
   // A trace row needs the end-of-step velocities: the fused EVN half-kick of the next step would be in them
@@ -1101,7 +1199,7 @@ extern "C" int ljmd_step(ljmd_system* s, double dt, int nsteps, int rdf_every) {
       }
       k += reps * period;    // the steps left (at least the last one) run below, with the same cadence
     }
-    const bool rdf = rdf_every > 0 && ((k + 1) % rdf_every == 0);
+    const bool rdf = rdf_every > 0 && ((seg_done + k + 1) % rdf_every == 0);
     if (s->flush_bytes) CU(cudaMemsetAsync(s->flush_buf, k & 0xff, s->flush_bytes, s->stream));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (s->timing) {
@@ -1120,6 +1218,9 @@ extern "C" int ljmd_step(ljmd_system* s, double dt, int nsteps, int rdf_every) {
       s->step_ev.push_back(e1);
     }
   }
+  seg_done += nsteps;
+  s->steps_since_sort += nsteps;
+  } while (seg_done < total_steps);
   if (s->timing) CU(cudaEventRecord(s->ev_end, s->stream));
   int rc = sync_scalars(s);
   if (rc) return rc;
@@ -1145,6 +1246,8 @@ extern "C" int ljmd_integrate_host(ljmd_system* s, double dt, float* pos4, float
   if (!pos4 || !vel4) return set_err(LJMD_ERR_ARG, "pos4/vel4 must not be NULL");
   int rc = upload_state(s, pos4, vel4);
   if (rc) return rc;
+  if ((rc = maybe_sort_records(s, false))) return rc;
+  s->steps_since_sort += 1;
   StepParams p = make_step_params(s, dt);
   if ((rc = one_step(s, p, false))) return rc;
   // a rank moves ITS shard both ways: up from the caller's arrays, back into the same places.  On one GPU (and
@@ -1162,12 +1265,13 @@ extern "C" int ljmd_compute_forces(ljmd_system* s, int with_rdf) {
   MULTI_ALL(s, ljmd_compute_forces(sub, with_rdf));
   CHECK_S(s);
   // positions the caller sees are the wrapped ones: evaluate there (CalculateForces reads h_Pos)
+  int rc = maybe_sort_records(s, false);
+  if (rc) return rc;
   StepParams p = make_step_params(s, 0.);
   k_prepare<<<step_grid(s), kStepThreads, 0, s->stream>>>(p);
   CU(cudaGetLastError());
   s->launches += 1;
-  int rc = allgather_positions(s);
-  if (rc) return rc;
+  if ((rc = allgather_positions(s))) return rc;
   if ((rc = evaluate(s, p, GATHER_EVAL, with_rdf != 0, 0))) return rc;
   rc = sync_scalars(s);
   if (s->timing) collect_timing(s);
@@ -1664,12 +1768,14 @@ int ljmd_legacy_forces(ljmd_system* s, const float* d_pos, float* d_force, float
   // its DMA has landed, and this handle's stream is non-blocking: order explicitly after the legacy stream.
   CU(cudaStreamSynchronize(cudaStreamLegacy));
   CU(cudaMemcpyAsync(s->pos, d_pos, (size_t)s->N * 16, cudaMemcpyDeviceToDevice, s->stream));
+  int rc = maybe_sort_records(s, false);   // the caller integrates on its side: one call = one step
+  if (rc) return rc;
+  s->steps_since_sort += 1;
   StepParams p = make_step_params(s, 0.);
   k_prepare<<<step_grid(s), kStepThreads, 0, s->stream>>>(p);
   CU(cudaGetLastError());
   s->launches += 1;
-  int rc = evaluate(s, p, GATHER_EVAL, rdf256 != nullptr, 0);
-  if (rc) return rc;
+  if ((rc = evaluate(s, p, GATHER_EVAL, rdf256 != nullptr, 0))) return rc;
   CU(cudaMemcpyAsync(d_force, s->force, (size_t)s->N * 16, cudaMemcpyDeviceToDevice, s->stream));
   if ((rc = sync_scalars(s))) return rc;
   if (pressure) *pressure = (float)s->h_sc->Pvirial;
@@ -1719,12 +1825,13 @@ static int init_phase(ljmd_system* s, int phase, unsigned long long seed, const 
 // after the three phases: what ljmd_set_state does once the arrays are on the device
 static int init_finish(ljmd_system* s) {
   CHECK_S(s);
+  int rc = maybe_sort_records(s, true);
+  if (rc) return rc;
   StepParams p = make_step_params(s, 0.);
   k_prepare<<<step_grid(s), kStepThreads, 0, s->stream>>>(p);
   CU(cudaGetLastError());
   s->launches += 1;
-  int rc = allgather_positions(s);
-  if (rc) return rc;
+  if ((rc = allgather_positions(s))) return rc;
   CU(cudaMemsetAsync(s->sc, 0, sizeof(DevScalars), s->stream));
   if ((rc = evaluate(s, p, GATHER_EVAL, false, 0))) return rc;
   s->rdf_nacc = 0;
@@ -1762,12 +1869,14 @@ extern "C" int ljmd_init_state(ljmd_system* s, unsigned long long seed) {
 // shared memory, float products, double accumulation per thread.
 template <bool PERIODIC>
 __global__ void __launch_bounds__(256) k_shear(const uint4* __restrict__ jrec, const float4* __restrict__ vel, int N,
-                                               int i_begin, int i_end, float c2, double kunit, double* __restrict__ out2) {
+                                               int i_begin, int i_end, float c2, double kunit, double* __restrict__ out2,
+                                               const int* __restrict__ slot) {
   __shared__ uint4 tile[256];
   __shared__ double red[2][8];
-  const int i = i_begin + blockIdx.x * 256 + threadIdx.x;
-  const bool live = i < i_end;
-  const uint4 me = jrec[live ? i : i_begin];
+  const int ip = i_begin + blockIdx.x * 256 + threadIdx.x;   // particle (the velocity's index)
+  const bool live = ip < i_end;
+  const int i = live ? (slot ? slot[ip - i_begin] : ip) : i_begin;   // its record
+  const uint4 me = jrec[i];
   double acc = 0.;
   for (int j0 = 0; j0 < N; j0 += 256) {
     __syncthreads();
@@ -1796,7 +1905,7 @@ __global__ void __launch_bounds__(256) k_shear(const uint4* __restrict__ jrec, c
   if (!live) acc = 0.;
   acc *= kunit * kunit;                                    // k-units^2 -> sigma^2 (1 for open boxes)
   double kin = 0.;
-  if (live) { const float4 v = vel[i - i_begin]; kin = (double)(-v.x * v.y); }   // :335 float product, double sum
+  if (live) { const float4 v = vel[ip - i_begin]; kin = (double)(-v.x * v.y); }   // :335 float product, double sum
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { acc += __shfl_xor_sync(0xffffffffu, acc, o); kin += __shfl_xor_sync(0xffffffffu, kin, o); }
   if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = acc; red[1][threadIdx.x >> 5] = kin; }
@@ -1818,8 +1927,8 @@ static int shear_parts(ljmd_system* s, double* conf, double* kin) {
   CU(cudaMalloc(&d, (size_t)2 * nb * sizeof(double)));
   const double k2 = 4294967296.0 / s->L;
   const uint4* jrec = periodic ? s->upos : reinterpret_cast<const uint4*>(s->posA);
-  if (periodic) k_shear<true><<<nb, 256, 0, s->stream>>>(jrec, s->vel, s->N, s->i_begin, s->i_end, (float)(k2 * k2), 1. / k2, d);
-  else k_shear<false><<<nb, 256, 0, s->stream>>>(jrec, s->vel, s->N, s->i_begin, s->i_end, 1.f, 1., d);
+  if (periodic) k_shear<true><<<nb, 256, 0, s->stream>>>(jrec, s->vel, s->N, s->i_begin, s->i_end, (float)(k2 * k2), 1. / k2, d, s->slot);
+  else k_shear<false><<<nb, 256, 0, s->stream>>>(jrec, s->vel, s->N, s->i_begin, s->i_end, 1.f, 1., d, s->slot);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { cudaFree(d); return set_err(LJMD_ERR_CUDA, "k_shear launch: %s", cudaGetErrorString(e)); }
   s->launches += 1;

@@ -60,6 +60,10 @@ struct SymParams {
   int nwin;        // windows per super-tile = gridDim.y
   int win_shift;   // blockIdx.y -> window (blockIdx.y + win_shift) mod nwin: the partial windows at both ends of
                    // the band are launched last, so the tail of the launch is made of the short CTAs
+  // warp frames (FRAMES kernels, periodic boxes; see "Warp frames" below)
+  int frames;      // 0: every chunk takes the fixed-point path (particle order not spatially sorted)
+  float kunit;     // L / 2^32: fixed-point units -> sigma
+  float far2;      // (R_far / kunit)^2: squared gap, in fixed-point units, from which a chunk may take the float path
 };
 
 // Units of a super-tile's band: tile t = 0..mi-1 owns blocks q in [t, t + h_t] counted from the super-tile's
@@ -76,6 +80,102 @@ __host__ __device__ inline int sym_partner_count(int g, int n) {
   return n / 2 - 1 + (g < n / 2 ? 1 : 0);
 }
 inline int sym_max_partner_count(int n) { return (n & 1) ? (n - 1) / 2 : n / 2; }
+
+// ---- Warp frames: the periodic minimum image without per-pair integer work -----------------------------------
+// The fixed-point minimum image costs an integer subtract and an I2FP per axis and pair (and the c2 multiply that
+// brings r^-2 back to sigma units): 7 of the ~25 issue slots of a pair.  When the particle order is spatially
+// sorted (ljmd_core.cu re-sorts the records along a Hilbert curve every few hundred steps) the 128 i-particles a
+// warp holds and the 32 j-records of a chunk are two small clouds, and for most (warp, chunk) combinations NO pair
+// can come near half a box length on any axis.  For those the image is one translation: the warp keeps its
+// i-particles as floats relative to the centre c of its own cloud, converts each staged j-record once to
+// (float)((int)(u_j - c)) * L/2^32 — the 32-bit wrap of that one subtract is the image — and the pair loop is the
+// open-box loop (one FADD2 per axis, no c2).  The decision is exact and per (warp, chunk): every lane checks its
+// own record against the warp's box on the ring of 2^32 units, |u_j - c| + h < 2^31 per axis (no pair can wrap),
+// one vote.  Chunks that fail, partial chunks and ragged tiles take the fixed-point loop, so the result never
+// depends on the order being sorted — only the speed does.  Accuracy: a frame coordinate is a float of up to L/2,
+// i.e. coarser than the fixed-point records near pairs need; so a chunk also has to be FAR — the gap between the
+// warp's box and each record at least R_far = 2.5 sigma, where the force gradient is 1e-4 of the contact value —
+// and the near chunks (a few per cent) keep the fixed-point path.
+struct WarpFrame {
+  int cx, cy, cz;              // centre of the warp's i-particles, fixed-point units (wrapping)
+  int hx, hy, hz;              // half extents (+2 units of slack), < 2^30
+  unsigned limx, limy, limz;   // 2^31 - h: a record with |u_j - c| below it cannot wrap against any i of the warp
+  bool ok;                     // the warp's particles span less than half the box on every axis, none is a clamped duplicate
+};
+
+// Load the thread's 2*NPAIR i-particles, WARP-CONTIGUOUS: warp w holds particles [ibase + w*64*NPAIR, +64*NPAIR),
+// lane l the ones at offsets l, 32 + l, 64 + l, ...; pair q = offsets (2q, 2q+1) * 32.  (k_force strides by
+// THREADS instead; here a warp's particles must be neighbours in the sorted order so that their box is small.)
+template <typename V, int THREADS, int NPAIR>
+__device__ __forceinline__ int sym_i_offset(int m) {
+  return ((int)threadIdx.x >> 5) * (64 * NPAIR) + m * 32 + ((int)threadIdx.x & 31);
+}
+template <typename V, bool PERIODIC, int THREADS, int NPAIR>
+__device__ __forceinline__ bool load_i_particles_warp(const ForceParams& p, int ibase, PairI<V> (&pi)[NPAIR]) {
+  bool all_valid = true;
+#pragma unroll
+  for (int q = 0; q < NPAIR; ++q) {
+    int i0 = ibase + sym_i_offset<V, THREADS, NPAIR>(2 * q), i1 = i0 + 32;
+    pi[q].v_lo = i0 < p.i_end;
+    pi[q].v_hi = i1 < p.i_end;
+    all_valid = all_valid && pi[q].v_lo && pi[q].v_hi;
+    if (!pi[q].v_lo) i0 = p.i_end - 1;
+    if (!pi[q].v_hi) i1 = p.i_end - 1;
+    pi[q].i_lo = (unsigned)i0;
+    pi[q].i_hi = (unsigned)i1;
+    const uint4 r0 = p.jrec[i0], r1 = p.jrec[i1];
+    pi[q].ax = (int)r0.x; pi[q].ay = (int)r0.y; pi[q].az = (int)r0.z;
+    pi[q].bx = (int)r1.x; pi[q].by = (int)r1.y; pi[q].bz = (int)r1.z;
+    if (!PERIODIC) {
+      const float4 f0 = p.posf[i0], f1 = p.posf[i1];
+      pi[q].x2 = mk2<V>(f0.x, f1.x); pi[q].y2 = mk2<V>(f0.y, f1.y); pi[q].z2 = mk2<V>(f0.z, f1.z);
+    } else {
+      pi[q].x2 = pi[q].y2 = pi[q].z2 = bc2<V>(0.f);
+    }
+  }
+  return all_valid;
+}
+
+// The warp's frame from the fixed-point coordinates just loaded, and the float copies of the i-particles in it.
+template <typename V, int NPAIR>
+__device__ __forceinline__ void make_warp_frame(PairI<V> (&pi)[NPAIR], float kunit, bool warp_all_valid, WarpFrame& fr) {
+  const unsigned full = 0xffffffffu;
+  const int u0x = __shfl_sync(full, pi[0].ax, 0), u0y = __shfl_sync(full, pi[0].ay, 0), u0z = __shfl_sync(full, pi[0].az, 0);
+  int lo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, hi[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
+#pragma unroll
+  for (int q = 0; q < NPAIR; ++q) {
+    const int r[6] = {pi[q].ax - u0x, pi[q].bx - u0x, pi[q].ay - u0y, pi[q].by - u0y, pi[q].az - u0z, pi[q].bz - u0z};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      lo[a] = min(lo[a], min(r[2 * a], r[2 * a + 1]));
+      hi[a] = max(hi[a], max(r[2 * a], r[2 * a + 1]));
+    }
+  }
+  bool small = warp_all_valid;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    lo[a] = __reduce_min_sync(full, lo[a]);
+    hi[a] = __reduce_max_sync(full, hi[a]);
+    // every particle within a quarter box of the first one: the spread is below half a box and lo/hi did not wrap
+    small = small && lo[a] > -(1 << 30) && hi[a] < (1 << 30);
+  }
+  fr.ok = small;
+  fr.cx = (int)((unsigned)u0x + (unsigned)((lo[0] + hi[0]) >> 1));
+  fr.cy = (int)((unsigned)u0y + (unsigned)((lo[1] + hi[1]) >> 1));
+  fr.cz = (int)((unsigned)u0z + (unsigned)((lo[2] + hi[2]) >> 1));
+  fr.hx = small ? ((hi[0] - lo[0]) >> 1) + 2 : 0;
+  fr.hy = small ? ((hi[1] - lo[1]) >> 1) + 2 : 0;
+  fr.hz = small ? ((hi[2] - lo[2]) >> 1) + 2 : 0;
+  fr.limx = 0x80000000u - (unsigned)fr.hx;
+  fr.limy = 0x80000000u - (unsigned)fr.hy;
+  fr.limz = 0x80000000u - (unsigned)fr.hz;
+#pragma unroll
+  for (int q = 0; q < NPAIR; ++q) {
+    pi[q].x2 = mk2<V>(__int2float_rn(pi[q].ax - fr.cx) * kunit, __int2float_rn(pi[q].bx - fr.cx) * kunit);
+    pi[q].y2 = mk2<V>(__int2float_rn(pi[q].ay - fr.cy) * kunit, __int2float_rn(pi[q].by - fr.cy) * kunit);
+    pi[q].z2 = mk2<V>(__int2float_rn(pi[q].az - fr.cz) * kunit, __int2float_rn(pi[q].bz - fr.cz) * kunit);
+  }
+}
 
 // ---- RDF pruning by block bounding boxes ----------------------------------------------------------------------
 // One CTA per block of B particles: component-wise min / max of the j-records (fixed-point for periodic boxes,
@@ -218,16 +318,46 @@ __device__ __forceinline__ void pair_sym(const uint4& uj, const PairI<V>& pi, Pa
     for (int c = 0; c < nchunk; ++c) {                                                                           \
       const int jl = (c << 5) + lane;                                                                            \
       /* stage the chunk twice back to back: step k reads entry lane + k, no wrap arithmetic */                  \
-      const uint4 rec = tu[min(jl, nj - 1)];                                                                     \
+      uint4 rec = tu[min(jl, nj - 1)];                                                                           \
+      const bool full = warp_all_valid && ((c << 5) + 32 <= nj);                                                 \
+      bool fl = false;                                                                                           \
+      if (FRAMES && !(RU) && fr.ok && full) {                                                                    \
+        /* my record against the warp's box on the ring: can any pair of this chunk wrap?  is it far enough? */ \
+        const int rx = (int)rec.x - fr.cx, ry = (int)rec.y - fr.cy, rz = (int)rec.z - fr.cz;                     \
+        const unsigned axu = (unsigned)abs(rx), ayu = (unsigned)abs(ry), azu = (unsigned)abs(rz);                \
+        const float gx = fmaxf(0.f, __int2float_rn((int)axu - fr.hx));                                           \
+        const float gy = fmaxf(0.f, __int2float_rn((int)ayu - fr.hy));                                           \
+        const float gz = fmaxf(0.f, __int2float_rn((int)azu - fr.hz));                                           \
+        const bool okj = axu < fr.limx && ayu < fr.limy && azu < fr.limz &&                                      \
+                         __fmaf_rn(gz, gz, __fmaf_rn(gy, gy, gx * gx)) >= sp.far2;                               \
+        fl = __all_sync(0xffffffffu, okj);                                                                       \
+        if (fl)                                                                                                  \
+          rec = make_uint4(__float_as_uint(__int2float_rn(rx) * sp.kunit), __float_as_uint(__int2float_rn(ry) * sp.kunit), \
+                           __float_as_uint(__int2float_rn(rz) * sp.kunit), 0u);                                  \
+      }                                                                                                          \
+      if (FRAMES && fl != cur_float) {                                                                           \
+        fold_forces(cur_float ? 4.f : p.fscale);   /* the accumulators change units with the path */             \
+        cur_float = fl;                                                                                          \
+      }                                                                                                          \
       __syncwarp();                                                                                              \
       mystage[lane] = rec;                                                                                       \
       mystage[lane + 32] = rec;                                                                                  \
       __syncwarp();                                                                                              \
       const uint4* sp_l = mystage + lane;                                                                        \
       float rjx = 0.f, rjy = 0.f, rjz = 0.f;                                                                     \
-      const bool full = warp_all_valid && ((c << 5) + 32 <= nj);                                                 \
       const unsigned nxt_lane = (lane + 1) & 31;                                                                 \
-      if (full) {                                                                                                \
+      if (FRAMES && fl) {                                                                                        \
+        _Pragma("unroll UNROLLK")                                                                                \
+        for (int k = 0; k < 32; ++k) {                                                                           \
+          const uint4 uj = sp_l[k];                                                                              \
+          _Pragma("unroll")                                                                                      \
+          for (int q = 0; q < NPAIR; ++q)                                                                        \
+            pair_sym<V, false, false, false>(uj, pi[q], acc[q], false, false, rjx, rjy, rjz, p, 0u, R);          \
+          rjx = __shfl_sync(0xffffffffu, rjx, nxt_lane);                                                         \
+          rjy = __shfl_sync(0xffffffffu, rjy, nxt_lane);                                                         \
+          rjz = __shfl_sync(0xffffffffu, rjz, nxt_lane);                                                         \
+        }                                                                                                        \
+      } else if (full) {                                                                                         \
         _Pragma("unroll UNROLLK")                                                                                \
         for (int k = 0; k < 32; ++k) {                                                                           \
           const uint4 uj = sp_l[k];                                                                              \
@@ -254,7 +384,12 @@ __device__ __forceinline__ void pair_sym(const uint4& uj, const PairI<V>& pi, Pa
           rjz = __shfl_sync(0xffffffffu, rjz, nxt_lane);                                                         \
         }                                                                                                        \
       }                                                                                                          \
-      /* the accumulators are home again; jl < BJ always.  12-byte entries: stride 3 words, conflict-free */     \
+      /* the accumulators are home again; jl < BJ always.  12-byte entries: stride 3 words, conflict-free.       \
+         FRAMES kernels scale here (the two paths accumulate in different units), the others at the very end */  \
+      if (FRAMES) {                                                                                              \
+        const float rs = fl ? 4.f : p.fscale;                                                                    \
+        rjx *= rs; rjy *= rs; rjz *= rs;                                                                         \
+      }                                                                                                          \
       myslice[3 * jl] = rjx; myslice[3 * jl + 1] = rjy; myslice[3 * jl + 2] = rjz;                                \
     }                                                                                                            \
   }
@@ -263,8 +398,10 @@ __device__ __forceinline__ void pair_sym(const uint4& uj, const PairI<V>& pi, Pa
 // packed in an int2: x = j0, y = nj | slot << 10 | tile << 16 | diag << 24 | first-of-tile << 25.
 constexpr int kSymMaxItems = 256;   // mi * mju <= 16 * 16
 
-template <typename V, bool PERIODIC, bool RDF, int THREADS, int MINB, int NPAIR, int UNROLLK = 4>
+// FRAMES (periodic only): chunks that qualify take the float loop in the warp's frame (see "Warp frames" above).
+template <typename V, bool PERIODIC, bool RDF, int THREADS, int MINB, int NPAIR, int UNROLLK = 4, bool FRAMES = false>
 __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp) {
+  static_assert(!FRAMES || PERIODIC, "warp frames replace the periodic minimum image only");
   pdl_trigger();
   pdl_wait();
   constexpr int IPT = 2 * NPAIR;
@@ -359,22 +496,36 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
   int cur_tile = -1;
   bool warp_all_valid = false;
   uint4 my_lo = make_uint4(0u, 0u, 0u, 0u), my_hi = my_lo;   // bounding box of my own block (RDF pruning)
+  WarpFrame fr;                  // FRAMES: this warp's frame for the tile in registers
+  fr.cx = fr.cy = fr.cz = fr.hx = fr.hy = fr.hz = 0; fr.limx = fr.limy = fr.limz = 0u; fr.ok = false;
+  bool cur_float = false;        // FRAMES: the tile-level force accumulators hold float-path (sigma) units
+  // FRAMES: tile-level force accumulators -> run-level ones, in final units (the two paths differ by L/2^32)
+  auto fold_forces = [&](float sc) {
+    const V s2 = bc2<V>(sc);
+#pragma unroll
+    for (int q = 0; q < NPAIR; ++q) {
+      fxrun[q] = fma2(acc[q].fx, s2, fxrun[q]);
+      fyrun[q] = fma2(acc[q].fy, s2, fyrun[q]);
+      fzrun[q] = fma2(acc[q].fz, s2, fzrun[q]);
+      acc[q].fx = acc[q].fy = acc[q].fz = zero2;
+    }
+  };
 
   // the tile in registers is done for this window: its partial forces leave the CTA
   auto store_tile = [&]() {
-    const float fs = p.fscale;
+    const float fs = FRAMES ? 1.f : p.fscale;   // FRAMES: the run-level sums are already in final units
 #pragma unroll
     for (int q = 0; q < NPAIR; ++q) {
       const float2 fx = upk(fxrun[q]), fy = upk(fyrun[q]), fz = upk(fzrun[q]);
       const float2 s6 = upk(s6run[q]), w = upk(wrun[q]);
-      const int il = (ibase - p.i_begin) + (2 * q) * THREADS + tid;
+      const int il = (ibase - p.i_begin) + sym_i_offset<V, THREADS, NPAIR>(2 * q);
       // r^-12 - r^-6 = u/12 - r^-6/2
       if (pi[q].v_lo) {
         out[il] = make_float4(fx.x * fs, fy.x * fs, fz.x * fs, w.x * (1.f / 12.f) - 0.5f * s6.x);
         wsum += (double)w.x;
       }
       if (pi[q].v_hi) {
-        out[il + THREADS] = make_float4(fx.y * fs, fy.y * fs, fz.y * fs, w.y * (1.f / 12.f) - 0.5f * s6.y);
+        out[il + 32] = make_float4(fx.y * fs, fy.y * fs, fz.y * fs, w.y * (1.f / 12.f) - 0.5f * s6.y);
         wsum += (double)w.y;
       }
       s6run[q] = wrun[q] = fxrun[q] = fyrun[q] = fzrun[q] = zero2;
@@ -392,9 +543,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
       if (cur_tile >= 0) store_tile();
       cur_tile = (d.y >> 16) & 255;
       ibase = ibase0 + cur_tile * B;
-      const bool all_valid = load_i_particles<V, PERIODIC, THREADS, NPAIR>(p, ibase, pi);
+      const bool all_valid = load_i_particles_warp<V, PERIODIC, THREADS, NPAIR>(p, ibase, pi);
       // is every lane of this warp holding real particles? (warp-uniform choice of the unmasked fast path)
       warp_all_valid = __all_sync(0xffffffffu, all_valid);
+      if (FRAMES) {
+        if (sp.frames) make_warp_frame<V, NPAIR>(pi, sp.kunit, warp_all_valid, fr);
+        else fr.ok = false;
+      }
       if (RDF && sp.bbox != nullptr) { const int gI = ibase / B; my_lo = sp.bbox[2 * gI]; my_hi = sp.bbox[2 * gI + 1]; }
     }
     const int st = it & 1;
@@ -404,14 +559,15 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
     if (diag) {
       // ---- diagonal block: ordered loop over its own particles, self pair excluded ----
       wgt = 1.f;
-      const int jrel0 = j0 - ibase - tid;
+      if (FRAMES && cur_float) { fold_forces(4.f); cur_float = false; }   // the ordered loop is fixed-point
+      const int jrel0 = j0 - ibase - sym_i_offset<V, THREADS, NPAIR>(0);   // j relative to my particle m = 0
 #pragma unroll 2
       for (int j = 0; j < nj; ++j) {
         const uint4 uj = tu[j];
         const int jr = jrel0 + j;
 #pragma unroll
         for (int q = 0; q < NPAIR; ++q)
-          pair_body<V, PERIODIC, true, RDF>(uj, pi[q], acc[q], jr == (2 * q) * THREADS, jr == (2 * q + 1) * THREADS,
+          pair_body<V, PERIODIC, true, RDF>(uj, pi[q], acc[q], jr == (2 * q) * 32, jr == (2 * q + 1) * 32,
                                             p, (unsigned)(j0 + j), R);
       }
     } else {
@@ -433,13 +589,16 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
     // fold the unit's tile-level accumulators into the run-level ones (two-level float summation);
     // an unordered pair of a partner block stands for two ordered pairs in the potential / virial sums
     const V w2 = bc2<V>(wgt);
+    if (FRAMES) fold_forces(cur_float ? 4.f : p.fscale);
 #pragma unroll
     for (int q = 0; q < NPAIR; ++q) {
       s6run[q] = fma2(acc[q].s6, w2, s6run[q]);
       wrun[q] = fma2(acc[q].w, w2, wrun[q]);
-      fxrun[q] = add2(fxrun[q], acc[q].fx);
-      fyrun[q] = add2(fyrun[q], acc[q].fy);
-      fzrun[q] = add2(fzrun[q], acc[q].fz);
+      if (!FRAMES) {
+        fxrun[q] = add2(fxrun[q], acc[q].fx);
+        fyrun[q] = add2(fyrun[q], acc[q].fy);
+        fzrun[q] = add2(fzrun[q], acc[q].fz);
+      }
       acc[q].s6 = acc[q].w = acc[q].fx = acc[q].fy = acc[q].fz = zero2;
     }
     __syncthreads();  // slices complete; stage st free for the load after next
@@ -470,7 +629,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
   // so the gather kernels never read stale data and nothing has to be cleared between steps
   {
     float4* dst = sp.rpart + ((size_t)blockIdx.x * sp.nwin + win) * ((size_t)sp.mju * BJ);
-    const float fs = p.fscale;
+    const float fs = FRAMES ? 1.f : p.fscale;   // FRAMES: the slices were scaled chunk by chunk
     for (int k = tid; k < sp.mju * BJ; k += THREADS)
       dst[k] = make_float4(racc[3 * k] * fs, racc[3 * k + 1] * fs, racc[3 * k + 2] * fs, 0.f);
   }

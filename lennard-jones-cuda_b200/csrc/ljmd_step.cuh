@@ -81,7 +81,19 @@ struct StepParams {
   float4* rsum;           // [npad] rank-local column sums (world > 1)
   const float4* rshard;   // [nloc] reaction totals after the reduce-scatter (world > 1, NCCL path)
   Fabric fab;             // peer windows (world > 1, fabric path)
+  // Record order (periodic Newton-3 runs): slot[il] is the global RECORD index of local particle il — where its
+  // evaluation position lives in posA / upos and which row entries of fpart / rpart / rsum are its.  The state
+  // arrays (pos, vel, force, tforce) stay in the caller's particle order; only the records are kept sorted along
+  // a Hilbert curve so that the force kernel's warps and chunks are compact clouds (ljmd_force_sym.cuh, "Warp
+  // frames").  A permutation of [i_begin, i_begin + nloc); nullptr = identity.  ANY permutation is correct: the
+  // records are rewritten through it before every evaluation, so a stale sort only costs speed.
+  const int* slot;
+  // the inverse: order[k] is the local particle whose record is i_begin + k (nullptr = identity).  k_gather runs
+  // record-major — its ~100 row and reaction reads per particle stay coalesced, only the handful of state-array
+  // accesses scatter — while the drift and finish kernels, which touch one record each, run particle-major.
+  const int* order;
 };
+__device__ __forceinline__ int record_of(const StepParams& p, int il) { return p.slot ? p.slot[il] : p.i_begin + il; }
 
 constexpr int kBlockParticles = 512;   // = kITile of ljmd_core.cu / B of k_force_sym
 
@@ -214,7 +226,7 @@ __global__ void __launch_bounds__(kStepThreads) k_drift(const StepParams p) {
   x.x = drift1(x.x, v.x, f.x, p.dt, p.dt2);
   x.y = drift1(x.y, v.y, f.y, p.dt, p.dt2);
   x.z = drift1(x.z, v.z, f.z, p.dt, p.dt2);
-  publish_position(p, p.i_begin + il, x);
+  publish_position(p, record_of(p, il), x);
   if (!CANON) {
     v.x = kick1(v.x, f.x, p.dt);
     v.y = kick1(v.y, f.y, p.dt);
@@ -227,7 +239,7 @@ __global__ void __launch_bounds__(kStepThreads) k_drift(const StepParams p) {
 __global__ void __launch_bounds__(kStepThreads) k_prepare(const StepParams p) {
   const int il = blockIdx.x * kStepThreads + threadIdx.x;
   if (il >= p.nloc) return;
-  publish_position(p, p.i_begin + il, p.pos[il]);
+  publish_position(p, record_of(p, il), p.pos[il]);
 }
 
 // Deterministic two-value block reduction + last-block final sum over all blocks.
@@ -294,12 +306,12 @@ enum { GATHER_EVAL = 0, GATHER_EVN = 1, GATHER_TVN = 2 };
 // boundary wrap, kinetic energy) goes straight on with the drift of step n+1 for its particle — the same
 // arithmetic k_drift would do on the values it just produced — so a batched ljmd_step runs one O(N) kernel
 // per step beside the force kernel instead of two.  `canon`: step n+1 is TVN (no first half-kick).
-__device__ __forceinline__ void fused_next_drift(const StepParams& p, int il, float4 x, float4& v, const float4& f,
+__device__ __forceinline__ void fused_next_drift(const StepParams& p, int rec, float4 x, float4& v, const float4& f,
                                                  bool canon) {
   x.x = drift1(x.x, v.x, f.x, p.dt, p.dt2);
   x.y = drift1(x.y, v.y, f.y, p.dt, p.dt2);
   x.z = drift1(x.z, v.z, f.z, p.dt, p.dt2);
-  publish_position(p, p.i_begin + il, x);
+  publish_position(p, rec, x);
   if (!canon) {
     v.x = kick1(v.x, f.x, p.dt);
     v.y = kick1(v.y, f.y, p.dt);
@@ -322,17 +334,20 @@ __global__ void __launch_bounds__(kStepThreads) k_gather(const StepParams p, int
   // address row loads with one thread each (N = 65 536: 76 -> 46 us; N = 1 500: the TVN step 23.8 -> 15.7 us).
   const int R = 1 << p.gather_shift;
   const int gt = blockIdx.x * kStepThreads + threadIdx.x;
-  const int il = gt >> p.gather_shift, r = gt & (R - 1);
+  const int rl = gt >> p.gather_shift, r = gt & (R - 1);   // rl: my record (local index): rows and reaction entries
+  const int rec = p.i_begin + rl;
+  int il = rl;                                             // il: the particle it belongs to (state arrays)
   double pe = 0., q = 0.;
   float4 f = make_float4(0.f, 0.f, 0.f, 0.f), rr = f;
-  if (il < p.nloc) {
+  if (rl < p.nloc) {
+    if (p.order) il = p.order[rl];
 #pragma unroll 8   // rows are independent loads: keep several in flight (up to ~130 rows with fine splits)
     for (int s = r; s < p.nsplit; s += R) {
-      const float4 g = p.fpart[(size_t)s * p.ilocal_cap + il];
+      const float4 g = p.fpart[(size_t)s * p.ilocal_cap + rl];
       f.x += g.x; f.y += g.y; f.z += g.z; f.w += g.w;
     }
     // Newton-3 kernel, one GPU: the reaction of every pair this particle was the j of
-    if (p.use_sym && p.world == 1) rr = reaction_sum(p, p.i_begin + il, r, R);
+    if (p.use_sym && p.world == 1) rr = reaction_sum(p, rec, r, R);
   }
   for (int o = 1; o < R; o <<= 1) {
     f.x += __shfl_xor_sync(0xffffffffu, f.x, o); f.y += __shfl_xor_sync(0xffffffffu, f.y, o);
@@ -340,18 +355,18 @@ __global__ void __launch_bounds__(kStepThreads) k_gather(const StepParams p, int
     rr.x += __shfl_xor_sync(0xffffffffu, rr.x, o); rr.y += __shfl_xor_sync(0xffffffffu, rr.y, o);
     rr.z += __shfl_xor_sync(0xffffffffu, rr.z, o);
   }
-  if (il < p.nloc && r == 0) {
+  if (rl < p.nloc && r == 0) {
     if (p.use_sym) {
       if (p.world > 1) {
         if (p.fab.n > 0) {
           // pull every rank's column sum for my particle straight from its window, fixed rank order
           rr = make_float4(0.f, 0.f, 0.f, 0.f);
           for (int q = 0; q < p.fab.n; ++q) {
-            const float4 g = reinterpret_cast<const float4*>(p.fab.base[q] + p.fab.off_rsum)[p.i_begin + il];
+            const float4 g = reinterpret_cast<const float4*>(p.fab.base[q] + p.fab.off_rsum)[rec];
             rr.x += g.x; rr.y += g.y; rr.z += g.z;
           }
         } else {
-          rr = p.rshard[il];
+          rr = p.rshard[rl];
         }
       }
       f.x += rr.x; f.y += rr.y; f.z += rr.z;
@@ -366,11 +381,11 @@ __global__ void __launch_bounds__(kStepThreads) k_gather(const StepParams p, int
       v.x = kick1(v.x, f.x, p.dt);
       v.y = kick1(v.y, f.y, p.dt);
       v.z = kick1(v.z, f.z, p.dt);
-      float4 x = p.posA[p.i_begin + il];
+      float4 x = p.posA[rec];
       apply_bc(x, v, p.L, p.bc);
       p.pos[il] = x;
       q = (double)sq3(v.x, v.y, v.z) * 0.5;
-      if (FUSE) fused_next_drift(p, il, x, v, f, false);
+      if (FUSE) fused_next_drift(p, rec, x, v, f, false);
       p.vel[il] = v;
     } else {
       const float4 fo = p.force[il];
@@ -409,11 +424,12 @@ __global__ void __launch_bounds__(kStepThreads) k_finish_tvn(const StepParams p,
     v.x = (float)__dadd_rn(__dmul_rn(a, (double)v.x), __dmul_rn(b, (double)tf.x));   // :503-505
     v.y = (float)__dadd_rn(__dmul_rn(a, (double)v.y), __dmul_rn(b, (double)tf.y));
     v.z = (float)__dadd_rn(__dmul_rn(a, (double)v.z), __dmul_rn(b, (double)tf.z));
-    float4 x = p.posA[p.i_begin + il];
+    const int rec = record_of(p, il);
+    float4 x = p.posA[rec];
     apply_bc(x, v, p.L, p.bc);
     p.pos[il] = x;
     q = (double)sq3(v.x, v.y, v.z) * 0.5;
-    if (FUSE) fused_next_drift(p, il, x, v, p.force[il], true);
+    if (FUSE) fused_next_drift(p, rec, x, v, p.force[il], true);
     p.vel[il] = v;
   }
   if (il == 0) { p.sc->chi = chi; p.sc->Tkin_trial = Tkin; }

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../lennard-jones-cuda_b200/csrc/ljmd_force_sym.cuh"
+#include "../lennard-jones-cuda_b200/csrc/ljmd_hilbert.cuh"
 using namespace ljmd;
 
 #define CK(x)                                                                         \
@@ -196,10 +197,13 @@ static void run_variant(const Problem& pb, const char* tag, int reps, int tile_j
 }
 
 // mju: units per window, mi: i-tiles per super-tile (0: pick like the library's planner for this N)
-template <typename V, bool PERIODIC, bool RDF, int THREADS, int MINB, int NPAIR, int UNROLLK = 4>
+static int g_win_shift = -1;    // >= 0: override of SymParams::win_shift
+static int g_frames = 1;        // FRAMES kernels: SymParams::frames
+static double g_rfar = 2.5;     // FRAMES kernels: R_far
+template <typename V, bool PERIODIC, bool RDF, int THREADS, int MINB, int NPAIR, int UNROLLK = 4, bool FRAMES = false>
 static void run_sym(const Problem& pb, const char* tag, int reps, int bj, std::vector<float4>* keep,
                     bool prune = true, int mju = 0, int mi = 1) {
-  auto kern = k_force_sym<V, PERIODIC, RDF, THREADS, MINB, NPAIR, UNROLLK>;
+  auto kern = k_force_sym<V, PERIODIC, RDF, THREADS, MINB, NPAIR, UNROLLK, FRAMES>;
   const int B = THREADS * 2 * NPAIR;
   const int n = (pb.N + B - 1) / B;
   const int cpb = B / bj;
@@ -243,6 +247,9 @@ static void run_sym(const Problem& pb, const char* tag, int reps, int bj, std::v
   }
   sp.rpart = pb.rpart; sp.ncols = 0; sp.nblk = n; sp.bj = bj;
   sp.mi = mi; sp.mju = mju; sp.nwin = nwin; sp.win_shift = std::min(nwin - 1, ((mi - 1) * cpb + mju - 1) / mju);
+  if (g_win_shift >= 0) sp.win_shift = std::min(nwin - 1, g_win_shift);
+  sp.frames = FRAMES ? g_frames : 0; sp.kunit = (float)(pb.L / 4294967296.0);
+  sp.far2 = (float)((g_rfar * 4294967296.0 / pb.L) * (g_rfar * 4294967296.0 / pb.L));
   const size_t rp_elems = (size_t)nsup * nwin * mju * bj;
   if ((size_t)nwin * pb.N > pb.fpart_elems || rp_elems > pb.rpart_elems) {
     printf("sym   %-44s skipped: needs %zu + %zu records of scratch\n", tag, (size_t)nwin * pb.N, rp_elems);
@@ -317,7 +324,7 @@ static void run_sym(const Problem& pb, const char* tag, int reps, int bj, std::v
 int main(int argc, char** argv) {
   const int N = argc > 1 ? atoi(argv[1]) : 65536;
   const int reps = argc > 2 ? atoi(argv[2]) : 5;
-  const double rho = 1.1;
+  const double rho = getenv("TUNE_RHO") ? atof(getenv("TUNE_RHO")) : 1.1;
   const double L = pow(N / rho, 1. / 3.);
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
@@ -339,6 +346,29 @@ int main(int argc, char** argv) {
     const double sc = 4294967296.0 / L;
     hu[i] = make_uint4((unsigned)(unsigned long long)llrint(hp[i].x * sc), (unsigned)(unsigned long long)llrint(hp[i].y * sc),
                        (unsigned)(unsigned long long)llrint(hp[i].z * sc), 0u);
+  }
+  // TUNE_ORDER=hilbert: the particles sorted along a Hilbert curve (what the library does for periodic boxes);
+  // TUNE_ORDER=random: shuffled (no locality at all); default: lattice order
+  if (const char* ord = getenv("TUNE_ORDER")) {
+    std::vector<std::pair<unsigned long long, int>> keyed(N);
+    int bits = 1;
+    while ((1LL << (3 * bits)) < 2LL * N && bits < 10) ++bits;
+    for (int i = 0; i < N; ++i) {
+      unsigned long long k;
+      if (!strcmp(ord, "hilbert")) {
+        auto cell = [&](float x) { int c = (int)(x / L * (1 << bits)); return (uint32_t)std::min(std::max(c, 0), (1 << bits) - 1); };
+        k = hilbert3(cell(hp[i].x), cell(hp[i].y), cell(hp[i].z), bits);
+      } else {
+        k = (unsigned long long)(rnd() * 1e15);
+      }
+      keyed[i] = {k, i};
+    }
+    std::sort(keyed.begin(), keyed.end());
+    std::vector<float4> hp2(N);
+    std::vector<uint4> hu2(N);
+    for (int i = 0; i < N; ++i) { hp2[i] = hp[keyed[i].second]; hu2[i] = hu[keyed[i].second]; }
+    hp.swap(hp2); hu.swap(hu2);
+    printf("particle order: %s (%d bits per axis)\n", ord, bits);
   }
   Problem pb;
   pb.N = N; pb.L = L; pb.sms = sms;
@@ -363,6 +393,26 @@ int main(int argc, char** argv) {
   if (argc > 3 && !strcmp(argv[3], "shipped")) {   // only the shipped Newton-3 variants (A/B of builds)
     run_sym<P2, true, false, 128, 3, 2, 4>(pb, "periodic sym t128 b3 np2 uk4 bj256", reps, 256, &keepP);
     run_sym<P2, false, false, 128, 3, 2, 4>(pb, "open sym t128 b3 np2 uk4 bj256", reps, 256, &keepO);
+    return 0;
+  }
+  if (argc > 3 && !strcmp(argv[3], "frames")) {
+    // warp frames (periodic boxes): the shipped fixed-point kernel against the FRAMES kernel, frames on and off;
+    // run it with TUNE_ORDER=hilbert|random and TUNE_RHO to see what the particle order is worth
+    const int mju = argc > 4 ? atoi(argv[4]) : 0, mi = argc > 5 ? atoi(argv[5]) : 1;
+    if (N <= 131072) run_variant<P2, true, false, 128, 4, 2, 4>(pb, "periodic ordered P2 t128 b4 np2 u4", reps, 1024, &keepP);
+    run_sym<P2, true, false, 128, 3, 2, 4, false>(pb, "periodic sym fixed-point (shipped r02)", reps, 256, &keepP, true, mju, mi);
+    g_frames = 0;
+    run_sym<P2, true, false, 128, 3, 2, 4, true>(pb, "periodic sym FRAMES kernel, frames off", reps, 256, &keepP, true, mju, mi);
+    g_frames = 1;
+    run_sym<P2, true, false, 128, 3, 2, 4, true>(pb, "periodic sym FRAMES kernel, frames on", reps, 256, &keepP, true, mju, mi);
+    g_rfar = 0.;
+    run_sym<P2, true, false, 128, 3, 2, 4, true>(pb, "periodic sym FRAMES kernel, R_far = 0", reps, 256, &keepP, true, mju, mi);
+    g_rfar = 2.5;
+    run_sym<P2, true, true, 128, 3, 2, 4, false>(pb, "periodic+RDF sym fixed-point", reps, 256, &keepP, true, mju, mi);
+    g_win_shift = 0;
+    run_sym<P2, true, true, 128, 3, 2, 4, false>(pb, "periodic+RDF sym fixed-point, diagonal windows first", reps, 256, &keepP, true, mju, mi);
+    g_win_shift = -1;
+    run_sym<P2, true, true, 128, 3, 2, 4, true>(pb, "periodic+RDF sym FRAMES kernel, frames on", reps, 256, &keepP, true, mju, mi);
     return 0;
   }
   if (argc > 3 && !strcmp(argv[3], "scan_ordered")) {   // ordered kernel, small N: how fine should the j-split be?
