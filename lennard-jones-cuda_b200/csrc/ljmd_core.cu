@@ -381,7 +381,12 @@ static int launch_force(ljmd_system* s, bool rdf) {
   fp.cut_fast = (float)(periodic ? cut * k2 * k2 : cut);
   fp.L = s->L; fp.thr1 = s->thr1; fp.thr2 = s->thr2; fp.dr2 = s->dr2; fp.inv_dr2 = 1.0f / s->dr2;
   const uint4* bbox = nullptr;
-  if (rdf && s->use_sym) {
+  // RDF evaluations of sorted records run the FRAMES build, which prunes chunk by chunk against the warp's own box
+  // (N = 65 536, L = 39: 2.21 -> 2.07 ms; N = 262 144, L = 96: 29.2 -> 27.0 ms) — except in small boxes, where
+  // nearly every chunk is within histogram range of every warp and the block-box kernel is as good (L = 27: 0.257 vs
+  // 0.262 ms).
+  const bool frames_rdf = rdf && s->use_sym && periodic && s->frames && s->sorted && s->L >= 32.;
+  if (rdf && s->use_sym && !frames_rdf) {
     // block bounding boxes: units whose two boxes are out of histogram range skip the RDF test altogether
     if (periodic) k_bbox<true, kITile><<<s->nblk, 128, 0, s->stream>>>(fp.jrec, s->N, s->bbox);
     else k_bbox<false, kITile><<<s->nblk, 128, 0, s->stream>>>(fp.jrec, s->N, s->bbox);
@@ -408,11 +413,10 @@ static int launch_force(ljmd_system* s, bool rdf) {
     sp.frames = (periodic && s->frames && s->sorted) ? 1 : 0;
     sp.kunit = (float)(s->L / 4294967296.0);
     sp.far2 = (float)((kFrameRfar * k2) * (kFrameRfar * k2));
-    // (the RDF build of the FRAMES kernel measured 8-15 % slower than the plain RDF kernel — 166 registers and a
-    // third inner loop beside the queue code — so RDF evaluations, one step in rdf_every, stay fixed-point)
-    if (rdf && s->sorted) sp.win_shift = 0;   // sorted records: the in-range pairs sit in the windows next to the
-                                              // diagonal, the longest CTAs of an RDF launch — start them first
-    if (periodic && s->frames && !rdf) e = launch_force_sym_t<true, false, true>(s, sp);
+    sp.rdf2 = (float)((cut * 1.002 + 1e-3) * k2 * k2);
+    // RDF evaluations of sorted records: the FRAMES build prunes chunk by chunk against the warp's own box (no
+    // block boxes needed); unsorted records keep the fixed-point RDF kernel with its block-box pruning
+    if (periodic && s->frames && (!rdf || frames_rdf)) e = rdf ? launch_force_sym_t<true, true, true>(s, sp) : launch_force_sym_t<true, false, true>(s, sp);
     else if (periodic) e = rdf ? launch_force_sym_t<true, true>(s, sp) : launch_force_sym_t<true, false>(s, sp);
     else e = rdf ? launch_force_sym_t<false, true>(s, sp) : launch_force_sym_t<false, false>(s, sp);
   } else if (periodic) e = rdf ? launch_force_t<true, true>(s, fp) : launch_force_t<true, false>(s, fp);
@@ -842,6 +846,7 @@ static int create_impl(ljmd_system** out, int N, double rho_or_negL, double T0, 
     CUC((sym_smem_opt_in<false, false>()));
     CUC((sym_smem_opt_in<false, true>()));
     CUC((sym_smem_opt_in<true, false, true>()));
+    CUC((sym_smem_opt_in<true, true, true>()));
     // record order: identity until the first sort (LJMD_FRAMES=0: stays the identity, fixed-point kernel only)
     {
       const char* e = getenv("LJMD_FRAMES");

@@ -182,16 +182,25 @@ __device__ __forceinline__ float image_exact(float d, const ForceParams& p) {
 // leaves most lanes idle.  Instead each warp queues (i, j) index pairs in shared memory and drains them 32 at
 // a time with every lane busy.  Bit 31 of the i index marks an unordered pair of the Newton-3 kernel, which
 // stands for (i,j) and (j,i): both fall in the same bin (the reference sequence is odd in the separation).
-constexpr int kRdfQueueCap = 128;   // < 32 waiting + at most 64 pushed by one call
+constexpr int kRdfQueueCap = 288;   // < 32 waiting + at most 64 pushed by one call, 4 calls between two drain checks
+                                    // of the Newton-3 kernel's RDF loop (ljmd_force_sym.cuh)
 struct RdfCtx {
   uint2* q;            // this warp's queue
   unsigned int* hist;  // this warp's 256-bin histogram
   int n;               // queue length (warp-uniform)
+  // where the drain finds the float positions of a queued pair: entry (i - ioff, j - joff) reads pa[.x], pb[.y].
+  // k_force: the global array, offsets 0.  k_force_sym: shared-memory copies of the tile in registers and of the
+  // unit's j-records (a drain is two dependent loads per pair in the middle of the pair loop: from L2 they stall
+  // the warp for most of a microsecond, and dense units drain every few steps).
+  const float4* pa;
+  const float4* pb;
+  unsigned ioff, joff;
 };
 
 template <bool PERIODIC>
-__device__ __forceinline__ void rdf_exact_one(const uint2 e, const ForceParams& p, unsigned int* hist) {
-  const float4 a = p.posf[e.x & 0x7fffffffu], b = p.posf[e.y];
+__device__ __forceinline__ void rdf_exact_one(const uint2 e, const ForceParams& p, const RdfCtx& R) {
+  unsigned int* hist = R.hist;
+  const float4 a = R.pa[e.x & 0x7fffffffu], b = R.pb[e.y];
   float rx = __fsub_rn(a.x, b.x), ry = __fsub_rn(a.y, b.y), rz = __fsub_rn(a.z, b.z);   // MDSystem.cpp:269-271
   if (PERIODIC) { rx = image_exact(rx, p); ry = image_exact(ry, p); rz = image_exact(rz, p); }
   // MDSystem.cpp:279 in float, un-fused, left to right
@@ -207,14 +216,17 @@ __device__ __forceinline__ void rdf_drain(RdfCtx& R, const ForceParams& p, bool 
   __syncwarp();
   while (R.n >= 32 || (all && R.n > 0)) {
     const int cnt = min(32, R.n);
-    if (lane < cnt) rdf_exact_one<PERIODIC>(R.q[R.n - cnt + lane], p, R.hist);
+    if (lane < cnt) rdf_exact_one<PERIODIC>(R.q[R.n - cnt + lane], p, R);
     R.n -= cnt;
   }
   __syncwarp();
 }
 
-// c_lo / c_hi: this lane's lo / hi pair is inside the histogram range (by the fast r^2, with margin)
-template <bool PERIODIC>
+// c_lo / c_hi: this lane's lo / hi pair is inside the histogram range (by the fast r^2, with margin).
+// DRAIN = false: the caller checks the queue itself, once per several calls (every inlined drain is ~150
+// instructions: eight copies in an unrolled loop body overflowed the instruction cache, ncu `no_instruction` 0.98
+// stalled warps per issue).
+template <bool PERIODIC, bool DRAIN = true>
 __device__ __forceinline__ void rdf_push(RdfCtx& R, bool c_lo, bool c_hi, unsigned i_lo, unsigned i_hi, unsigned j,
                                          const ForceParams& p) {
   const unsigned m_lo = __ballot_sync(0xffffffffu, c_lo), m_hi = __ballot_sync(0xffffffffu, c_hi);
@@ -224,7 +236,7 @@ __device__ __forceinline__ void rdf_push(RdfCtx& R, bool c_lo, bool c_hi, unsign
   R.n += __popc(m_lo);
   if (c_hi) R.q[R.n + __popc(m_hi & lt)] = make_uint2(i_hi, j);
   R.n += __popc(m_hi);
-  if (R.n >= 32) rdf_drain<PERIODIC>(R, p, false);
+  if (DRAIN && R.n >= 32) rdf_drain<PERIODIC>(R, p, false);
 }
 
 // One pair of i-particles (two lanes of V).
@@ -279,7 +291,8 @@ __device__ __forceinline__ void pair_body(const uint4& uj, const PairI<V>& pi, P
   if (RDF) {
     // clamped duplicate lanes (v_* false) and the self pair never count
     rdf_push<PERIODIC>(R, r2s.x < p.cut_fast && pi.v_lo && !(DIAG && self_lo),
-                       r2s.y < p.cut_fast && pi.v_hi && !(DIAG && self_hi), pi.i_lo, pi.i_hi, jglobal, p);
+                       r2s.y < p.cut_fast && pi.v_hi && !(DIAG && self_hi), pi.i_lo - R.ioff, pi.i_hi - R.ioff,
+                       jglobal - R.joff, p);
   }
 }
 
@@ -433,6 +446,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force(const ForceParams p) {
   R.q = queues + (tid >> 5) * kRdfQueueCap;
   R.hist = hist + (tid >> 5) * kRdfBins;
   R.n = 0;
+  R.pa = R.pb = p.posf;
+  R.ioff = R.joff = 0u;
 
   for (int t = 0; t < ntiles; ++t) {
     if (tid == 0 && t + 1 < ntiles) issue(t + 1);

@@ -64,6 +64,8 @@ struct SymParams {
   int frames;      // 0: every chunk takes the fixed-point path (particle order not spatially sorted)
   float kunit;     // L / 2^32: fixed-point units -> sigma
   float far2;      // (R_far / kunit)^2: squared gap, in fixed-point units, from which a chunk may take the float path
+  float rdf2;      // (histogram range / kunit)^2 with margin: a chunk whose every record is farther than this from
+                   // the warp's box cannot hold an in-range pair and skips the RDF loop (FRAMES + RDF kernels)
 };
 
 // Units of a super-tile's band: tile t = 0..mi-1 owns blocks q in [t, t + h_t] counted from the super-tile's
@@ -303,8 +305,8 @@ __device__ __forceinline__ void pair_sym(const uint4& uj, const PairI<V>& pi, Pa
   if (RDF) {
     // the reference counts (i,j) and (j,i); its float sequence is odd in the separation, so both land in the
     // same bin: one queue entry with the "counts twice" bit (31) set
-    rdf_push<PERIODIC>(R, r2s.x < p.cut_fast && !(KILL && kill_lo), r2s.y < p.cut_fast && !(KILL && kill_hi),
-                       pi.i_lo | 0x80000000u, pi.i_hi | 0x80000000u, jglobal, p);
+    rdf_push<PERIODIC, false>(R, r2s.x < p.cut_fast && !(KILL && kill_lo), r2s.y < p.cut_fast && !(KILL && kill_hi),
+                       (pi.i_lo - R.ioff) | 0x80000000u, (pi.i_hi - R.ioff) | 0x80000000u, jglobal - R.joff, p);
   }
 }
 
@@ -321,19 +323,24 @@ __device__ __forceinline__ void pair_sym(const uint4& uj, const PairI<V>& pi, Pa
       uint4 rec = tu[min(jl, nj - 1)];                                                                           \
       const bool full = warp_all_valid && ((c << 5) + 32 <= nj);                                                 \
       bool fl = false;                                                                                           \
-      if (FRAMES && !(RU) && fr.ok && full) {                                                                    \
+      bool ru_chunk = (RU);   /* build the RDF for this chunk? */                                                \
+      if (FRAMES && fr.ok && full) {                                                                             \
         /* my record against the warp's box on the ring: can any pair of this chunk wrap?  is it far enough? */ \
         const int rx = (int)rec.x - fr.cx, ry = (int)rec.y - fr.cy, rz = (int)rec.z - fr.cz;                     \
         const unsigned axu = (unsigned)abs(rx), ayu = (unsigned)abs(ry), azu = (unsigned)abs(rz);                \
         const float gx = fmaxf(0.f, __int2float_rn((int)axu - fr.hx));                                           \
         const float gy = fmaxf(0.f, __int2float_rn((int)ayu - fr.hy));                                           \
         const float gz = fmaxf(0.f, __int2float_rn((int)azu - fr.hz));                                           \
-        const bool okj = axu < fr.limx && ayu < fr.limy && azu < fr.limz &&                                      \
-                         __fmaf_rn(gz, gz, __fmaf_rn(gy, gy, gx * gx)) >= sp.far2;                               \
-        fl = __all_sync(0xffffffffu, okj);                                                                       \
-        if (fl)                                                                                                  \
-          rec = make_uint4(__float_as_uint(__int2float_rn(rx) * sp.kunit), __float_as_uint(__int2float_rn(ry) * sp.kunit), \
-                           __float_as_uint(__int2float_rn(rz) * sp.kunit), 0u);                                  \
+        const float g2 = __fmaf_rn(gz, gz, __fmaf_rn(gy, gy, gx * gx));   /* squared gap record <-> box */        \
+        /* RDF: no record of the chunk within histogram range of the warp's box -> no pair can count */          \
+        if (RU) ru_chunk = __any_sync(0xffffffffu, g2 <= sp.rdf2);                                               \
+        if (!ru_chunk) {                                                                                         \
+          const bool okj = axu < fr.limx && ayu < fr.limy && azu < fr.limz && g2 >= sp.far2;                     \
+          fl = __all_sync(0xffffffffu, okj);                                                                     \
+          if (fl)                                                                                                \
+            rec = make_uint4(__float_as_uint(__int2float_rn(rx) * sp.kunit), __float_as_uint(__int2float_rn(ry) * sp.kunit), \
+                             __float_as_uint(__int2float_rn(rz) * sp.kunit), 0u);                                \
+        }                                                                                                        \
       }                                                                                                          \
       if (FRAMES && fl != cur_float) {                                                                           \
         fold_forces(cur_float ? 4.f : p.fscale);   /* the accumulators change units with the path */             \
@@ -357,14 +364,30 @@ __device__ __forceinline__ void pair_sym(const uint4& uj, const PairI<V>& pi, Pa
           rjy = __shfl_sync(0xffffffffu, rjy, nxt_lane);                                                         \
           rjz = __shfl_sync(0xffffffffu, rjz, nxt_lane);                                                         \
         }                                                                                                        \
+      } else if (full && (RU) && ru_chunk) {                                                                     \
+        /* two rotation steps per trip, ONE drain check: the loop body must stay inside the instruction cache */ \
+        _Pragma("unroll 1")                                                                                      \
+        for (int k = 0; k < 32; k += 2) {                                                                        \
+          _Pragma("unroll")                                                                                      \
+          for (int kk = 0; kk < 2; ++kk) {                                                                       \
+            const uint4 uj = sp_l[k + kk];                                                                       \
+            const unsigned jg = (unsigned)(j0 + (c << 5) + ((lane + k + kk) & 31));                              \
+            _Pragma("unroll")                                                                                    \
+            for (int q = 0; q < NPAIR; ++q)                                                                      \
+              pair_sym<V, PERIODIC, false, RU>(uj, pi[q], acc[q], false, false, rjx, rjy, rjz, p, jg, R);        \
+            rjx = __shfl_sync(0xffffffffu, rjx, nxt_lane);                                                       \
+            rjy = __shfl_sync(0xffffffffu, rjy, nxt_lane);                                                       \
+            rjz = __shfl_sync(0xffffffffu, rjz, nxt_lane);                                                       \
+          }                                                                                                      \
+          if (R.n >= 32) rdf_drain<PERIODIC>(R, p, false);                                                       \
+        }                                                                                                        \
       } else if (full) {                                                                                         \
         _Pragma("unroll UNROLLK")                                                                                \
         for (int k = 0; k < 32; ++k) {                                                                           \
           const uint4 uj = sp_l[k];                                                                              \
-          const unsigned jg = (unsigned)(j0 + (c << 5) + ((lane + k) & 31)); /* only live when RU */             \
           _Pragma("unroll")                                                                                      \
           for (int q = 0; q < NPAIR; ++q)                                                                        \
-            pair_sym<V, PERIODIC, false, RU>(uj, pi[q], acc[q], false, false, rjx, rjy, rjz, p, jg, R);          \
+            pair_sym<V, PERIODIC, false, false>(uj, pi[q], acc[q], false, false, rjx, rjy, rjz, p, 0u, R);       \
           rjx = __shfl_sync(0xffffffffu, rjx, nxt_lane);                                                         \
           rjy = __shfl_sync(0xffffffffu, rjy, nxt_lane);                                                         \
           rjz = __shfl_sync(0xffffffffu, rjz, nxt_lane);                                                         \
@@ -382,6 +405,7 @@ __device__ __forceinline__ void pair_sym(const uint4& uj, const PairI<V>& pi, Pa
           rjx = __shfl_sync(0xffffffffu, rjx, nxt_lane);                                                         \
           rjy = __shfl_sync(0xffffffffu, rjy, nxt_lane);                                                         \
           rjz = __shfl_sync(0xffffffffu, rjz, nxt_lane);                                                         \
+          if (RU) { if (R.n >= 32) rdf_drain<PERIODIC>(R, p, false); }                                           \
         }                                                                                                        \
       }                                                                                                          \
       /* the accumulators are home again; jl < BJ always.  12-byte entries: stride 3 words, conflict-free.       \
@@ -423,6 +447,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
   int* nitems_s = reinterpret_cast<int*>(tail + 16 + 8 * NW + kSymMaxItems * 8);   // [4]: item count
   unsigned int* hist = reinterpret_cast<unsigned int*>(tail + 32 + 8 * NW + kSymMaxItems * 8);         // [NW][256] (RDF)
   uint2* queues = reinterpret_cast<uint2*>(tail + 32 + 8 * NW + kSymMaxItems * 8 + NW * kRdfBins * 4);  // [NW][cap] (RDF)
+  // RDF: float positions of the unit's j-records (double-buffered like tile_u) and of the tile in registers
+  float4* tile_f = reinterpret_cast<float4*>(tail + 32 + 8 * NW + kSymMaxItems * 8 + NW * kRdfBins * 4 + NW * kRdfQueueCap * 8);  // [2][BJ]
+  float4* itile_f = tile_f + (size_t)2 * BJ;                                                                                       // [B]
 
   const int ibase0 = p.i_begin + blockIdx.x * sp.mi * B;   // first particle of the super-tile
   const int ntiles = min(sp.mi, (p.i_end - ibase0 + B - 1) / B);   // the rank's last super-tile may be short
@@ -465,8 +492,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
   auto issue = [&](int it, int st) {
     const int2 d = items[it];
     const uint32_t bytes = (uint32_t)(d.y & 1023) * 16u;
-    mbar_expect_tx(&bars[st], bytes);
+    mbar_expect_tx(&bars[st], RDF ? 2u * bytes : bytes);
     bulk_g2s(tile_u + (size_t)st * BJ, p.jrec + d.x, bytes, &bars[st]);
+    if (RDF) bulk_g2s(tile_f + (size_t)st * BJ, p.posf + d.x, bytes, &bars[st]);
   };
   if (nitems > 0 && tid == 0) issue(0, 0);
 
@@ -487,6 +515,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
   R.q = queues + warp * kRdfQueueCap;
   R.hist = hist + warp * kRdfBins;
   R.n = 0;
+  R.pa = itile_f; R.pb = tile_f;
+  R.ioff = R.joff = 0u;
   float* myslice = slices + (size_t)warp * BJ * 3;
   uint4* mystage = stage + warp * 64;
   double wsum = 0.;
@@ -550,11 +580,24 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
         if (sp.frames) make_warp_frame<V, NPAIR>(pi, sp.kunit, warp_all_valid, fr);
         else fr.ok = false;
       }
+      if (RDF) {
+        // the drains read the float positions of this warp's own i-particles: a copy in shared memory
+        // (the queue is empty here: it is flushed at the end of every unit)
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < NPAIR; ++q) {
+          itile_f[pi[q].i_lo - (unsigned)ibase] = p.posf[pi[q].i_lo];
+          itile_f[pi[q].i_hi - (unsigned)ibase] = p.posf[pi[q].i_hi];
+        }
+        __syncwarp();
+        R.ioff = (unsigned)ibase;
+      }
       if (RDF && sp.bbox != nullptr) { const int gI = ibase / B; my_lo = sp.bbox[2 * gI]; my_hi = sp.bbox[2 * gI + 1]; }
     }
     const int st = it & 1;
     mbar_wait(&bars[st], (uint32_t)((it >> 1) & 1));
     const uint4* tu = tile_u + (size_t)st * BJ;
+    if (RDF) { R.pb = tile_f + (size_t)st * BJ; R.joff = (unsigned)j0; }
     float wgt;
     if (diag) {
       // ---- diagonal block: ordered loop over its own particles, self pair excluded ----
@@ -573,7 +616,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
     } else {
       // ---- partner block: each unordered pair once, reaction accumulators travel with the rotating j ----
       wgt = 2.f;
-      if (RDF) {
+      if (RDF && FRAMES) {
+        // sorted records: the per-chunk test against the warp's own box (tighter than two 512-block boxes) decides
+        LJMD_SYM_PARTNER_CHUNKS(true)
+      } else if (RDF) {
         // bounding boxes of the two blocks farther apart than the histogram range: no pair of this unit can
         // count, run the plain loop (uniform: every thread of the CTA sees the same two boxes)
         bool near = true;
@@ -601,6 +647,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
       }
       acc[q].s6 = acc[q].w = acc[q].fx = acc[q].fy = acc[q].fz = zero2;
     }
+    if (RDF) rdf_drain<PERIODIC>(R, p, true);   // queued pairs point into this unit's stage: flush before it is refilled
     __syncthreads();  // slices complete; stage st free for the load after next
     if (!diag) {
       // reaction of this unit: sum the warps' slices in warp order, add to the window accumulator
@@ -653,7 +700,7 @@ inline size_t force_sym_smem_bytes(bool rdf, int bj, int threads, int mju) {
   // j-chunk double buffer, per-warp rotation stages, per-warp reaction slices (12 B), window accumulator (12 B),
   // barriers, block-sum scratch, work list + its length, RDF scratch
   return (size_t)2 * bj * 16 + (size_t)nw * 64 * 16 + (size_t)nw * bj * 12 + (size_t)mju * bj * 12 + 16 + 8 * nw +
-         kSymMaxItems * 8 + 16 + (rdf ? rdf_smem_bytes(threads) : 0);
+         kSymMaxItems * 8 + 16 + (rdf ? rdf_smem_bytes(threads) + (size_t)2 * bj * 16 + (size_t)threads * 4 * 16 : 0);
 }
 
 }  // namespace ljmd

@@ -250,6 +250,7 @@ static void run_sym(const Problem& pb, const char* tag, int reps, int bj, std::v
   if (g_win_shift >= 0) sp.win_shift = std::min(nwin - 1, g_win_shift);
   sp.frames = FRAMES ? g_frames : 0; sp.kunit = (float)(pb.L / 4294967296.0);
   sp.far2 = (float)((g_rfar * 4294967296.0 / pb.L) * (g_rfar * 4294967296.0 / pb.L));
+  sp.rdf2 = (float)((25.6 * 1.002 + 1e-3) * k2 * k2);
   const size_t rp_elems = (size_t)nsup * nwin * mju * bj;
   if ((size_t)nwin * pb.N > pb.fpart_elems || rp_elems > pb.rpart_elems) {
     printf("sym   %-44s skipped: needs %zu + %zu records of scratch\n", tag, (size_t)nwin * pb.N, rp_elems);
