@@ -82,6 +82,11 @@ int ljmd_create(ljmd_system** out, int N, double rho, double T0, int canonical, 
  * Host arrays keep their full length: every device reads and writes its own shard of them.  ndev == 1 is
  * ljmd_create.  Fails when the devices cannot map each other's memory or N is too small to give every device a
  * 512-particle block.  New functionality: the reference is single-device.
+ * Environment LJMD_SHARE_DEVICES=1 allows a device to be listed more than once (several ranks on one GPU, each on
+ * its own stream): a diagnostic mode that runs the whole sharded data path on a box with fewer GPUs than ranks —
+ * the ranks wait for each other inside kernels, so set CUDA_DEVICE_MAX_CONNECTIONS >= the rank count (one hardware
+ * queue per rank's stream) and CUDA_MODULE_LOADING=EAGER (a lazily loaded kernel's first launch would synchronise
+ * the context behind a peer's spinning barrier) before CUDA starts.
  */
 int ljmd_create_multi(ljmd_system** out, int N, double rho, double T0, int canonical, int bc,
                       float rdf_dr2, const int* devices, int ndev);

@@ -2150,15 +2150,21 @@ extern "C" int ljmd_create_multi(ljmd_system** out, int N, double rho, double T0
     cudaGetLastError();
     return set_err(LJMD_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
   }
+  // LJMD_SHARE_DEVICES=1: a device may be listed more than once — several ranks of the sharded system then run on
+  // one GPU, each on its own stream (a diagnostic mode: the whole multi-rank data path — shard plan, windows,
+  // barriers, reaction exchange — on a box with fewer GPUs than ranks; no speed-up, the ranks share the SMs).
+  const char* share_env = std::getenv("LJMD_SHARE_DEVICES");
+  const bool share = share_env && share_env[0] == '1';
   for (int a = 0; a < ndev; ++a) {
     if (devices[a] < 0 || devices[a] >= visible) return set_err(LJMD_ERR_ARG, "device %d out of range (%d visible)", devices[a], visible);
     for (int b = 0; b < a; ++b)
-      if (devices[a] == devices[b]) return set_err(LJMD_ERR_ARG, "device %d listed twice", devices[a]);
+      if (devices[a] == devices[b] && !share)
+        return set_err(LJMD_ERR_ARG, "device %d listed twice (LJMD_SHARE_DEVICES=1 allows it)", devices[a]);
   }
   for (int a = 0; a < ndev; ++a)
     for (int b = 0; b < ndev; ++b) {
       int ok = 1;
-      if (a != b) CU(cudaDeviceCanAccessPeer(&ok, devices[a], devices[b]));
+      if (devices[a] != devices[b]) CU(cudaDeviceCanAccessPeer(&ok, devices[a], devices[b]));
       if (!ok) return set_err(LJMD_ERR_CUDA, "device %d cannot map the memory of device %d (no NVLink / PCIe peer access)", devices[a], devices[b]);
     }
   MultiCtl* c = new (std::nothrow) MultiCtl();
@@ -2180,7 +2186,7 @@ extern "C" int ljmd_create_multi(ljmd_system** out, int N, double rho, double T0
     // wire the fabric: every device maps every peer, the windows are plain pointers in this address space
     rc = multi_run(c, [&](ljmd_system* sub, int r) {
       for (int q = 0; q < ndev; ++q) {
-        if (q == r) continue;
+        if (c->dev[q] == c->dev[r]) continue;   // itself, or a rank sharing this device
         const cudaError_t e = cudaDeviceEnablePeerAccess(c->dev[q], 0);
         if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
           return set_err(LJMD_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", c->dev[q], cudaGetErrorString(e));

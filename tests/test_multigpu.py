@@ -143,7 +143,36 @@ def test_device_init_is_identical_on_any_gpu_count(pkg, gpu_lib, world):
     assert abs(ps1 - ps2) <= 1e-9 * max(1.0, abs(ps1))
 
 
-def test_multi_handle_argument_errors(pkg, gpu_lib):
+# ------------------------------------------------------------------ several ranks on ONE device
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("case", [CASES[0], CASES[2], ("evn_hardwall_w", 0, 1, 20011, 0.05)], ids=lambda c: c[0])
+def test_ranks_sharing_one_device_match_single_gpu(pkg, gpu_lib, tmp_path, world, case):
+    """LJMD_SHARE_DEVICES=1 lets ljmd_create_multi put several ranks on one GPU: the complete sharded data path —
+    shard plan, peer windows, barriers, reaction exchange, shard-only host I/O — runs at world 2, 4 and 8 on a box
+    with a single device, against the plain single-GPU handle."""
+    name, canonical, bc, N, rho = case
+    nblk = -(-N // 512)
+    if (world - 1) * -(-nblk // world) >= nblk:
+        pytest.skip("shards are whole 512-particle blocks: the last rank would get none")
+    out = os.path.join(tmp_path, "shared.npz")
+    # ranks that share a device wait for each other INSIDE kernels (the barrier), so their kernels must be able to
+    # run side by side: one hardware queue per stream, and no lazy module loading (the first launch of a kernel would
+    # synchronise the context behind a peer's spinning barrier)
+    env = dict(os.environ, LJMD_SHARE_DEVICES="1", CUDA_DEVICE_MAX_CONNECTIONS="32", CUDA_MODULE_LOADING="EAGER")
+    run = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "shared_device_worker.py"), out, str(world),
+                          str(canonical), str(bc), str(N), str(rho)], capture_output=True, text=True, timeout=600, env=env)
+    assert run.returncode == 0, run.stderr[-3000:]
+    z = np.load(out)
+    got = {k: z[k] for k in z.files}
+    compare_with_single_gpu(pkg, got, canonical, bc, N, rho)
+    with pkg.ljmd.LJSystem(N, T0=1.0, rho=rho, canonical=canonical, bc=bc) as one:
+        one.init_state(77)
+        p1, v1, _ = one.get_state()
+    assert np.array_equal(got["init_pos"], p1) and np.array_equal(got["init_vel"], v1)
+
+
+def test_multi_handle_argument_errors(pkg, gpu_lib, monkeypatch):
+    monkeypatch.delenv("LJMD_SHARE_DEVICES", raising=False)
     with pytest.raises(pkg.ljmd.LJMDError):
         pkg.ljmd.LJSystem(4096, devices=[0, 0])                       # a device listed twice
     with pytest.raises(pkg.ljmd.LJMDError):
