@@ -451,11 +451,19 @@ def main_ours(args, pkg):
             i2 = s2.launch_info()
             pp = float(c2["N"]) * (c2["N"] - 1)
             r2 = force_roofline(c2, i2, world, t2["force_ms"], t2["dev_ms"], st, fp32_nominal, fp32_measured, clk)
+            g2, d2 = s2.last_gather_timing(), s2.last_reduce_timing()
+            g2_ms = max_over_ranks(g2["gather_ms"] / max(1, g2["launches"]))
+            d2_ms = max_over_ranks(d2["reduce_ms"] / max(1, d2["launches"])) if world > 1 else 0.0
             sweep[name] = {"workload": describe(name, c2, world)["workload"], "steps": st, "warmup": 3,
                            "ms_per_step": t2["dev_ms"] / st, "value": pp * st / (t2["dev_ms"] * 1e-3), "unit": "pairs/s",
                            "md_steps_per_s": st / (t2["dev_ms"] * 1e-3), "force_kernel_ms": t2["force_ms"],
                            "roofline_frac": r2["frac"], "frac_of_measured_peak": r2["frac_of_measured_peak"],
-                           "force_share_of_step": r2["kernel_share_of_step"], "launch": i2}
+                           "force_share_of_step": r2["kernel_share_of_step"],
+                           # where the rest of the step goes (per launch, max over ranks): k_gather, the sharded
+                           # runs' k_reduce_reaction, and what is left (drift/finish kernels, barriers, launch gaps)
+                           "gather_kernel_ms": g2_ms, "reduce_reaction_kernel_ms": d2_ms,
+                           "other_ms_per_step": t2["dev_ms"] / st - t2["force_ms"] - g2_ms - d2_ms,
+                           "launch": i2}
             s2.close()
 
     if rank == 0:

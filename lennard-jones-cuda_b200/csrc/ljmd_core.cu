@@ -883,6 +883,10 @@ static int create_impl(ljmd_system** out, int N, double rho_or_negL, double T0, 
   while (s->gather_shift < 3 && ((long long)s->nloc << s->gather_shift) < 2LL * kStepThreads * s->num_sms &&
          (2 << s->gather_shift) * 2 <= s->nsplit + (s->use_sym ? (s->n_super + 1) / 2 : 0))
     s->gather_shift += 1;
+  if (const char* e = getenv("LJMD_GATHER_SHIFT")) {   // tuning override: 2^shift lanes per particle, 0..3
+    const int v = atoi(e);
+    if (v >= 0 && v <= 3) s->gather_shift = v;
+  }
   CUC(cudaMalloc(&s->part, (size_t)2 * (gather_grid(s) + 1) * sizeof(double)));
   CUC(cudaMalloc(&s->counter, sizeof(unsigned int)));
   CUC(cudaMalloc(&s->velh, 65536 * sizeof(unsigned int)));

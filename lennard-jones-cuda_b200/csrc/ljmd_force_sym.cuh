@@ -586,8 +586,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_force_sym(const SymParams sp)
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < NPAIR; ++q) {
-          itile_f[pi[q].i_lo - (unsigned)ibase] = p.posf[pi[q].i_lo];
-          itile_f[pi[q].i_hi - (unsigned)ibase] = p.posf[pi[q].i_hi];
+          // (clamped duplicates of a ragged last tile never queue a pair; they must not touch the entry of the
+          // particle they duplicate either: it belongs to another warp, which may be reading it)
+          if (pi[q].v_lo) itile_f[pi[q].i_lo - (unsigned)ibase] = p.posf[pi[q].i_lo];
+          if (pi[q].v_hi) itile_f[pi[q].i_hi - (unsigned)ibase] = p.posf[pi[q].i_hi];
         }
         __syncwarp();
         R.ioff = (unsigned)ibase;

@@ -559,6 +559,30 @@ def test_full_size_forces_subsample(pkg, oracle, gpu_lib, kernel, config):
         assert err_w2 <= 2 * SCALAR_TOL
 
 
+def test_twice_the_benchmark_size_ragged(pkg, oracle, gpu_lib):
+    """Beyond the largest BASELINE configuration: N = 2 * 1 048 576 + 777 (a ragged last block, 4 098 blocks of 512:
+    258 windows of partial-force rows, 8.7 GB of them) periodic, one evaluation and one step under the Newton-3
+    kernel; 256+ sampled particles (the ragged tail included) against the FP64 arbiter over all N partners."""
+    N, rho, T = 2 * 1048576 + 777, 0.3, 1.0
+    pos = pkg.snapshots.lattice(N, rho, jitter=0.05, seed=11)
+    vel = pkg.snapshots.velocities(N, T, seed=11)
+    with pkg.ljmd.LJSystem(N, T0=T, rho=rho, canonical=True, bc=0) as s:
+        assert s.launch_info()["newton3"]
+        s.set_state(pos, vel)
+        _, _, frc = s.get_state()
+        sc = s.scalars()
+        idx_tail = np.arange(N - 40, N, dtype=np.int32)
+        f64, fterm, _, _ = oracle.forces_f64_subset(pos, s.L, 0, idx_tail)
+        err_tail = (np.abs(frc[idx_tail, :3].astype(np.float64) - f64).max(axis=1) / fterm).max()
+        err_f, _, n = subsample_force_error(oracle, pos, s.L, 0, frc, nsample=256)
+        assert max(err_f, err_tail) <= FORCE_TOL, f"N={N}: force error {err_f:.3e} ({n} sampled), tail {err_tail:.3e}"
+        f = frc[:, :3].astype(np.float64)
+        assert np.abs(f.sum(axis=0)).max() <= 3e-6 * np.abs(f).sum()     # Newton's third law over 2.2e12 pairs
+        assert abs(2.0 * frc[:, 3].astype(np.float64).sum() - sc["V"]) <= 2e-6 * np.abs(frc[:, 3]).astype(np.float64).sum()
+        s.step(0.004, 1)
+        assert abs(s.scalars()["T"] - T) <= 1e-3                         # TVN pins the kinetic temperature
+
+
 # ------------------------------------------------------------------ full-size properties (no O(N^2) oracle)
 def test_full_size_properties_c3(pkg, gpu_lib):
     """N = 65 536 solid (C3): Newton's third law, RDF against the k-d-tree restatement (bit-exact),
