@@ -104,29 +104,51 @@ __host__ __device__ inline int partner_count(int g, int n) {
 
 // Sum of the reaction blocks that hold contributions for global particle j (block J = j / 512).  Super-tile a of
 // this rank (first global block I0 = blk0 + a * mi) accumulated the reaction on J in band unit
-// u = ((J - I0) mod n) * cpb + jj / bj when u lies inside its band (ljmd_force_sym.cuh); every entry of a band is
-// written on every launch (zeros included).  Walks the super-tiles in ascending order (fixed order:
-// deterministic), several loads in flight.
+// u = ((J - I0) mod n) * cpb + jj / bj when u lies inside its band, q = (J - I0) mod n <= qmax
+// (ljmd_force_sym.cuh); every entry of a band is written on every launch (zeros included).  With D = (J - blk0)
+// mod n the covering super-tiles are two runs of t: t * mi <= D with q = D - t * mi <= qmax, and t * mi > D with
+// q = D + n - t * mi <= qmax.  Both are walked in ascending t (fixed order: deterministic; the same order and the
+// same bits as a predicated walk over every t), four independent loads in flight: with the coverage test inside
+// the loop every load sat behind its own branch and its add behind the load — 32 serial L2/DRAM latencies per
+// thread, a third of k_gather's stall samples at N = 65 536 (profiles/r02_gather_kernel_ncu_C3.md).
+// A super-tile's windows lie back to back, rp_stride = mju * bj records each, so band unit u of super-tile t
+// starts at record (t * nwin * mju + u) * bj whatever window it is in: no division in the loop.
 __device__ __forceinline__ float4 reaction_sum(const StepParams& p, int j, int first = 0, int stride = 1) {
   const int J = j / kBlockParticles, jj = j - J * kBlockParticles;
-  const int n = p.nblk;
+  const int n = p.nblk, mi = p.sym_mi;
   const int hmax = (n & 1) ? (n - 1) / 2 : n / 2;
   const int cpb = kBlockParticles / p.sym_bj;
-  int qmax = p.sym_mi - 1 + hmax;
+  int qmax = mi - 1 + hmax;
   if (qmax > n - 1) qmax = n - 1;
   const int c = jj / p.sym_bj, jr = jj - c * p.sym_bj;
+  const size_t band = (size_t)p.sym_nwin * p.sym_mju;
+  const float4* base = p.rpart + (size_t)c * p.sym_bj + jr;
+  int D = J - p.blk0;
+  if (D < 0) D += n;
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-  for (int t = first; t < p.n_super; t += stride) {   // (first, stride): this lane's share when several lanes split a particle
-    int q = J - (p.blk0 + t * p.sym_mi);
-    if (q < 0) q += n;
-    if (q <= qmax) {
-      const int u = q * cpb + c;
-      const int w = u / p.sym_mju;
-      const float4 g = p.rpart[((size_t)t * p.sym_nwin + w) * p.rp_stride + (size_t)(u - w * p.sym_mju) * p.sym_bj + jr];
-      a.x += g.x; a.y += g.y; a.z += g.z;
+  // t in [lo, hi] with t = first (mod stride) — this lane's share when several lanes split a particle (stride is a
+  // power of two); q = Dq - t * mi
+  auto walk = [&](int lo, int hi, int Dq) {
+    // (a short last batch loads under a predicate and adds zeros: with 8 lanes per particle a lane's whole share
+    // is one partial batch, which must not fall back to one load at a time)
+    for (int t = lo + ((first - lo) & (stride - 1)); t <= hi; t += 4 * stride) {
+      float4 g[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        // load unconditionally from a clamped (valid) address, select afterwards: a guarded load makes ptxas
+        // put every load behind a branch again
+        const int tt = t + m * stride, tc = min(tt, hi);
+        const float4 v = base[((size_t)tc * band + (size_t)((Dq - tc * mi) * cpb)) * p.sym_bj];
+        const bool on = tt <= hi;
+        g[m] = make_float4(on ? v.x : 0.f, on ? v.y : 0.f, on ? v.z : 0.f, 0.f);
+      }
+#pragma unroll
+      for (int m = 0; m < 4; ++m) { a.x += g[m].x; a.y += g[m].y; a.z += g[m].z; }
     }
-  }
+  };
+  const int tD = D / mi;
+  walk(D > qmax ? (D - qmax + mi - 1) / mi : 0, min(p.n_super - 1, tD), D);
+  walk(max(tD + 1, (D + n - qmax + mi - 1) / mi), p.n_super - 1, D + n);
   return a;
 }
 
@@ -242,6 +264,21 @@ __global__ void __launch_bounds__(kStepThreads) k_prepare(const StepParams p) {
   publish_position(p, record_of(p, il), p.pos[il]);
 }
 
+// sum_k a[tid + k * kStepThreads] in ascending k, loads batched eight deep (L2: ld.global.cg)
+__device__ __forceinline__ double strided_sum_l2(const double* a, int n) {
+  double t = 0.;
+  int k = threadIdx.x;
+  for (; k + 7 * kStepThreads < n; k += 8 * kStepThreads) {
+    double v[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) v[m] = __ldcg(a + k + m * kStepThreads);
+#pragma unroll
+    for (int m = 0; m < 8; ++m) t += v[m];
+  }
+  for (; k < n; k += kStepThreads) t += __ldcg(a + k);
+  return t;
+}
+
 // Deterministic two-value block reduction + last-block final sum over all blocks.
 // Returns true in thread 0 of the last block after sc->sums[ia], sc->sums[ib] are written.
 __device__ __forceinline__ bool reduce_two(double a, double b, const StepParams& p, int ia, int ib,
@@ -270,13 +307,14 @@ __device__ __forceinline__ bool reduce_two(double a, double b, const StepParams&
   if (!is_last) return false;
   __threadfence();
   // last block: fixed-order sums (deterministic run to run)
+  // (the partials were written by other CTAs of this launch / by the force kernel: L2 loads, never L1.  Eight
+  // loads go out before the first add: a strided walk of up to 16 640 force-block sums with one dependent
+  // load per add cost the last block 0.6 us per trip, 20 us of a 73 us k_gather at N = 65 536; the order of the
+  // additions — and with it every bit of the sums — is what it was.)
   double ta = 0., tb = 0., tw = 0.;
-  const volatile double* part = p.part;
-  for (int k = threadIdx.x; k < (int)gridDim.x; k += kStepThreads) { ta += part[k]; tb += part[gridDim.x + k]; }
-  if (also_force_blocks) {
-    const volatile double* bw = p.blockW;
-    for (int k = threadIdx.x; k < p.nforce_blocks; k += kStepThreads) tw += bw[k];
-  }
+  ta = strided_sum_l2(p.part, (int)gridDim.x);
+  tb = strided_sum_l2(p.part + gridDim.x, (int)gridDim.x);
+  if (also_force_blocks) tw = strided_sum_l2(p.blockW, p.nforce_blocks);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     ta += __shfl_xor_sync(0xffffffffu, ta, o);
@@ -339,12 +377,31 @@ __global__ void __launch_bounds__(kStepThreads) k_gather(const StepParams p, int
   int il = rl;                                             // il: the particle it belongs to (state arrays)
   double pe = 0., q = 0.;
   float4 f = make_float4(0.f, 0.f, 0.f, 0.f), rr = f;
+  // the state-array reads of the tail (lane 0 of a group) go out first: two dependent latencies (order -> vel,
+  // force, posA) that would otherwise follow the row sums
+  float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), fo0 = v0, x0 = v0;
   if (rl < p.nloc) {
     if (p.order) il = p.order[rl];
-#pragma unroll 8   // rows are independent loads: keep several in flight (up to ~130 rows with fine splits)
-    for (int s = r; s < p.nsplit; s += R) {
-      const float4 g = p.fpart[(size_t)s * p.ilocal_cap + rl];
-      f.x += g.x; f.y += g.y; f.z += g.z; f.w += g.w;
+    if (r == 0) {
+      v0 = p.vel[il];
+      if (MODE == GATHER_TVN) fo0 = p.force[il];
+      if (MODE == GATHER_EVN) x0 = p.posA[rec];
+    }
+    // rows are independent loads (up to ~130 rows with fine splits): eight in flight, added in row order
+    {
+      const float4* row = p.fpart + rl;
+      const size_t cap = (size_t)p.ilocal_cap;
+      for (int s = r; s < p.nsplit; s += 8 * R) {   // (a short last batch: predicated loads, zeros added)
+        float4 g[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          const int sm = s + m * R;
+          g[m] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (sm < p.nsplit) g[m] = row[(size_t)sm * cap];
+        }
+#pragma unroll
+        for (int m = 0; m < 8; ++m) { f.x += g[m].x; f.y += g[m].y; f.z += g[m].z; f.w += g[m].w; }
+      }
     }
     // Newton-3 kernel, one GPU: the reaction of every pair this particle was the j of
     if (p.use_sym && p.world == 1) rr = reaction_sum(p, rec, r, R);
@@ -372,7 +429,7 @@ __global__ void __launch_bounds__(kStepThreads) k_gather(const StepParams p, int
       f.x += rr.x; f.y += rr.y; f.z += rr.z;
     }
     pe = (double)f.w;
-    float4 v = p.vel[il];
+    float4 v = v0;
     if (MODE == GATHER_EVAL) {
       p.force[il] = f;
       q = (double)sq3(v.x, v.y, v.z) * 0.5;                 // :334
@@ -381,14 +438,14 @@ __global__ void __launch_bounds__(kStepThreads) k_gather(const StepParams p, int
       v.x = kick1(v.x, f.x, p.dt);
       v.y = kick1(v.y, f.y, p.dt);
       v.z = kick1(v.z, f.z, p.dt);
-      float4 x = p.posA[rec];
+      float4 x = x0;
       apply_bc(x, v, p.L, p.bc);
       p.pos[il] = x;
       q = (double)sq3(v.x, v.y, v.z) * 0.5;
       if (FUSE) fused_next_drift(p, rec, x, v, f, false);
       p.vel[il] = v;
     } else {
-      const float4 fo = p.force[il];
+      const float4 fo = fo0;
       p.force[il] = f;
       float4 tf;
       tf.x = __fadd_rn(__fmul_rn(0.5f, fo.x), __fmul_rn(0.5f, f.x));   // :477-479,486-488

@@ -173,13 +173,40 @@ def test_newton3_super_tiles_cover_every_block_pair_once(pkg, N, world, sms):
                 if p["i_end"] == p["i_begin"]:
                     continue
                 qmax = min(g["mi"] - 1 + hmax, n - 1)
-                for t in range(g["n_super"]):
-                    q = (J - (g["blk0"] + t * g["mi"])) % n
-                    if q <= qmax:
-                        u = q * cpb + c
-                        w = u // g["mju"]
-                        found |= racc[(r, t, w, u - w * g["mju"])]       # KeyError = the kernel never writes it
+                covering = [(t, (J - (g["blk0"] + t * g["mi"])) % n) for t in range(g["n_super"])]
+                covering = [(t, q) for t, q in covering if q <= qmax]
+                # reaction_sum walks two runs of t instead of testing every t: the same (t, q), in the same order,
+                # also when 2, 4 or 8 lanes split a particle's super-tiles (t = first mod stride)
+                for stride in (1, 2, 4, 8):
+                    walked = []
+                    for first in range(stride):
+                        walked.append(_reaction_walk(J, g["blk0"], n, g["mi"], qmax, g["n_super"], first, stride))
+                        assert walked[-1] == [(t, q) for t, q in covering if t % stride == first]
+                for t, q in covering:
+                    u = q * cpb + c
+                    w = u // g["mju"]
+                    # the record offset without the window: windows of a super-tile lie back to back
+                    assert (t * g["nwin"] + w) * g["mju"] + (u - w * g["mju"]) == t * g["nwin"] * g["mju"] + u
+                    found |= racc[(r, t, w, u - w * g["mju"])]       # KeyError = the kernel never writes it
             assert found == {(I, J, c) for I in range(n) if I != J and (I, J) in done}
+
+
+def _reaction_walk(J, blk0, n, mi, qmax, n_super, first, stride):
+    """The (t, q) sequence of reaction_sum() in csrc/ljmd_step.cuh, line by line."""
+    D = J - blk0
+    if D < 0:
+        D += n
+    out = []
+
+    def walk(lo, hi, Dq):
+        t = lo + ((first - lo) & (stride - 1))
+        while t <= hi:
+            out.append((t, Dq - t * mi))
+            t += stride
+    tD = D // mi
+    walk((D - qmax + mi - 1) // mi if D > qmax else 0, min(n_super - 1, tD), D)
+    walk(max(tD + 1, (D + n - qmax + mi - 1) // mi), n_super - 1, D + n)
+    return out
 
 
 def _emulate_image(d, L, thr1, thr2):
