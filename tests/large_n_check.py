@@ -1,6 +1,6 @@
 """One-off check beyond the tested sizes: one force evaluation at N = 4 194 304 and N = 8 388 608 (periodic,
 rho* = 0.3) and the FP64 subsample arbiter on 128 particles; prints the kernel family the library chose, the time
-of the evaluation and the worst force error.  usage: python tools/large_n_check.py [N ...]"""
+of the evaluation and the worst force error.  usage: python tests/large_n_check.py [N ...]"""
 import os
 import sys
 import time
@@ -8,7 +8,7 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np  # noqa: E402
 from ljpkg import load  # noqa: E402
-from oracle.oracle import Oracle  # noqa: E402  (a tool, not the product: the arbiter is the checker here)
+from oracle.oracle import Oracle  # noqa: E402  (test infrastructure: the arbiter is the checker here)
 
 pkg, o = load(), Oracle()
 for N in [int(a) for a in sys.argv[1:]] or [4194304, 8388608]:
