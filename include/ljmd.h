@@ -86,7 +86,7 @@ int ljmd_create(ljmd_system** out, int N, double rho, double T0, int canonical, 
  * its own stream): a diagnostic mode that runs the whole sharded data path on a box with fewer GPUs than ranks —
  * the ranks wait for each other inside kernels, so set CUDA_DEVICE_MAX_CONNECTIONS >= the rank count (one hardware
  * queue per rank's stream) and CUDA_MODULE_LOADING=EAGER (a lazily loaded kernel's first launch would synchronise
- * the context behind a peer's spinning barrier) before CUDA starts.
+ * the context behind a peer's spinning barrier) before CUDA starts; without the latter the call fails with a message.
  */
 int ljmd_create_multi(ljmd_system** out, int N, double rho, double T0, int canonical, int bc,
                       float rdf_dr2, const int* devices, int ndev);

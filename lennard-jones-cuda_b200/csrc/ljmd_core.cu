@@ -2165,6 +2165,17 @@ extern "C" int ljmd_create_multi(ljmd_system** out, int N, double rho, double T0
       if (devices[a] == devices[b] && !share)
         return set_err(LJMD_ERR_ARG, "device %d listed twice (LJMD_SHARE_DEVICES=1 allows it)", devices[a]);
   }
+  bool shared_any = false;
+  for (int a = 0; a < ndev; ++a)
+    for (int b = 0; b < a; ++b) shared_any = shared_any || devices[a] == devices[b];
+  if (shared_any) {
+    // ranks on one device wait for each other inside kernels: a lazily loaded kernel's first launch would
+    // synchronise the context behind a peer's spinning barrier and the step would end in the barrier's watchdog
+    const char* ml = std::getenv("CUDA_MODULE_LOADING");
+    if (!ml || strcmp(ml, "EAGER") != 0)
+      return set_err(LJMD_ERR_ARG, "ranks sharing a device need CUDA_MODULE_LOADING=EAGER in the environment before "
+                                   "CUDA starts (and CUDA_DEVICE_MAX_CONNECTIONS >= %d)", ndev);
+  }
   for (int a = 0; a < ndev; ++a)
     for (int b = 0; b < ndev; ++b) {
       int ok = 1;

@@ -177,6 +177,11 @@ def test_multi_handle_argument_errors(pkg, gpu_lib, monkeypatch):
         pkg.ljmd.LJSystem(4096, devices=[0, 0])                       # a device listed twice
     with pytest.raises(pkg.ljmd.LJMDError):
         pkg.ljmd.LJSystem(4096, devices=[0, 999])                     # no such device
+    monkeypatch.setenv("LJMD_SHARE_DEVICES", "1")
+    if os.environ.get("CUDA_MODULE_LOADING") != "EAGER":
+        with pytest.raises(pkg.ljmd.LJMDError, match="CUDA_MODULE_LOADING=EAGER"):
+            pkg.ljmd.LJSystem(4096, devices=[0, 0])                   # sharing needs eager module loading: say so at once
+    monkeypatch.delenv("LJMD_SHARE_DEVICES")
     with pkg.ljmd.LJSystem(2048, T0=1.0, rho=0.5, devices=[0]) as s:  # one device: plain ljmd_create
         assert s.launch_info()["world"] == 1
     if gpu_lib.ljmd_device_count() >= 2:
