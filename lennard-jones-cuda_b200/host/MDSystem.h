@@ -7,9 +7,13 @@
 //  * there is no CPU backend: `useCUDA` is accepted and ignored, construction fails loudly without a GPU;
 //  * `NdNdr2` is refreshed when RDF() is called (the histogram is rebuilt lazily on the device from the
 //    positions of the last force evaluation) instead of on every Integrate();
-//  * `Pshear` is not computed (the reference's own GPU path never sets it either, MDSystem.cpp:240-251);
-//  * initial velocities come from a seeded std::mt19937_64 (env LJMD_SEED, default time-seeded like the
-//    reference's MTRand), so `rangen` / `m_MaxwellGenerator` members are not exposed.
+//  * `Pshear` is 0 unless LJMD_PSHEAR=1 is set (then every Integrate() also evaluates ljmd_get_pshear: the
+//    reference's CPU-path formula, MDSystem.cpp:299,309,335,353, in one extra all-pairs pass; the reference's own
+//    GPU path never sets it, MDSystem.cpp:240-251);
+//  * initial conditions are sampled on the device (ljmd_init_state: the reference's lattice, seeded Philox
+//    velocities; env LJMD_SEED, default time-seeded like the reference's MTRand; LJMD_HOST_INIT=1 keeps a host
+//    sampler on std::mt19937_64), so `rangen` / `m_MaxwellGenerator` members are not exposed;
+//  * `m_config.numGPUs` (new, defaulted) / env LJMD_DEVICES shard the system over several GPUs.
 #ifndef mdsystem_h
 #define mdsystem_h
 // Callers of the reference header also get these through its includes and rely on them (printf, pow, ...).
@@ -47,7 +51,7 @@ class MDSystem {
 
   // total energy, instant temperature, kinetic energy, potential energy, pressure
   double U, T, K, V, P;
-  double Pshear;  // not computed (0)
+  double Pshear;  // 0 unless LJMD_PSHEAR=1 (see above)
   bool CUDAInit;
 
   // host mirrors, float[4N] each, refreshed by every method that changes them
