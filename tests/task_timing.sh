@@ -1,6 +1,6 @@
 #!/bin/bash
 # Wall time of the fluctuation driver: device-resident CLI (tasks/bin) vs the reference's driver source on the
-# MDSystem class (oracle/_ref, one upload + download per step).  Usage: tools/task_timing.sh [N] [rho] [steps]
+# MDSystem class (oracle/_ref, one upload + download per step).  Usage: tests/task_timing.sh [N] [rho] [steps]
 N=${1:-400}; RHO=${2:-0.05}; STEPS=${3:-2000}
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 W=$(mktemp -d)
